@@ -1,0 +1,165 @@
+/*
+ * tonga_b200.h -- C ABI of libtonga_b200.so: the B200 (sm_100a) implementation of the per-iteration forward
+ * model + likelihood + proposal loop of Geronimorz/MCMC-in-Tonga's reversible-jump t* tomography.
+ *
+ * The reference has NO FFI today: its boundary is a set of Julia top-level functions made global by
+ * `@everywhere include(...)` (main_inversion.jl:4-9).  A drop-in replacement is a .jl file included after
+ * MCsub.jl / TD_inversion_function.jl that re-defines those methods and forwards to `ccall` on the entry
+ * points below (mcmc-in-tonga_b200/julia/TongaB200.jl; binding shown in INTEGRATION.md).  Each entry point cites
+ * the reference interface it replaces (file:line relative to the reference repo).
+ *
+ * Conventions
+ *   - plain C types only; every host pointer is caller-owned and is NOT retained after the call returns
+ *     (the library copies at create time); outputs go to caller-allocated buffers.
+ *   - return value: 0 = TONGA_OK, negative = error class; message via tonga_last_error() (thread local).
+ *     No C++ exception crosses the ABI.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with TONGA_ERR_CUDA.
+ *   - nucleus / ray / point indices are 0-based at the ABI (the Julia shim converts).
+ *   - "cells" arrays are SoA per model: [model][4][Kcap] doubles = x[Kcap], y[Kcap], z[Kcap], zeta[Kcap].
+ *   - flat point order: ray 0's valid points, then ray 1's, ... (CSR; NaN padding of the reference layout dropped).
+ */
+#ifndef TONGA_B200_H
+#define TONGA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TONGA_OK 0
+#define TONGA_ERR_ARG (-1)      /* bad argument                                                       */
+#define TONGA_ERR_CUDA (-2)     /* CUDA runtime error / no device                                     */
+#define TONGA_ERR_CAPACITY (-3) /* model / shared-memory / history capacity exceeded                  */
+#define TONGA_ERR_STATE (-4)    /* call order (e.g. run before models were set)                       */
+#define TONGA_ERR_DATA (-5)     /* ray data on which the Julia code would throw (DimensionMismatch)   */
+
+typedef struct tonga_ctx tonga_ctx;       /* device-resident ray geometry + observations (one per GPU)        */
+typedef struct tonga_chains tonga_chains; /* a batch of independent RJ-MCMC chains resident on that GPU       */
+
+/* Hot-path subset of `struct parameters` (define_TDstructure.jl:1-44) plus the nucleus box, i.e. min/max of
+ * dataStruct.xVec / yVec / zVec as TD_inversion_function.jl:30-32,78-80,230-232 and MCsub.jl:92-94 use them. */
+typedef struct {
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+    double sig;                        /* percent, define_TDstructure.jl:8                                     */
+    double zeta_scale;                 /* :9                                                                   */
+    double max_sig;                    /* :12 (only the sigma move, an extension, reads it)                    */
+    double n_iter, burn_in, keep_each; /* :24-26 (Float64 in the reference)                                    */
+    int32_t min_cells, max_cells;      /* :10-11                                                               */
+    int32_t prior;                     /* :15  1 uniform (default), 2 normal, 3 exponential                    */
+    int32_t debug_prior;               /* :3   1 = sample the prior: evaluate() returns phi = 1 (MCsub.jl:134) */
+    int32_t interp_style;              /* :13  must be 1 (nearest); style 2 is broken in the reference (F7)    */
+    int32_t n_actions;                 /* 4 = reference (`rand(1:4)`, TD_inversion_function.jl:72); 5 adds the sigma move */
+} tonga_params;
+
+/* One proposal of TD_inversion_function.jl:72-251 in recorded form (replay parity; reference seeds are wall-clock,
+ * TD_inversion_function.jl:13).  action: 1 birth (x,y,z,zeta=zetanew,u) :76-125 | 2 death (idx=kill,u) :126-181 |
+ * 3 change (idx,zeta=zetan,u) :183-218 | 4 move (idx,x,y,z,u) :220-251 | 5 sigma (zeta=sig_n,u) :252-272 (extension). */
+typedef struct {
+    int32_t action;
+    int32_t idx;
+    double x, y, z;
+    double zeta;
+    double u;
+} tonga_proposal;
+
+const char *tonga_last_error(void);
+int tonga_version(void);
+int tonga_device_count(int *n_out);
+
+/* ---- geometry context: replaces the DataStruct fields evaluate() reads (DefStruct.jl:5-30; MCsub.jl:138-171).
+ * rayX/rayY/rayZ: m x R column-major (a column is one ray), NaN tail padding; rayL/rayU: (m-1) x R
+ * (load_data_Tonga.jl:66-69); tS, allSig: R.  Flattened once into device SoA arrays (points, dt = rayL*rayU). */
+int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double *rayX, const double *rayY, const double *rayZ,
+                 const double *rayL, const double *rayU, const double *tS, const double *allSig,
+                 const tonga_params *params, int32_t device);
+void tonga_destroy(tonga_ctx *ctx);
+/* R, number of valid points P, number of segments S, padded point count used on the device */
+int tonga_info(const tonga_ctx *ctx, int32_t *R, int64_t *P, int64_t *S, int64_t *Ppad);
+/* ray_off[R+1]: CSR offsets of the flat point order (for interpreting `owners`) */
+int tonga_ray_offsets(const tonga_ctx *ctx, int32_t *ray_off);
+int tonga_synchronize(tonga_ctx *ctx);
+
+/* ---- evaluate(model, dataStruct, TD_parameters), MCsub.jl:123-185.
+ * ptS_out[R] (model.ptS), *phi_out (model.phi), *like_out (model.likelihood: the model-independent constant of
+ * MCsub.jl:179), *loglik_out (the Gaussian log-likelihood :179-180 evidently intended); any may be NULL.
+ * noise = hierarchical noise scale multiplying allSig (1.0 = reference). */
+int tonga_evaluate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z, const double *zeta,
+                   double noise, double *ptS_out, double *phi_out, double *like_out, double *loglik_out);
+
+/* Batched evaluate over nModels independent models (replaces nModels calls of MCsub.jl:123-185).
+ * K[nModels]; cells[nModels][4][Kcap]; noise[nModels] or NULL; outputs (any may be NULL): ptS[nModels][R],
+ * phi[nModels], owners[nModels][P] (0-based nearest nucleus per flat point, -1 if none within sqrt(1e9)). */
+int tonga_evaluate_batch(tonga_ctx *ctx, int32_t nModels, int32_t Kcap, const int32_t *K, const double *cells,
+                         const double *noise, double *ptS, double *phi, int32_t *owners);
+/* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the context's stream.
+ * owners_dev may be NULL. */
+int tonga_evaluate_batch_dev(tonga_ctx *ctx, int32_t nModels, int32_t Kcap, const int32_t *K_dev,
+                             const double *cells_dev, const double *noise_dev, double *ptS_dev, double *phi_dev,
+                             int32_t *owners_dev);
+
+/* ---- Interpolation(TD_parameters, model, X, Y, Z), MCsub.jl:306-336, and v_nearest, MCsub.jl:247-263.
+ * X[nX] is trimmed at its first NaN (:312-316); nY / nZ may be 1 (slice broadcast, :317-322).
+ * zeta_out[nX], idx_out[nX] (may be NULL); *npoints_out = number of values written. */
+int tonga_interpolate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z,
+                      const double *zeta, int32_t nX, const double *X, int32_t nY, const double *Y, int32_t nZ,
+                      const double *Z, double *zeta_out, int32_t *idx_out, int32_t *npoints_out);
+
+/* ---- chain batch: replaces `pmap(x -> TD_inversion_function(TD_parameters, dataStruct, x), 1:n_chains)`
+ * (main_inversion.jl:15) for nChains chains resident on this GPU.  chain_id0 = global id of the first chain
+ * (device Philox streams are keyed by (seed, global chain id) so results do not depend on the GPU count).
+ * hist_cap = kept models per chain the history can hold (TD_inversion_function.jl:25 num_models_per_chain). */
+int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
+                        int32_t hist_cap);
+void tonga_chains_destroy(tonga_chains *ch);
+
+/* Start models.  build_starting (MCsub.jl:76-121) on the device ... */
+int tonga_chains_build_starting(tonga_chains *ch);
+/* ... or from the host (e.g. a checkpoint, TD_inversion_function.jl:56): K[nChains], cells[nChains][4][Kcap],
+ * noise[nChains] or NULL.  Both run a full evaluate to establish owners, t*, phi. */
+int tonga_chains_set_models(tonga_chains *ch, int32_t Kcap, const int32_t *K, const double *cells, const double *noise);
+/* per-chain inverse temperature (parallel tempering extension; 1.0 = reference); NULL resets to 1 */
+int tonga_chains_set_beta(tonga_chains *ch, const double *beta);
+
+/* The proposal loop, TD_inversion_function.jl:70-302, nIter iterations for every chain, entirely on the device
+ * (incremental Voronoi update, t* re-integration of touched rays, misfit, alpha, accept/reject, thinning).
+ *   mode 0: device Philox proposals.          recs (host, [nChains][nIter]) receives them if non-NULL.
+ *   mode 1: replay recs (host, [nChains][nIter]).
+ * Optional host traces [nChains][nIter]: accept flag, phi after the iteration, nCells after the iteration. */
+int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, tonga_proposal *recs, int8_t *tr_accept,
+                     double *tr_phi, int32_t *tr_K);
+
+/* Current models: K[nChains], cells[nChains][4][Kcap], phi, ptS[nChains][R], noise, owners[nChains][P]; any NULL. */
+int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K, double *cells, double *phi, double *ptS,
+                           double *noise, int32_t *owners);
+/* iteration counter, and per chain and action (birth, death, change, move, sigma): counts[nChains][3][5] =
+ * proposals drawn / accepted / evaluated (i.e. not rejected a priori: at the nCells limits, zeta or position out of bounds) */
+int tonga_chains_get_stats(tonga_chains *ch, int64_t *iter, int64_t *counts);
+/* Forget history, thinning counters, statistics and the iteration counter (models and streams stay); the next
+ * tonga_chains_run starts again at iter = 1, as a fresh TD_inversion_function call would. */
+int tonga_chains_reset(tonga_chains *ch);
+/* Device time (CUDA events on the library's stream) of the sampler kernel of the last tonga_chains_run, in ms. */
+int tonga_chains_last_kernel_ms(tonga_chains *ch, float *ms);
+/* Thinned history (model_hist, TD_inversion_function.jl:275-281,304): n_hist[nChains] models kept so far; arrays are
+ * [nChains][hist_cap][...]: hist_K, hist_cells[..][4][Kcap], hist_phi, hist_ptS[..][R], hist_iter, hist_action,
+ * hist_accept, hist_next_action (the action of the following iteration, which the reference's aliasing writes into the
+ * stored model: SURVEY 5.4).  Any may be NULL. */
+int tonga_chains_get_history(tonga_chains *ch, int32_t Kcap, int32_t *n_hist, int32_t *hist_K, double *hist_cells,
+                             double *hist_phi, double *hist_ptS, int64_t *hist_iter, int32_t *hist_action,
+                             int32_t *hist_accept, int32_t *hist_next_action);
+/* Consistency check on the device: re-run the full evaluate for every chain's current model and compare it with the
+ * incrementally maintained state.  owner_mismatch = number of points whose owner differs; max_dphi / max_dts =
+ * largest |difference| in phi / t* (the two paths share their reduction order, so both should be exactly 0). */
+int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, double *max_dphi, double *max_dts);
+/* Device pointers of the packed history / state for zero-copy consumers (e.g. torch.distributed gathers).
+ * Layouts as in tonga_chains_get_history with Kcap = tonga_chains_kcap(). */
+int tonga_chains_kcap(const tonga_chains *ch);
+int tonga_chains_device_ptrs(tonga_chains *ch, void **n_hist, void **hist_K, void **hist_cells, void **hist_phi,
+                             void **hist_ptS, void **state_K, void **state_cells, void **state_phi);
+
+/* ---- measurement helpers (bench.py): peak FP64 / FP32 FMA rate of this device in TFLOP/s (FMA = 2 flop). */
+int tonga_peak_flops(tonga_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,312 @@
+// evaluate.cu -- full forward model + misfit, batched over models:
+//   evaluate       MCsub.jl:123-185   (ray loop :142-163, misfit :169-175, "likelihood" :179-182)
+//   Interpolation  MCsub.jl:306-336   (NaN trim, slice broadcast, nearest nucleus per point)
+//   v_nearest      MCsub.jl:247-263   (strict <, lowest index wins, 1e9 start value)
+//
+// Kernel 1 (tg_eval_kernel): CTA = (ray tile, model).  The model's nuclei are staged in shared memory; phase 1 is a
+// flat, fully occupied pass over the tile's points (4 points per thread held in registers while the nucleus loop
+// broadcasts each nucleus from shared memory) that produces the owner of every point; phase 2 integrates t* with one
+// warp per ray in the canonical order.  Kernel 2 (tg_phi_kernel) reduces the per-ray misfit terms in the canonical
+// order.  FP64 throughout, no FMA contraction in the distance (bit-exact owners).
+#include <cmath>
+#include <cstring>
+
+#include "tonga_internal.cuh"
+
+namespace tg {
+
+constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_PPT = 4;  // points per thread per pass
+#define TG_NONE16 0xFFFFu
+
+// Bulk global->shared copy through the TMA unit (cp.async.bulk, SASS UBLKCP) with an mbarrier; used to stage a
+// model's nuclei when the tile is large enough to be worth it (>= 2 KB and 16-byte aligned).
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS)
+tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
+               const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
+               const double *__restrict__ dt, const int32_t *__restrict__ ray_off, int R, int64_t P, int64_t Ppad,
+               int tile_pts, double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int model = blockIdx.y;
+    const Tile tile = tiles[blockIdx.x];
+    const int K = Ks[model];
+    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier | owner16[tile_pts]
+    double *s_nx = reinterpret_cast<double *>(smem_raw);
+    double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zeta + Kcap);
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_bar + 1);
+
+    const double *mc = cells + (size_t)model * 4 * Kcap;
+    const uint32_t nbytes = (uint32_t)(4 * Kcap * sizeof(double));
+    const bool use_bulk = (nbytes >= 2048u) && ((nbytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(mc) & 15u) == 0);
+    if (use_bulk) {  // one TMA bulk copy of the whole [4][Kcap] block
+        if (threadIdx.x == 0) {
+            mbar_init(s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(s_bar, nbytes);
+            bulk_g2s(s_nx, mc, nbytes, s_bar);
+        }
+        mbar_wait(s_bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < 4 * Kcap; i += EVAL_THREADS) s_nx[i] = mc[i];
+        __syncthreads();
+    }
+
+    // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263)
+    const int npts = tile.p1 - tile.p0;
+    for (int base = 0; base < npts; base += EVAL_THREADS * EVAL_PPT) {
+        double x[EVAL_PPT], y[EVAL_PPT], z[EVAL_PPT], best[EVAL_PPT];
+        int bi[EVAL_PPT];
+#pragma unroll
+        for (int q = 0; q < EVAL_PPT; q++) {
+            const int j = base + q * EVAL_THREADS + threadIdx.x;
+            const int p = tile.p0 + (j < npts ? j : 0);
+            x[q] = px[p]; y[q] = py[p]; z[q] = pz[p];
+            best[q] = 1e9;  // mdist = 1e9, MCsub.jl:250
+            bi[q] = -1;
+        }
+#pragma unroll 2
+        for (int i = 0; i < K; i++) {
+            const double ax = s_nx[i], ay = s_ny[i], az = s_nz[i];
+#pragma unroll
+            for (int q = 0; q < EVAL_PPT; q++) {
+                const double d = dist2_exact(ax, ay, az, x[q], y[q], z[q]);
+                if (d < best[q]) { best[q] = d; bi[q] = i; }  // strict <: lowest index wins ties (:255)
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < EVAL_PPT; q++) {
+            const int j = base + q * EVAL_THREADS + threadIdx.x;
+            if (j < npts) {
+                s_owner[j] = bi[q] < 0 ? (uint16_t)TG_NONE16 : (uint16_t)bi[q];
+                const int64_t p = tile.p0 + j;
+                if (owners32) owners32[(size_t)model * P + p] = bi[q];
+                if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: t* per ray, one warp per ray, canonical order (MCsub.jl:147,153/159)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EVAL_THREADS / 32;
+    auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16 ? 0.0 : s_zeta[o]; };
+    for (int r = tile.r0 + warp; r < tile.r1; r += nwarps) {
+        const int q0 = ray_off[r], n = ray_off[r + 1] - q0;
+        const double t = ray_tstar_canonical<uint16_t>(s_owner - tile.p0, dt, q0, n, lane, zeta_of);
+        if (lane == 0) ptS[(size_t)model * R + r] = t;
+    }
+}
+
+// padded tail of the u8 chain-state owner arrays: NONE
+__global__ void tg_owner_pad_kernel(uint8_t *owners8, int64_t P, int64_t Ppad, int nModels) {
+    const int64_t pad = Ppad - P;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < pad * nModels) owners8[(i / pad) * Ppad + P + (i % pad)] = (uint8_t)TG_OWNER_NONE;
+}
+
+__global__ void __launch_bounds__(TG_PHI_LANES)
+tg_phi_kernel(int R, const double *__restrict__ ptS, const double *__restrict__ tS, const double *__restrict__ sig,
+              const double *__restrict__ noise, double *__restrict__ phi, int debug_prior) {
+    __shared__ double scratch[4];
+    const int model = blockIdx.x;
+    if (debug_prior) {  // MCsub.jl:128-136: phi = 1, nothing else computed
+        if (threadIdx.x == 0) phi[model] = 1.0;
+        return;
+    }
+    const double nz = noise ? noise[model] : 1.0;
+    const double *t = ptS + (size_t)model * R;
+    const double v = phi_canonical_128(R, threadIdx.x, scratch, [&](int r) { return misfit_term(t[r], tS[r], sig[r], nz); });
+    if (threadIdx.x == 0) phi[model] = v;
+}
+
+int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev) {
+    if (nModels <= 0) return TONGA_OK;
+    if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
+    if (!ctx->prm.debug_prior && ctx->n_tiles > 0) {
+        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + sizeof(uint16_t) * (size_t)ctx->tile_pts;
+        if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
+        TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(ctx->n_tiles, nModels);
+        tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
+                                                                  ctx->d_pz, ctx->d_dt, ctx->d_ray_off, ctx->R, ctx->P,
+                                                                  ctx->Ppad, ctx->tile_pts, ptS_dev, owners32_dev, owners8_dev);
+        TG_CUDA(cudaGetLastError());
+    }
+    if (owners8_dev && ctx->Ppad > ctx->P) {
+        const int64_t n = (ctx->Ppad - ctx->P) * nModels;
+        tg_owner_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(owners8_dev, ctx->P, ctx->Ppad, nModels);
+        TG_CUDA(cudaGetLastError());
+    }
+    if (phi_dev) {
+        tg_phi_kernel<<<nModels, TG_PHI_LANES, 0, ctx->stream>>>(ctx->R, ptS_dev, ctx->d_tS, ctx->d_sig, noise_dev, phi_dev,
+                                                                ctx->prm.debug_prior);
+        TG_CUDA(cudaGetLastError());
+    }
+    return TONGA_OK;
+}
+
+// one thread per query point; nuclei staged in shared memory
+__global__ void __launch_bounds__(256)
+tg_interp_kernel(int K, const double *__restrict__ cells /* [4][K] */, int n, const double *__restrict__ X, int nY,
+                 const double *__restrict__ Y, int nZ, const double *__restrict__ Z, double *__restrict__ zeta_out,
+                 int32_t *__restrict__ idx_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s = reinterpret_cast<double *>(smem_raw);
+    for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) s[i] = cells[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double x = X[k], y = (nY == 1) ? Y[0] : Y[k], z = (nZ == 1) ? Z[0] : Z[k];
+    double best = 1e9, v = 0.0;
+    int bi = -1;
+    for (int i = 0; i < K; i++) {
+        const double d = dist2_exact(s[i], s[K + i], s[2 * K + i], x, y, z);
+        if (d < best) { best = d; bi = i; v = s[3 * K + i]; }
+    }
+    zeta_out[k] = v;
+    if (idx_out) idx_out[k] = bi;
+}
+
+}  // namespace tg
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int tonga_evaluate_batch_dev(tonga_ctx *ctx, int32_t nModels, int32_t Kcap, const int32_t *K_dev,
+                                        const double *cells_dev, const double *noise_dev, double *ptS_dev, double *phi_dev,
+                                        int32_t *owners_dev) {
+    if (!ctx || nModels < 0 || Kcap < 1 || !K_dev || !cells_dev || !ptS_dev)
+        return tg::fail(TONGA_ERR_ARG, "tonga_evaluate_batch_dev: bad argument (ptS_dev is required)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    return tg::launch_evaluate(ctx, nModels, Kcap, K_dev, cells_dev, noise_dev, ptS_dev, phi_dev, owners_dev, nullptr);
+}
+
+extern "C" int tonga_evaluate_batch(tonga_ctx *ctx, int32_t nModels, int32_t Kcap, const int32_t *K, const double *cells,
+                                    const double *noise, double *ptS, double *phi, int32_t *owners) {
+    if (!ctx || nModels < 0 || Kcap < 1 || !K || !cells) return tg::fail(TONGA_ERR_ARG, "tonga_evaluate_batch: bad argument");
+    if (nModels == 0) return TONGA_OK;
+    for (int i = 0; i < nModels; i++)
+        if (K[i] < 0 || K[i] > Kcap) return tg::fail(TONGA_ERR_ARG, "tonga_evaluate_batch: K[i] outside [0, Kcap]");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const size_t R = (size_t)ctx->R, P = (size_t)ctx->P, n = (size_t)nModels;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_K = 0, o_cells = o_K + al(4 * n), o_noise = o_cells + al(8 * n * 4 * Kcap), o_pts = o_noise + al(8 * n),
+                 o_phi = o_pts + al(8 * n * (R ? R : 1)), o_own = o_phi + al(8 * n), total = o_own + (owners ? al(4 * n * (P ? P : 1)) : 0);
+    int rc = tg::ensure_scratch(ctx, total);
+    if (rc != TONGA_OK) return rc;
+    char *d = (char *)ctx->d_scratch;
+    cudaStream_t s = ctx->stream;
+    TG_CUDA(cudaMemcpyAsync(d + o_K, K, 4 * n, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(d + o_cells, cells, 8 * n * 4 * Kcap, cudaMemcpyHostToDevice, s));
+    if (noise) TG_CUDA(cudaMemcpyAsync(d + o_noise, noise, 8 * n, cudaMemcpyHostToDevice, s));
+    rc = tg::launch_evaluate(ctx, nModels, Kcap, (const int32_t *)(d + o_K), (const double *)(d + o_cells),
+                             noise ? (const double *)(d + o_noise) : nullptr, (double *)(d + o_pts), (double *)(d + o_phi),
+                             owners ? (int32_t *)(d + o_own) : nullptr, nullptr);
+    if (rc != TONGA_OK) return rc;
+    if (ptS && R && !ctx->prm.debug_prior) TG_CUDA(cudaMemcpyAsync(ptS, d + o_pts, 8 * n * R, cudaMemcpyDeviceToHost, s));
+    if (phi) TG_CUDA(cudaMemcpyAsync(phi, d + o_phi, 8 * n, cudaMemcpyDeviceToHost, s));
+    if (owners && P && !ctx->prm.debug_prior) TG_CUDA(cudaMemcpyAsync(owners, d + o_own, 4 * n * P, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaStreamSynchronize(s));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_evaluate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z,
+                              const double *zeta, double noise, double *ptS_out, double *phi_out, double *like_out,
+                              double *loglik_out) {
+    if (!ctx || K < 0 || (K > 0 && (!x || !y || !z || !zeta))) return tg::fail(TONGA_ERR_ARG, "tonga_evaluate: bad argument");
+    const int Kcap = K > 0 ? K : 1;
+    std::vector<double> cells((size_t)4 * Kcap, 0.0);
+    if (K > 0) {
+        std::memcpy(&cells[0], x, 8 * (size_t)K);
+        std::memcpy(&cells[Kcap], y, 8 * (size_t)K);
+        std::memcpy(&cells[2 * (size_t)Kcap], z, 8 * (size_t)K);
+        std::memcpy(&cells[3 * (size_t)Kcap], zeta, 8 * (size_t)K);
+    }
+    double phi = 0.0;
+    int rc = tonga_evaluate_batch(ctx, 1, Kcap, &K, cells.data(), &noise, ptS_out, &phi, nullptr);
+    if (rc != TONGA_OK) return rc;
+    if (phi_out) *phi_out = phi;
+    if (ctx->prm.debug_prior) {  // MCsub.jl:129-136: likelihood = 1
+        if (like_out) *like_out = 1.0;
+        if (loglik_out) *loglik_out = 1.0;
+        return TONGA_OK;
+    }
+    // MCsub.jl:179 with allSig scaled by `noise`: sum_k (-log(noise*sig_k*sqrt(2pi))) * R
+    const double R = (double)ctx->R;
+    if (like_out) *like_out = (noise == 1.0) ? ctx->like_const : (ctx->sum_neglog - R * std::log(noise)) * R;
+    if (loglik_out) *loglik_out = (ctx->sum_neglog - R * std::log(noise)) - 0.5 * phi;
+    return TONGA_OK;
+}
+
+extern "C" int tonga_interpolate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z,
+                                 const double *zeta, int32_t nX, const double *X, int32_t nY, const double *Y, int32_t nZ,
+                                 const double *Z, double *zeta_out, int32_t *idx_out, int32_t *npoints_out) {
+    if (!ctx || K < 0 || nX < 0 || (K > 0 && (!x || !y || !z || !zeta)) || (nX > 0 && (!X || !Y || !Z || !zeta_out)))
+        return tg::fail(TONGA_ERR_ARG, "tonga_interpolate: bad argument");
+    int npoints = nX;  // MCsub.jl:312-316
+    for (int k = 0; k < nX; k++)
+        if (std::isnan(X[k])) { npoints = k; break; }
+    if (npoints_out) *npoints_out = npoints;
+    if (npoints == 0) return TONGA_OK;
+    if ((nY != 1 && nY < npoints) || (nZ != 1 && nZ < npoints))
+        return tg::fail(TONGA_ERR_ARG, "tonga_interpolate: Y / Z shorter than the trimmed X (Julia would throw BoundsError)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)npoints, k4 = (size_t)4 * (K > 0 ? K : 1);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t ny = (nY == 1) ? 1 : n, nz = (nZ == 1) ? 1 : n;
+    const size_t o_c = 0, o_X = o_c + al(8 * k4), o_Y = o_X + al(8 * n), o_Z = o_Y + al(8 * ny), o_o = o_Z + al(8 * nz),
+                 o_i = o_o + al(8 * n), total = o_i + al(4 * n);
+    if (8 * k4 > ctx->smem_optin) return tg::fail(TONGA_ERR_CAPACITY, "tonga_interpolate: K too large for shared memory");
+    int rc = tg::ensure_scratch(ctx, total);
+    if (rc != TONGA_OK) return rc;
+    char *d = (char *)ctx->d_scratch;
+    cudaStream_t s = ctx->stream;
+    if (K > 0) {
+        TG_CUDA(cudaMemcpyAsync(d + o_c, x, 8 * (size_t)K, cudaMemcpyHostToDevice, s));
+        TG_CUDA(cudaMemcpyAsync(d + o_c + 8 * (size_t)K, y, 8 * (size_t)K, cudaMemcpyHostToDevice, s));
+        TG_CUDA(cudaMemcpyAsync(d + o_c + 16 * (size_t)K, z, 8 * (size_t)K, cudaMemcpyHostToDevice, s));
+        TG_CUDA(cudaMemcpyAsync(d + o_c + 24 * (size_t)K, zeta, 8 * (size_t)K, cudaMemcpyHostToDevice, s));
+    }
+    TG_CUDA(cudaMemcpyAsync(d + o_X, X, 8 * n, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(d + o_Y, Y, 8 * ny, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(d + o_Z, Z, 8 * nz, cudaMemcpyHostToDevice, s));
+    const size_t smem = 8 * k4;
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    tg::tg_interp_kernel<<<(unsigned)((n + 255) / 256), 256, smem, s>>>(K, (const double *)(d + o_c), npoints, (const double *)(d + o_X),
+                                                                      nY, (const double *)(d + o_Y), nZ, (const double *)(d + o_Z),
+                                                                      (double *)(d + o_o), (int32_t *)(d + o_i));
+    TG_CUDA(cudaGetLastError());
+    TG_CUDA(cudaMemcpyAsync(zeta_out, d + o_o, 8 * n, cudaMemcpyDeviceToHost, s));
+    if (idx_out) TG_CUDA(cudaMemcpyAsync(idx_out, d + o_i, 4 * n, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaStreamSynchronize(s));
+    return TONGA_OK;
+}

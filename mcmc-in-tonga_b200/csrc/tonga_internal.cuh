@@ -1,0 +1,174 @@
+// tonga_internal.cuh -- shared device helpers and host-side structs of libtonga_b200.so (sm_100a only).
+//
+// Numerical contract (DESIGN.md "Exactness"):
+//   * squared distance exactly as MCsub.jl:254 evaluates it in Julia: fl(fl(dx*dx + dy*dy) + dz*dz) with
+//     dx = mx - x; no FMA contraction (explicit __dmul_rn / __dadd_rn), so owners are bit-exact;
+//   * per-segment term exactly as MCsub.jl:147,153: (rayl*rayu) * ((0.5*(za+zb)) / 1000); the division is done
+//     with a 3-op FMA sequence that returns the correctly rounded quotient (checked against `/` on 3e8 samples);
+//   * per-ray misfit term exactly as MCsub.jl:171: ((d*d)*1.0) / (sig*sig);
+//   * ONE canonical summation order for t* (per ray) and phi (per model), shared by the full evaluate kernel and
+//     the incremental sampler kernel, so "incremental == full" holds bit for bit on the device.  The reference's
+//     own order (Julia `sum`, SIMD pairwise) is unspecified; parity with the oracle is 1e-9 relative.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tonga_b200.h"
+
+// ------------------------------------------------------------------------------------------------ constants
+#define TG_OWNER_NONE 0x7Fu  // u8 owner code: no nucleus closer than sqrt(1e9) (v_nearest returns 0.0, MCsub.jl:249-250)
+#define TG_OWNER_TAG 0x80u   // u8 owner bit 7: pending "switches to the proposal's implicit new owner"
+#define TG_MAX_K_U8 126      // largest nCells representable with u8 owners (indices 0..125, +1 for a birth)
+#define TG_PHI_LANES 128     // virtual lanes of the canonical phi reduction
+#define TG_PT_TILE 512       // points are padded to a multiple of this (128 threads x 4 points)
+
+namespace tg {
+
+// ------------------------------------------------------------------------------------------------ errors
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+#define TG_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return tg::fail(TONGA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ exact math
+__device__ __forceinline__ double dist2_exact(double mx, double my, double mz, double x, double y, double z) {
+    // (mx - x)^2 + (my - y)^2 + (mz - z)^2, MCsub.jl:254 -- never contracted into FMAs
+    const double dx = __dsub_rn(mx, x), dy = __dsub_rn(my, y), dz = __dsub_rn(mz, z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ double div1000_exact(double a) {
+    // correctly rounded a / 1000 (Markstein: y = RN(1/b), q0 = a*y, r = a - b*q0 exactly, q = q0 + r*y)
+    const double y = 0.001;
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-q0, 1000.0, a);
+    return __fma_rn(r, y, q0);
+}
+
+__device__ __forceinline__ double seg_term(double dt, double za, double zb) {
+    // MCsub.jl:147,153:  (rayl*rayu) * ((0.5*(za+zb)) / 1000);  dt = fl(rayl*rayu) is precomputed on the host
+    return __dmul_rn(dt, div1000_exact(__dmul_rn(0.5, __dadd_rn(za, zb))));
+}
+
+__device__ __forceinline__ double misfit_term(double pts, double ts, double sig, double noise) {
+    // MCsub.jl:171:  ((ptS - tS)^2 * 1.0) / sig^2   with sig = noise * allSig (noise == 1.0 -> reference)
+    const double sg = __dmul_rn(noise, sig);
+    const double d = __dsub_rn(pts, ts);
+    return __ddiv_rn(__dmul_rn(__dmul_rn(d, d), 1.0), __dmul_rn(sg, sg));
+}
+
+__device__ __forceinline__ double warp_sum_canonical(double v) {
+    // xor butterfly: every lane ends with the same, order-defined sum
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// Canonical t* of one ray by one warp.  zlut maps an owner byte/code to zeta.  p0 = first flat point, n = #points.
+// lane l sums terms j = l, l+32, ... (ascending), then the xor butterfly.
+template <typename OwnerT, typename ZetaOf>
+__device__ __forceinline__ double ray_tstar_canonical(const OwnerT *__restrict__ owner, const double *__restrict__ dt,
+                                                      int p0, int n, int lane, ZetaOf zeta_of) {
+    double acc = 0.0;
+    for (int j = lane; j < n - 1; j += 32) {
+        const double za = zeta_of(owner[p0 + j]);
+        const double zb = zeta_of(owner[p0 + j + 1]);
+        acc = __dadd_rn(acc, seg_term(dt[p0 + j], za, zb));
+    }
+    return warp_sum_canonical(acc);
+}
+
+// Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES (=128) threads (4 warps).
+// term(r) must be callable by any thread.  scratch: 4 doubles of shared memory.  Result valid in all threads.
+template <typename TermOf>
+__device__ __forceinline__ double phi_canonical_128(int R, int t128, double *scratch, TermOf term) {
+    double acc = 0.0;
+    for (int r = t128; r < R; r += TG_PHI_LANES) acc = __dadd_rn(acc, term(r));
+    acc = warp_sum_canonical(acc);
+    if ((t128 & 31) == 0) scratch[t128 >> 5] = acc;
+    __syncthreads();
+    const double tot = __dadd_rn(__dadd_rn(__dadd_rn(scratch[0], scratch[1]), scratch[2]), scratch[3]);
+    __syncthreads();
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+    uint32_t k0, k1;
+    __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+        const uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32);
+        lo = (uint32_t)p;
+    }
+    __host__ __device__ inline void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+        uint32_t ka = k0, kb = k1;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            uint32_t h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, c0, h0, l0);
+            mulhilo(0xCD9E8D57u, c2, h1, l1);
+            const uint32_t n0 = h1 ^ c1 ^ ka, n1 = l1, n2 = h0 ^ c3 ^ kb, n3 = l0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            ka += 0x9E3779B9u;
+            kb += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+__host__ __device__ inline double u53(uint32_t a, uint32_t b) {  // uniform [0,1), 53 bits
+    return (double)((((uint64_t)a << 32) | b) >> 11) * 0x1.0p-53;
+}
+__host__ __device__ inline double u53_open(uint32_t a, uint32_t b) {  // uniform (0,1)
+    return ((double)((((uint64_t)a << 32) | b) >> 11) + 0.5) * 0x1.0p-53;
+}
+
+// ------------------------------------------------------------------------------------------------ host structs
+struct Tile { int r0, r1, p0, p1; };  // rays [r0,r1), flat points [p0,p1)
+
+}  // namespace tg
+
+struct tonga_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    tonga_params prm{};
+    int m = 0, R = 0;
+    int64_t P = 0, S = 0, Ppad = 0;
+    int max_npts = 0;
+    // device geometry (SoA, flat point order, padded with NaN coordinates / zero dt)
+    double *d_px = nullptr, *d_py = nullptr, *d_pz = nullptr;  // [Ppad]
+    double *d_dt = nullptr;                                    // [Ppad] dt of the segment starting at p (0 at ray ends)
+    int32_t *d_rayid = nullptr;                                // [Ppad]
+    int32_t *d_ray_off = nullptr;                              // [R+1]
+    double *d_tS = nullptr, *d_sig = nullptr;                  // [R]
+    tg::Tile *d_tiles = nullptr;
+    int n_tiles = 0;
+    int tile_pts = 0;
+    std::vector<int32_t> h_ray_off;
+    double like_const = 0.0;  // MCsub.jl:179 for noise = 1
+    double sum_neglog = 0.0;  // sum_k -log(allSig_k*sqrt(2pi))
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::mutex mu;
+    // scratch for host-pointer entry points (grown on demand)
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+namespace tg {
+int ensure_scratch(tonga_ctx *ctx, size_t bytes);
+int ensure_pinned(tonga_ctx *ctx, size_t bytes);
+// launches (all asynchronous on ctx->stream)
+int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev,
+                    uint8_t *owners8_dev /* [nModels][Ppad] chain-state layout, or NULL */);
+}  // namespace tg

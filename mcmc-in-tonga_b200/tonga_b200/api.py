@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's hot-path interface, forwarding to libtonga_b200.so.
+
+Same names, argument order and return values as the Julia functions they replace (file:line relative to the reference):
+
+  evaluate(model, dataStruct, TD_parameters) -> (model, dataStruct, valid)            MCsub.jl:123-185
+  Interpolation(TD_parameters, model, X, Y, Z) -> Vector{Float64}(npoints)            MCsub.jl:306-336
+  v_nearest(x, y, z, mx, my, mz, mv) -> Float64                                       MCsub.jl:247-263
+  build_starting(TD_parameters, dataStruct) -> (model, dataStruct, valid)             MCsub.jl:76-121
+  TD_inversion_function(TD_parameters, dataStruct, chain) -> model_hist              TD_inversion_function.jl:7-305
+  run_chains(TD_parameters, dataStruct, chains) -> Vector{Vector{Model}}              main_inversion.jl:15 (the pmap line)
+
+plus the batched / low-level objects (`Context`, `Chains`) the tests and bench.py drive.  Julia is absent from this
+image; `julia/TongaB200.jl` holds the same shim written in Julia.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import PROPOSAL_DTYPE, TongaError, TongaParams, check, dp, ip, lp, bp
+from .structs import DataStruct, Model, parameters
+
+
+def make_params(TD_parameters: parameters, dataStruct: DataStruct, n_actions: int = 4) -> TongaParams:
+    p = TongaParams()
+    # min(xVec...) / max(xVec...) etc., TD_inversion_function.jl:30-32,78-80
+    p.xmin, p.xmax = dataStruct.xVec.min(), dataStruct.xVec.max()
+    p.ymin, p.ymax = dataStruct.yVec.min(), dataStruct.yVec.max()
+    p.zmin, p.zmax = dataStruct.zVec.min(), dataStruct.zVec.max()
+    p.sig, p.zeta_scale, p.max_sig = float(TD_parameters.sig), float(TD_parameters.zeta_scale), float(TD_parameters.max_sig)
+    p.n_iter, p.burn_in, p.keep_each = float(TD_parameters.n_iter), float(TD_parameters.burn_in), float(TD_parameters.keep_each)
+    p.min_cells, p.max_cells = int(TD_parameters.min_cells), int(TD_parameters.max_cells)
+    p.prior, p.debug_prior, p.interp_style = int(TD_parameters.prior), int(TD_parameters.debug_prior), int(TD_parameters.interp_style)
+    p.n_actions = n_actions
+    return p
+
+
+def pack_models(models, Kcap=None):
+    """list of (x, y, z, zeta) or Model -> K[n] int32, cells[n,4,Kcap] float64."""
+    tup = [(m.xCell, m.yCell, m.zCell, m.zeta) if isinstance(m, Model) else m for m in models]
+    K = np.array([len(t[0]) for t in tup], np.int32)
+    Kcap = int(Kcap or max(int(K.max()) if len(K) else 1, 1))
+    cells = np.zeros((len(tup), 4, Kcap))
+    for i, t in enumerate(tup):
+        for a in range(4):
+            cells[i, a, :K[i]] = t[a]
+    return K, cells
+
+
+class Context:
+    """Device-resident ray geometry + observations: what `dataStruct` is to evaluate()."""
+
+    def __init__(self, dataStruct: DataStruct | None, TD_parameters: parameters | None = None, device: int = 0,
+                 n_actions: int = 4, params: TongaParams | None = None):
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        if dataStruct is None:  # geometry-less context (v_nearest / Interpolation on arbitrary points only)
+            z = np.zeros((1, 0), order="F")
+            p = params or TongaParams()
+            p.interp_style = 1
+            self.R, self.m = 0, 1
+            check(self.lib.tonga_create(C.byref(self._h), 1, 0, dp(z), dp(z), dp(z), dp(z), dp(z), dp(z), dp(z), C.byref(p), device))
+            self.params = p
+        else:
+            ds = dataStruct
+            f = lambda a: np.asfortranarray(a, dtype=np.float64)
+            rx, ry, rz, rl, ru = f(ds.rayX), f(ds.rayY), f(ds.rayZ), f(ds.rayL), f(ds.rayU)
+            self.m, self.R = rx.shape
+            if rl.shape != (self.m - 1, self.R) or ru.shape != rl.shape:
+                raise TongaError(-1, "rayL / rayU must be (m-1) x R")
+            tS, sg = np.ascontiguousarray(ds.tS, dtype=np.float64), np.ascontiguousarray(ds.allSig, dtype=np.float64)
+            self.params = params or make_params(TD_parameters, ds, n_actions)
+            check(self.lib.tonga_create(C.byref(self._h), self.m, self.R, dp(rx), dp(ry), dp(rz), dp(rl), dp(ru), dp(tS), dp(sg),
+                                        C.byref(self.params), device))
+        R, P, S, Pp = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.tonga_info(self._h, C.byref(R), C.byref(P), C.byref(S), C.byref(Pp)))
+        self.P, self.S, self.Ppad = P.value, S.value, Pp.value
+        self.device = device
+        self._fin = weakref.finalize(self, self.lib.tonga_destroy, self._h)
+
+    def close(self):
+        self._fin()
+
+    def ray_offsets(self) -> np.ndarray:
+        off = np.zeros(self.R + 1, np.int32)
+        check(self.lib.tonga_ray_offsets(self._h, ip(off)))
+        return off
+
+    def evaluate(self, x, y, z, zeta, noise: float = 1.0):
+        """One model -> dict(ptS, phi, likelihood, loglik_gauss)."""
+        x, y, z, zeta = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, zeta))
+        ptS = np.zeros(max(self.R, 1))
+        phi, like, lg = C.c_double(), C.c_double(), C.c_double()
+        check(self.lib.tonga_evaluate(self._h, len(x), dp(x), dp(y), dp(z), dp(zeta), float(noise), dp(ptS), C.byref(phi), C.byref(like), C.byref(lg)))
+        return dict(ptS=ptS[:self.R], phi=phi.value, likelihood=like.value, loglik_gauss=lg.value)
+
+    def evaluate_batch(self, K, cells, noise=None, want_ptS=True, want_owners=False):
+        """K[n], cells[n,4,Kcap] -> dict(phi[n], ptS[n,R] | None, owners[n,P] | None)."""
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        cells = np.ascontiguousarray(cells, dtype=np.float64)
+        n, four, Kcap = cells.shape
+        assert four == 4 and len(K) == n
+        noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        ptS = np.zeros((n, self.R)) if want_ptS else None
+        phi = np.zeros(n)
+        owners = np.zeros((n, self.P), np.int32) if want_owners else None
+        check(self.lib.tonga_evaluate_batch(self._h, n, Kcap, ip(K), dp(cells), dp(noise), dp(ptS), dp(phi), ip(owners)))
+        return dict(phi=phi, ptS=ptS, owners=owners)
+
+    def evaluate_batch_dev(self, n, Kcap, K_ptr, cells_ptr, noise_ptr, ptS_ptr, phi_ptr, owners_ptr=None):
+        """Device-pointer variant (ints from torch .data_ptr()); asynchronous on the context's stream."""
+        check(self.lib.tonga_evaluate_batch_dev(self._h, n, Kcap, K_ptr, cells_ptr, noise_ptr, ptS_ptr, phi_ptr, owners_ptr))
+
+    def synchronize(self):
+        check(self.lib.tonga_synchronize(self._h))
+
+    def interpolate(self, mx, my, mz, mv, X, Y, Z):
+        mx, my, mz, mv = (np.ascontiguousarray(a, dtype=np.float64) for a in (mx, my, mz, mv))
+        X, Y, Z = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (X, Y, Z))
+        out = np.zeros(max(len(X), 1))
+        idx = np.zeros(max(len(X), 1), np.int32)
+        npts = C.c_int32()
+        check(self.lib.tonga_interpolate(self._h, len(mx), dp(mx), dp(my), dp(mz), dp(mv), len(X), dp(X), len(Y), dp(Y), len(Z), dp(Z),
+                                         dp(out), ip(idx), C.byref(npts)))
+        return out[:npts.value].copy(), idx[:npts.value].copy()
+
+    def peak_flops(self):
+        a, b = C.c_double(), C.c_double()
+        check(self.lib.tonga_peak_flops(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class Chains:
+    """A batch of independent RJ-MCMC chains resident on one GPU (replaces the pmap chain farm, main_inversion.jl:15)."""
+
+    def __init__(self, ctx: Context, n_chains: int, chain_id0: int = 0, seed: int = 20260000, hist_cap: int | None = None):
+        self.ctx, self.lib, self.n = ctx, ctx.lib, n_chains
+        p = ctx.params
+        if hist_cap is None:  # num_models_per_chain, TD_inversion_function.jl:25
+            hist_cap = int((p.n_iter - p.burn_in) / p.keep_each) + 1 if p.keep_each > 0 else 0
+        self.hist_cap = hist_cap
+        self._h = C.c_void_p()
+        check(self.lib.tonga_chains_create(ctx._h, C.byref(self._h), n_chains, chain_id0, seed, hist_cap))
+        self.KC = self.lib.tonga_chains_kcap(self._h)
+        self._fin = weakref.finalize(self, self.lib.tonga_chains_destroy, self._h)
+        self._ctx_keepalive = ctx
+
+    def close(self):
+        self._fin()
+
+    def build_starting(self):
+        check(self.lib.tonga_chains_build_starting(self._h))
+
+    def set_models(self, K, cells, noise=None):
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        cells = np.ascontiguousarray(cells, dtype=np.float64)
+        assert cells.shape[0] == self.n and cells.shape[1] == 4
+        noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        check(self.lib.tonga_chains_set_models(self._h, cells.shape[2], ip(K), dp(cells), dp(noise)))
+
+    def set_beta(self, beta):
+        beta = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+        check(self.lib.tonga_chains_set_beta(self._h, dp(beta)))
+
+    def run(self, n_iter: int, recs: np.ndarray | None = None, record: bool = False, trace: bool = False):
+        """Generate mode (device Philox) unless `recs` ([n, n_iter] PROPOSAL_DTYPE) is given (replay).
+        -> dict(recs (if record), accept, phi, K (if trace))."""
+        mode = 0 if recs is None else 1
+        if recs is not None:
+            recs = np.ascontiguousarray(recs, dtype=PROPOSAL_DTYPE)
+            assert recs.shape == (self.n, n_iter), recs.shape
+        elif record:
+            recs = np.zeros((self.n, n_iter), PROPOSAL_DTYPE)
+        acc = np.zeros((self.n, n_iter), np.int8) if trace else None
+        phi = np.zeros((self.n, n_iter)) if trace else None
+        K = np.zeros((self.n, n_iter), np.int32) if trace else None
+        check(self.lib.tonga_chains_run(self._h, n_iter, mode, None if recs is None else recs.ctypes.data, bp(acc), dp(phi), ip(K)))
+        return dict(recs=recs, accept=acc, phi=phi, K=K)
+
+    def state(self, want_ptS=True, want_owners=False):
+        n, KC = self.n, self.KC
+        K = np.zeros(n, np.int32)
+        cells = np.zeros((n, 4, KC))
+        phi = np.zeros(n)
+        noise = np.zeros(n)
+        ptS = np.zeros((n, self.ctx.R)) if want_ptS else None
+        owners = np.zeros((n, self.ctx.P), np.int32) if want_owners else None
+        check(self.lib.tonga_chains_get_state(self._h, KC, ip(K), dp(cells), dp(phi), dp(ptS), dp(noise), ip(owners)))
+        return dict(K=K, cells=cells, phi=phi, ptS=ptS, noise=noise, owners=owners)
+
+    def stats(self):
+        it = C.c_int64()
+        counts = np.zeros((self.n, 3, 5), np.int64)  # proposed / accepted / evaluated per action
+        check(self.lib.tonga_chains_get_stats(self._h, C.byref(it), lp(counts)))
+        return it.value, counts
+
+    def reset(self):
+        check(self.lib.tonga_chains_reset(self._h))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(self.lib.tonga_chains_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def history(self, want_ptS=True):
+        n, H, KC, R = self.n, self.hist_cap, self.KC, self.ctx.R
+        out = dict(n_hist=np.zeros(n, np.int32), K=np.zeros((n, H), np.int32), cells=np.zeros((n, H, 4, KC)),
+                   phi=np.zeros((n, H)), ptS=np.zeros((n, H, R)) if want_ptS else None, iter=np.zeros((n, H), np.int64),
+                   action=np.zeros((n, H), np.int32), accept=np.zeros((n, H), np.int32), next_action=np.zeros((n, H), np.int32))
+        check(self.lib.tonga_chains_get_history(self._h, KC, ip(out["n_hist"]), ip(out["K"]), dp(out["cells"]), dp(out["phi"]),
+                                                dp(out["ptS"]), lp(out["iter"]), ip(out["action"]), ip(out["accept"]),
+                                                ip(out["next_action"])))
+        return out
+
+    def verify(self):
+        """Full re-evaluate of every chain on the device vs the incrementally maintained state."""
+        mm, dphi, dts = C.c_int64(), C.c_double(), C.c_double()
+        check(self.lib.tonga_chains_verify(self._h, C.byref(mm), C.byref(dphi), C.byref(dts)))
+        return mm.value, dphi.value, dts.value
+
+    def device_ptrs(self):
+        names = ("n_hist", "hist_K", "hist_cells", "hist_phi", "hist_ptS", "state_K", "state_cells", "state_phi")
+        ptrs = [C.c_void_p() for _ in names]
+        check(self.lib.tonga_chains_device_ptrs(self._h, *[C.byref(p) for p in ptrs]))
+        return {k: p.value for k, p in zip(names, ptrs)}
+
+
+# ------------------------------------------------------------------------------------------ reference-named functions
+_CTX_CACHE: dict = {}
+_UTIL_CTX: list = []
+
+
+def context_for(dataStruct: DataStruct, TD_parameters: parameters, device: int = 0, n_actions: int = 4) -> Context:
+    """One Context per (dataStruct, parameters) pair, like the Julia shim's cache keyed on objectid(dataStruct)."""
+    key = (id(dataStruct), id(TD_parameters), device, n_actions)
+    ent = _CTX_CACHE.get(key)
+    if ent is None or ent[0]() is not dataStruct:
+        ctx = Context(dataStruct, TD_parameters, device, n_actions)
+        _CTX_CACHE[key] = (weakref.ref(dataStruct), ctx)
+        return ctx
+    return ent[1]
+
+
+def _util_ctx() -> Context:
+    if not _UTIL_CTX:
+        _UTIL_CTX.append(Context(None))
+    return _UTIL_CTX[0]
+
+
+def v_nearest(x, y, z, mx, my, mz, mv) -> float:
+    """MCsub.jl:247-263."""
+    out, _ = _util_ctx().interpolate(mx, my, mz, mv, [x], [y], [z])
+    return float(out[0])
+
+
+def Interpolation(TD_parameters: parameters, model: Model, X, Y, Z) -> np.ndarray:  # noqa: N802
+    """MCsub.jl:306-336 (interp_style 1; style 2 raises, as it does in the reference: SURVEY F7)."""
+    if TD_parameters.interp_style != 1:
+        raise TongaError(-1, "interp_style 2 (IDW) is broken in the reference (MCsub.jl:332 uses undefined variables)")
+    out, _ = _util_ctx().interpolate(model.xCell, model.yCell, model.zCell, model.zeta, X, Y, Z)
+    return out
+
+
+def evaluate(model: Model, dataStruct: DataStruct, TD_parameters: parameters):
+    """MCsub.jl:123-185: sets model.phi / ptS / tS / likelihood, returns (model, dataStruct, valid=1)."""
+    ctx = context_for(dataStruct, TD_parameters)
+    r = ctx.evaluate(model.xCell, model.yCell, model.zCell, model.zeta)
+    model.phi = r["phi"]
+    model.likelihood = r["likelihood"]
+    if TD_parameters.debug_prior != 1:  # :134-136 returns before ptS / tS are touched
+        model.ptS = r["ptS"].copy()
+        model.tS = dataStruct.tS  # alias, :175
+    return model, dataStruct, 1
+
+
+def build_starting(TD_parameters: parameters, dataStruct: DataStruct, seed: int = 20260000, chain: int = 0):
+    """MCsub.jl:76-121 with the device Philox stream of chain `chain`."""
+    ctx = context_for(dataStruct, TD_parameters)
+    ch = Chains(ctx, 1, chain_id0=chain, seed=seed, hist_cap=0)
+    ch.build_starting()
+    st = ch.state()
+    k = int(st["K"][0])
+    model = Model(float(k), st["cells"][0, 0, :k].copy(), st["cells"][0, 1, :k].copy(), st["cells"][0, 2, :k].copy(),
+                  st["cells"][0, 3, :k].copy(), float(st["phi"][0]), st["ptS"][0].copy(), dataStruct.tS,
+                  ctx.evaluate(st["cells"][0, 0, :k], st["cells"][0, 1, :k], st["cells"][0, 2, :k], st["cells"][0, 3, :k])["likelihood"],
+                  -1, -1, -1.0, -1.0)
+    ch.close()
+    return model, dataStruct, 1
+
+
+def history_to_models(hist: dict, dataStruct: DataStruct, likelihood: float, reference_aliasing: bool = False):
+    """Packed history -> Vector{Vector{Model}} as `plot_model_hist` consumes it (MCsub.jl:762-767).
+    reference_aliasing=True reproduces the stored action/accept of the reference (next iteration's action, accept = 0:
+    TD_inversion_function.jl:73-74 mutate the object already pushed at :280)."""
+    out = []
+    for c in range(len(hist["n_hist"])):
+        ms = []
+        for j in range(min(int(hist["n_hist"][c]), hist["K"].shape[1])):
+            k = int(hist["K"][c, j])
+            cl = hist["cells"][c, j]
+            action = int(hist["next_action"][c, j]) if reference_aliasing and hist["next_action"][c, j] > 0 else int(hist["action"][c, j])
+            accept = 0 if reference_aliasing else int(hist["accept"][c, j])
+            ms.append(Model(float(k), cl[0, :k].copy(), cl[1, :k].copy(), cl[2, :k].copy(), cl[3, :k].copy(), float(hist["phi"][c, j]),
+                            hist["ptS"][c, j].copy() if hist["ptS"] is not None else np.zeros(1), dataStruct.tS, likelihood,
+                            action, accept, -1.0, -1.0))
+        out.append(ms)
+    return out
+
+
+def run_chains(TD_parameters: parameters, dataStruct: DataStruct, chains, seed: int = 20260000, device: int = 0,
+               reference_aliasing: bool = False):
+    """Replaces `pmap(x -> TD_inversion_function(TD_parameters, dataStruct, x), 1:n_chains)` (main_inversion.jl:15):
+    all chains of `chains` (an iterable of consecutive chain numbers) run batched on one GPU."""
+    chains = list(chains)
+    assert chains == list(range(chains[0], chains[0] + len(chains))), "chains must be consecutive"
+    ctx = context_for(dataStruct, TD_parameters, device)
+    ch = Chains(ctx, len(chains), chain_id0=chains[0], seed=seed)
+    ch.build_starting()  # TD_inversion_function.jl:43-45
+    ch.run(int(TD_parameters.n_iter))  # :70
+    hist = ch.history()
+    like = ctx.evaluate(*[hist["cells"][0, 0, a, :max(int(hist["K"][0, 0]), 1)] for a in range(4)])["likelihood"] if TD_parameters.debug_prior != 1 else 1.0
+    out = history_to_models(hist, dataStruct, like, reference_aliasing)
+    ch.close()
+    return out
+
+
+def TD_inversion_function(TD_parameters: parameters, dataStruct1: DataStruct, chain: int, seed: int = 20260000):  # noqa: N802
+    """TD_inversion_function.jl:7-305 for one chain -> model_hist (list of Model).  Prefer run_chains() for many."""
+    return run_chains(TD_parameters, dataStruct1, [chain], seed=seed)[0]

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): cell indices bit-exact; t* and phi within 1e-9 relative (FP64); accept/reject
+decisions identical on replayed proposal streams.  The oracle sums t*/phi left to right, the device uses its
+canonical tree order, hence a tolerance on the sums (never on the indices).
+"""
+import numpy as np
+import pytest
+
+from conftest import box_of, random_model, random_ragged
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _orc(ds, p, **kw):
+    import oracle as O
+    return O.make_params(box_of(ds), sig=p.sig, zeta_scale=p.zeta_scale, max_sig=p.max_sig, n_iter=p.n_iter, burn_in=p.burn_in,
+                         keep_each=p.keep_each, min_cells=p.min_cells, max_cells=p.max_cells, prior=p.prior,
+                         debug_prior=p.debug_prior, **kw), O.Data(ds.rayX, ds.rayY, ds.rayZ, ds.rayL, ds.rayU, ds.tS, ds.allSig)
+
+
+def _flat_owners(own_mR, ctx):
+    """oracle owners [m, R] -> flat CSR order used by the C ABI."""
+    off = ctx.ray_offsets()
+    return np.concatenate([own_mR[:off[i + 1] - off[i], i] for i in range(ctx.R)]) if ctx.R else np.zeros(0, np.int32)
+
+
+@pytest.fixture(scope="module")
+def tonga_ctx(tonga):
+    from tonga_b200.api import Context
+    ds, p = tonga
+    return Context(ds, p), ds, p
+
+
+def _close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + 1e-300)
+
+
+@pytest.mark.parametrize("K", [1, 5, 20, 100])
+def test_evaluate_tonga381(tonga_ctx, K):
+    import oracle as O
+    ctx, ds, p = tonga_ctx
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(100 + K)
+    x, y, z, zeta = random_model(rng, K, box_of(ds))
+    ref = O.evaluate(op, od, x, y, z, zeta, want_owners=True)
+    got = ctx.evaluate(x, y, z, zeta)
+    Kb, cells = np.array([K], np.int32), np.stack([x, y, z, zeta])[None]
+    gb = ctx.evaluate_batch(Kb, cells, want_owners=True)
+    assert np.array_equal(gb["owners"][0], _flat_owners(ref["owners"], ctx)), "owners must be bit-exact"
+    assert _close(got["ptS"], ref["ptS"]) and _close(gb["ptS"][0], ref["ptS"])
+    assert _close(got["phi"], ref["phi"]) and gb["phi"][0] == got["phi"]
+    assert _close(got["likelihood"], ref["likelihood"], 1e-12)
+    assert _close(got["loglik_gauss"], ref["loglik_gauss"])
+
+
+def test_evaluate_batch_many_models(tonga_ctx):
+    import oracle as O
+    ctx, ds, p = tonga_ctx
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(7)
+    models = [random_model(rng, int(k), box_of(ds)) for k in rng.integers(1, 101, 24)]
+    from tonga_b200.api import pack_models
+    K, cells = pack_models(models, Kcap=104)
+    noise = rng.uniform(0.5, 2.0, len(models))
+    noise[:4] = 1.0
+    gb = ctx.evaluate_batch(K, cells, noise=noise, want_owners=True)
+    for i, mdl in enumerate(models):
+        ref = O.evaluate(op, od, *mdl, noise=noise[i], want_owners=True)
+        assert np.array_equal(gb["owners"][i], _flat_owners(ref["owners"], ctx))
+        assert _close(gb["ptS"][i], ref["ptS"]) and _close(gb["phi"][i], ref["phi"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_evaluate_random_ragged(seed):
+    import oracle as O
+    from tonga_b200.api import Context
+    ds, p = random_ragged(seed, R=37 + 11 * seed, m=9 + 30 * seed)
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(seed)
+    for K in (1, 3, 17, 64):
+        mdl = random_model(rng, K, box_of(ds))
+        ref = O.evaluate(op, od, *mdl, want_owners=True)
+        gb = ctx.evaluate_batch(np.array([K], np.int32), np.stack(mdl)[None], want_owners=True)
+        assert np.array_equal(gb["owners"][0], _flat_owners(ref["owners"], ctx))
+        assert _close(gb["ptS"][0], ref["ptS"]) and _close(gb["phi"][0], ref["phi"])
+    ctx.close()
+
+
+def test_evaluate_large_K_uses_bulk_copy(tonga_ctx):
+    """K = 2000 nuclei (BASELINE config 3 regime): 64 KB of nuclei staged by one TMA bulk copy."""
+    import oracle as O
+    ctx, ds, p = tonga_ctx
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(5)
+    mdl = random_model(rng, 2000, box_of(ds))
+    ref = O.evaluate(op, od, *mdl, want_owners=True)
+    gb = ctx.evaluate_batch(np.array([2000], np.int32), np.stack(mdl)[None], want_owners=True)
+    assert np.array_equal(gb["owners"][0], _flat_owners(ref["owners"], ctx))
+    assert _close(gb["ptS"][0], ref["ptS"]) and _close(gb["phi"][0], ref["phi"])
+
+
+def test_v_nearest_kats():
+    """tie -> lowest index; nothing within sqrt(1e9) -> 0.0; single nucleus; NaN trim."""
+    import oracle as O
+    from tonga_b200.api import Context, v_nearest
+    ctx = Context(None)
+    # exact tie between nuclei 1 and 2 (mirror images), nucleus 0 farther
+    mx, my, mz, mv = np.array([9.0, 1.0, -1.0]), np.zeros(3), np.zeros(3), np.array([7.0, 11.0, 13.0])
+    out, idx = ctx.interpolate(mx, my, mz, mv, [0.0], [0.0], [0.0])
+    assert idx[0] == 1 and out[0] == 11.0
+    assert O.v_nearest(0.0, 0.0, 0.0, mx, my, mz, mv) == (11.0, 1)
+    # all nuclei farther than sqrt(1e9) km: v = 0.0 (MCsub.jl:249-250)
+    out, idx = ctx.interpolate(np.array([4e4]), np.zeros(1), np.zeros(1), np.array([5.0]), [0.0], [0.0], [0.0])
+    assert out[0] == 0.0 and idx[0] == -1
+    assert O.v_nearest(0.0, 0.0, 0.0, np.array([4e4]), np.zeros(1), np.zeros(1), np.array([5.0])) == (0.0, -1)
+    # single nucleus
+    assert v_nearest(1.0, 2.0, 3.0, [0.0], [0.0], [0.0], [42.0]) == 42.0
+    # NaN trim (MCsub.jl:312-316) and slice broadcast (:317-322)
+    X = np.array([0.0, 1.0, 2.0, np.nan, 5.0])
+    out, idx = ctx.interpolate(mx, my, mz, mv, X, [0.0], [0.0])
+    ro, ri = O.interpolation(mx, my, mz, mv, X, [0.0], [0.0])
+    assert len(out) == 3 and np.array_equal(out, ro) and np.array_equal(idx, ri)
+    # random points / nuclei
+    rng = np.random.default_rng(3)
+    mx, my, mz, mv = rng.normal(size=(4, 57)) * 100
+    X, Y, Z = rng.normal(size=(3, 1000)) * 100
+    out, idx = ctx.interpolate(mx, my, mz, mv, X, Y, Z)
+    ro, ri = O.interpolation(mx, my, mz, mv, X, Y, Z)
+    assert np.array_equal(idx, ri) and np.array_equal(out, ro)
+    ctx.close()
+
+
+def _start_models(rng, n, ds, kmin=5, kmax=40):
+    return [random_model(rng, int(k), box_of(ds)) for k in rng.integers(kmin, kmax + 1, n)]
+
+
+def _oracle_generate(op, od, mdl, n_iter, seed, hist_cap=0):
+    import oracle as O
+    mb = O.ModelBuf(op.max_cells + 1, od.R).set(*mdl)
+    assert O.lib().orc_evaluate(op, od.c, mb.c, None, None) == 1
+    g = O.rng(seed)
+    return O.chain_run(op, od, mb, n_iter, g=g, hist_cap=hist_cap), mb
+
+
+@pytest.mark.parametrize("prior", [1, 2, 3])
+def test_replay_oracle_stream_on_device(tonga, prior):
+    """Oracle draws the proposals; the device replays them: identical accept/reject, K, final model; phi to 1e-9."""
+    import copy
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.prior = prior
+    p.n_iter, p.burn_in, p.keep_each = 400.0, 100.0, 10.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(11 + prior)
+    n, n_iter = 6, 400
+    models = _start_models(rng, n, ds)
+    runs = [_oracle_generate(op, od, models[c], n_iter, 1000 + c, hist_cap=64) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n, hist_cap=64)
+    K, cells = pack_models(models, Kcap=ch.KC)
+    ch.set_models(K, cells)
+    out = ch.run(n_iter, recs=recs, trace=True)
+    st = ch.state(want_owners=True)
+    hist = ch.history()
+    for c, (r, mb) in enumerate(runs):
+        assert np.array_equal(out["accept"][c], r.accept), f"accept/reject sequence differs (chain {c})"
+        assert np.array_equal(out["K"][c], r.K)
+        assert _close(out["phi"][c], r.phi)
+        k = mb.K
+        assert st["K"][c] == k
+        for a, ref in enumerate(mb.cells()):
+            assert np.array_equal(st["cells"][c, a, :k], ref), "final nuclei must be bit-identical"
+        assert _close(st["ptS"][c], mb.ptS[:od.R])
+        # thinning (TD_inversion_function.jl:275-281)
+        assert hist["n_hist"][c] == r.n_hist == 30
+        assert np.array_equal(hist["K"][c, :r.n_hist], r.hist_K[:r.n_hist])
+        assert np.array_equal(hist["iter"][c, :r.n_hist], r.hist_iter[:r.n_hist])
+        assert np.array_equal(hist["action"][c, :r.n_hist], r.hist_action[:r.n_hist])
+        assert np.array_equal(hist["accept"][c, :r.n_hist], r.hist_accept[:r.n_hist])
+        assert _close(hist["phi"][c, :r.n_hist], r.hist_phi[:r.n_hist])
+        for j in range(r.n_hist):
+            kj = r.hist_K[j]
+            assert np.array_equal(hist["cells"][c, j, :, :kj], r.hist_cells[j, :, :kj])
+        assert _close(hist["ptS"][c, :r.n_hist], r.hist_ptS[:r.n_hist])
+    mm, dphi, dts = ch.verify()
+    assert (mm, dphi, dts) == (0, 0.0, 0.0), "incremental state must equal a full evaluate bit for bit"
+    ch.close(); ctx.close()
+
+
+def test_device_stream_replayed_by_oracle(tonga):
+    """The device draws (Philox) and records; the oracle replays: identical decisions and final models."""
+    import copy
+    import oracle as O
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 600.0, 300.0, 10.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    n, n_iter = 8, 600
+    ch = Chains(ctx, n, chain_id0=3, seed=42)
+    ch.build_starting()
+    st0 = ch.state()
+    out = ch.run(n_iter, record=True, trace=True)
+    st1 = ch.state()
+    assert set(np.unique(out["recs"]["action"])) <= {1, 2, 3, 4}
+    for c in range(n):
+        k0 = st0["K"][c]
+        mb = O.ModelBuf(op.max_cells + 1, od.R).set(*[st0["cells"][c, a, :k0] for a in range(4)])
+        assert O.lib().orc_evaluate(op, od.c, mb.c, None, None) == 1
+        assert _close(mb.c.phi, st0["phi"][c])
+        r = O.chain_run(op, od, mb, n_iter, recs=out["recs"][c])
+        assert np.array_equal(r.accept, out["accept"][c])
+        assert np.array_equal(r.K, out["K"][c])
+        assert _close(r.phi, out["phi"][c])
+        k1 = mb.K
+        assert k1 == st1["K"][c]
+        for a, ref in enumerate(mb.cells()):
+            assert np.array_equal(st1["cells"][c, a, :k1], ref)
+    it, counts = ch.stats()
+    assert it == n_iter and counts[:, 0].sum() == n * n_iter
+    assert (counts[:, 1] <= counts[:, 0]).all() and counts[:, 1].sum() == out["accept"].sum()
+    assert ch.verify() == (0, 0.0, 0.0)
+    ch.close(); ctx.close()
+
+
+def test_incremental_equals_full_long_run(tonga_ctx):
+    """after thousands of birth/death/change/move proposals on many chains the incrementally
+    maintained owners / t* / phi equal a from-scratch evaluate, bit for bit."""
+    from tonga_b200.api import Chains
+    ctx, ds, p = tonga_ctx
+    ch = Chains(ctx, 64, seed=7, hist_cap=0)
+    ch.build_starting()
+    for _ in range(3):
+        ch.run(1500)
+        assert ch.verify() == (0, 0.0, 0.0)
+    it, counts = ch.stats()
+    acc = counts[:, 1].sum(0) / np.maximum(counts[:, 0].sum(0), 1)
+    assert (counts[:, 0].sum(0)[:4] > 0).all() and counts[:, 0].sum(0)[4] == 0
+    assert 0.01 < acc[:4].min() and acc[:4].max() < 0.99
+    st = ch.state()
+    assert (st["K"] >= p.min_cells).all() and (st["K"] <= p.max_cells).all()
+    ch.close()
+
+
+def test_replay_edge_cases(tonga):
+    """A-priori rejections (birth at max_cells, death at min_cells, zeta out of bounds, move out of the box) and exact
+    behaviour at the K limits, on a small random ragged set with tiny K limits."""
+    import copy
+    import oracle as O
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = random_ragged(5, R=29, m=23)
+    p = copy.copy(p0)
+    p.min_cells, p.max_cells = 2, 6
+    p.n_iter, p.burn_in, p.keep_each = 1500.0, 0.0, 50.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(2)
+    n, n_iter = 5, 1500
+    models = _start_models(rng, n, ds, 2, 6)
+    runs = [_oracle_generate(op, od, models[c], n_iter, 50 + c) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n)
+    ch.set_models(*pack_models(models, Kcap=ch.KC))
+    out = ch.run(n_iter, recs=recs, trace=True)
+    for c, (r, mb) in enumerate(runs):
+        assert np.array_equal(out["accept"][c], r.accept) and np.array_equal(out["K"][c], r.K)
+        assert _close(out["phi"][c], r.phi)
+    allK = np.concatenate([r.K for r, _ in runs])
+    assert allK.min() == 2 and allK.max() == 6  # both limits were hit
+    assert ch.verify() == (0, 0.0, 0.0)
+    ch.close(); ctx.close()
+
+
+def test_sigma_move_extension(tonga):
+    """Action 5 (hierarchical noise; dead code in the reference, spec in DESIGN.md): oracle stream replayed on device."""
+    import copy
+    import oracle as O
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.max_sig = 3.0
+    ctx = Context(ds, p, n_actions=5)
+    op, od = _orc(ds, p, n_actions=5)
+    rng = np.random.default_rng(21)
+    n, n_iter = 4, 500
+    models = _start_models(rng, n, ds)
+    runs = [_oracle_generate(op, od, models[c], n_iter, 900 + c) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    assert (recs["action"] == 5).any()
+    ch = Chains(ctx, n)
+    ch.set_models(*pack_models(models, Kcap=ch.KC))
+    out = ch.run(n_iter, recs=recs, trace=True)
+    st = ch.state()
+    for c, (r, mb) in enumerate(runs):
+        assert np.array_equal(out["accept"][c], r.accept) and np.array_equal(out["K"][c], r.K)
+        assert _close(out["phi"][c], r.phi)
+        assert st["noise"][c] == mb.c.noise
+    assert ch.verify() == (0, 0.0, 0.0)
+    ch.close(); ctx.close()
+
+
+def test_debug_prior_mode(tonga):
+    """debug_prior = 1 (MCsub.jl:134-136): phi == 1 always, so the chain samples the prior."""
+    import copy
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.debug_prior = 1
+    ctx = Context(ds, p)
+    r = ctx.evaluate([1.0], [2.0], [3.0], [4.0])
+    assert r["phi"] == 1.0 and r["likelihood"] == 1.0
+    ctx.close()
+
+
+def test_reference_named_api(tonga):
+    import copy
+    from tonga_b200 import api
+    from tonga_b200.structs import Model
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 300.0, 100.0, 10.0
+    rng = np.random.default_rng(0)
+    x, y, z, zeta = random_model(rng, 12, box_of(ds))
+    mdl = Model(12.0, x, y, z, zeta)
+    mdl, ds2, valid = api.evaluate(mdl, ds, p)
+    assert valid == 1 and ds2 is ds and mdl.ptS.shape == (381,) and mdl.tS is ds.tS and mdl.phi > 0
+    zs = api.Interpolation(p, mdl, ds.rayX[:, 0], ds.rayY[:, 0], ds.rayZ[:, 0])
+    n0 = int((~np.isnan(ds.rayX[:, 0])).sum())
+    assert len(zs) == n0
+    hists = api.run_chains(p, ds, range(1, 4))
+    assert len(hists) == 3 and all(len(h) == 20 for h in hists)
+    for h in hists:
+        for m_ in h:
+            assert p.min_cells <= m_.nCells <= p.max_cells and len(m_.xCell) == int(m_.nCells)
+            assert (m_.zeta > 0).all() and (m_.zeta < p.zeta_scale).all()
+    one = api.TD_inversion_function(p, ds, 2)
+    assert len(one) == 20 and one[0].phi == hists[1][0].phi  # chain 2's stream does not depend on the batch it runs in
+    m0, _, v = api.build_starting(p, ds, chain=1)
+    assert v == 1 and p.min_cells <= m0.nCells <= p.max_cells
