@@ -1,5 +1,6 @@
 // ctx.cu -- geometry context of libtonga_b200.so: the one-time flatten of the reference's DataStruct ray arrays
 // (DefStruct.jl:5-30) into device-resident SoA arrays, plus error plumbing.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -92,21 +93,37 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     }
     const int64_t P = ray_off[R];
     const int64_t Ppad = ((P + TG_PT_TILE - 1) / TG_PT_TILE) * TG_PT_TILE + (P == 0 ? TG_PT_TILE : 0);
+    const int Rp = (R + 1) & ~1;
+    // device order: rays sorted by length, longest first (stable), so that the 32 rays a warp integrates finish together
+    std::vector<int32_t> ray_orig(R);
+    for (int i = 0; i < R; i++) ray_orig[i] = i;
+    std::stable_sort(ray_orig.begin(), ray_orig.end(), [&](int a, int b) {
+        return (ray_off[a + 1] - ray_off[a]) > (ray_off[b + 1] - ray_off[b]);
+    });
+    std::vector<int32_t> sray_off(R + 1, 0);
+    for (int rs = 0; rs < R; rs++) sray_off[rs + 1] = sray_off[rs] + (ray_off[ray_orig[rs] + 1] - ray_off[ray_orig[rs]]);
     const double qnan = std::nan("");
-    std::vector<double> px(Ppad, qnan), py(Ppad, qnan), pz(Ppad, qnan), dt(Ppad, 0.0);
-    std::vector<int32_t> rayid(Ppad, 0);
+    std::vector<double> px(Ppad, qnan), py(Ppad, qnan), pz(Ppad, qnan);
+    const int nsegmax = m > 1 ? m - 1 : 1;
+    std::vector<double> dtT((size_t)nsegmax * (Rp > 0 ? Rp : 2), 0.0);
+    std::vector<int32_t> rayid(Ppad, 0), point_orig(Ppad, -1);
+    std::vector<double> tS_s(R), sig_s(R);
     int64_t S = 0;
-    for (int i = 0; i < R; i++) {
+    for (int rs = 0; rs < R; rs++) {
+        const int i = ray_orig[rs];
         const int np = ray_off[i + 1] - ray_off[i];
+        tS_s[rs] = tS[i];
+        sig_s[rs] = allSig[i];
         for (int k = 0; k < np; k++) {
-            const size_t src = (size_t)i * m + k, dst = (size_t)ray_off[i] + k;
+            const size_t src = (size_t)i * m + k, dst = (size_t)sray_off[rs] + k;
             px[dst] = rayX[src];
             py[dst] = rayY[src];
             pz[dst] = rayZ[src];
-            rayid[dst] = i;
+            rayid[dst] = rs;
+            point_orig[dst] = ray_off[i] + k;
             if (k < np - 1) {
-                const size_t s = (size_t)i * (m - 1) + k;
-                dt[dst] = rayL[s] * rayU[s];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction possible)
+                const size_t sg = (size_t)i * (m - 1) + k;
+                dtT[(size_t)k * Rp + rs] = rayL[sg] * rayU[sg];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction)
                 S++;
             }
         }
@@ -120,8 +137,8 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
         int r0 = 0;
         while (r0 < R) {
             int r1 = r0;
-            while (r1 < R && ray_off[r1 + 1] - ray_off[r0] <= tile_pts) r1++;
-            tiles.push_back({r0, r1, ray_off[r0], ray_off[r1]});
+            while (r1 < R && sray_off[r1 + 1] - sray_off[r0] <= tile_pts) r1++;
+            tiles.push_back({r0, r1, sray_off[r0], sray_off[r1]});
             r0 = r1;
         }
     }
@@ -136,6 +153,9 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     ctx->Ppad = Ppad;
     ctx->max_npts = max_npts;
     ctx->h_ray_off = ray_off;
+    ctx->h_ray_orig = ray_orig;
+    ctx->h_point_orig = point_orig;
+    ctx->Rp = Rp;
     ctx->n_tiles = (int)tiles.size();
     ctx->tile_pts = tile_pts;
     cudaDeviceProp prop;
@@ -167,11 +187,13 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     chk(upload(&ctx->d_px, px, ctx->stream));
     chk(upload(&ctx->d_py, py, ctx->stream));
     chk(upload(&ctx->d_pz, pz, ctx->stream));
-    chk(upload(&ctx->d_dt, dt, ctx->stream));
+    chk(upload(&ctx->d_dtT, dtT, ctx->stream));
     chk(upload(&ctx->d_rayid, rayid, ctx->stream));
-    chk(upload(&ctx->d_ray_off, ray_off, ctx->stream));
-    chk(upload(&ctx->d_tS, std::vector<double>(tS, tS + R), ctx->stream));
-    chk(upload(&ctx->d_sig, std::vector<double>(allSig, allSig + R), ctx->stream));
+    chk(upload(&ctx->d_ray_off, sray_off, ctx->stream));
+    chk(upload(&ctx->d_ray_orig, ray_orig, ctx->stream));
+    chk(upload(&ctx->d_point_orig, point_orig, ctx->stream));
+    chk(upload(&ctx->d_tS, tS_s, ctx->stream));
+    chk(upload(&ctx->d_sig, sig_s, ctx->stream));
     chk(upload(&ctx->d_tiles, tiles, ctx->stream));
     if (rc == TONGA_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = tg::fail(TONGA_ERR_CUDA, "tonga_create: upload failed");
     if (rc != TONGA_OK) {
@@ -186,8 +208,9 @@ extern "C" void tonga_destroy(tonga_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dt);
-    cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_tS); cudaFree(ctx->d_sig);
+    cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dtT);
+    cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_ray_orig); cudaFree(ctx->d_point_orig);
+    cudaFree(ctx->d_tS); cudaFree(ctx->d_sig);
     cudaFree(ctx->d_tiles);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -6,7 +6,7 @@
 // Kernel 1 (tg_eval_kernel): CTA = (ray tile, model).  The model's nuclei are staged in shared memory; phase 1 is a
 // flat, fully occupied pass over the tile's points (4 points per thread held in registers while the nucleus loop
 // broadcasts each nucleus from shared memory) that produces the owner of every point; phase 2 integrates t* with one
-// warp per ray in the canonical order.  Kernel 2 (tg_phi_kernel) reduces the per-ray misfit terms in the canonical
+// thread per (length-sorted) ray in the canonical left-to-right order.  Kernel 2 (tg_phi_kernel) reduces the per-ray misfit terms in the canonical
 // order.  FP64 throughout, no FMA contraction in the distance (bit-exact owners).
 #include <cmath>
 #include <cstring>
@@ -48,8 +48,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 __global__ void __launch_bounds__(EVAL_THREADS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
-               const double *__restrict__ dt, const int32_t *__restrict__ ray_off, int R, int64_t P, int64_t Ppad,
-               int tile_pts, double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8) {
+               const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
+               const int32_t *__restrict__ point_orig, int R, int Rp, int64_t P, int64_t Ppad, int tile_pts,
+               double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int model = blockIdx.y;
     const Tile tile = tiles[blockIdx.x];
@@ -107,20 +108,19 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
             if (j < npts) {
                 s_owner[j] = bi[q] < 0 ? (uint16_t)TG_NONE16 : (uint16_t)bi[q];
                 const int64_t p = tile.p0 + j;
-                if (owners32) owners32[(size_t)model * P + p] = bi[q];
+                if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi[q];  // caller's flat order
                 if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
             }
         }
     }
     __syncthreads();
 
-    // ---- phase 2: t* per ray, one warp per ray, canonical order (MCsub.jl:147,153/159)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EVAL_THREADS / 32;
+    // ---- phase 2: t* per ray, one thread per ray (rays are length-sorted), left-to-right sum (MCsub.jl:147,153/159)
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16 ? 0.0 : s_zeta[o]; };
-    for (int r = tile.r0 + warp; r < tile.r1; r += nwarps) {
+    for (int r = tile.r0 + threadIdx.x; r < tile.r1; r += EVAL_THREADS) {
         const int q0 = ray_off[r], n = ray_off[r + 1] - q0;
-        const double t = ray_tstar_canonical<uint16_t>(s_owner - tile.p0, dt, q0, n, lane, zeta_of);
-        if (lane == 0) ptS[(size_t)model * R + r] = t;
+        const double t = ray_tstar_seq<uint16_t>(s_owner - tile.p0, dtT, Rp, r, q0, n, zeta_of);
+        ptS[(size_t)model * R + ray_orig[r]] = t;  // caller's ray order
     }
 }
 
@@ -132,7 +132,8 @@ __global__ void tg_owner_pad_kernel(uint8_t *owners8, int64_t P, int64_t Ppad, i
 }
 
 __global__ void __launch_bounds__(TG_PHI_LANES)
-tg_phi_kernel(int R, const double *__restrict__ ptS, const double *__restrict__ tS, const double *__restrict__ sig,
+tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, const int32_t *__restrict__ ray_orig,
+              const double *__restrict__ tS, const double *__restrict__ sig /* sorted ray order */,
               const double *__restrict__ noise, double *__restrict__ phi, int debug_prior) {
     __shared__ double scratch[4];
     const int model = blockIdx.x;
@@ -142,7 +143,7 @@ tg_phi_kernel(int R, const double *__restrict__ ptS, const double *__restrict__ 
     }
     const double nz = noise ? noise[model] : 1.0;
     const double *t = ptS + (size_t)model * R;
-    const double v = phi_canonical_128(R, threadIdx.x, scratch, [&](int r) { return misfit_term(t[r], tS[r], sig[r], nz); });
+    const double v = phi_canonical_128(R, threadIdx.x, scratch, [&](int r) { return misfit_term(t[ray_orig[r]], tS[r], sig[r], nz); });
     if (threadIdx.x == 0) phi[model] = v;
 }
 
@@ -156,8 +157,9 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
-                                                                  ctx->d_pz, ctx->d_dt, ctx->d_ray_off, ctx->R, ctx->P,
-                                                                  ctx->Ppad, ctx->tile_pts, ptS_dev, owners32_dev, owners8_dev);
+                                                                  ctx->d_pz, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
+                                                                  ctx->R, ctx->Rp, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
+                                                                  owners32_dev, owners8_dev);
         TG_CUDA(cudaGetLastError());
     }
     if (owners8_dev && ctx->Ppad > ctx->P) {
@@ -166,7 +168,7 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         TG_CUDA(cudaGetLastError());
     }
     if (phi_dev) {
-        tg_phi_kernel<<<nModels, TG_PHI_LANES, 0, ctx->stream>>>(ctx->R, ptS_dev, ctx->d_tS, ctx->d_sig, noise_dev, phi_dev,
+        tg_phi_kernel<<<nModels, TG_PHI_LANES, 0, ctx->stream>>>(ctx->R, ptS_dev, ctx->d_ray_orig, ctx->d_tS, ctx->d_sig, noise_dev, phi_dev,
                                                                 ctx->prm.debug_prior);
         TG_CUDA(cudaGetLastError());
     }

@@ -28,608 +28,11 @@ namespace tg {
 constexpr int ST = 128;  // threads per chain CTA (4 warps) == TG_PHI_LANES
 static_assert(ST == TG_PHI_LANES, "the canonical phi reduction is defined over 128 lanes");
 
-struct SamplerArgs {
-    // geometry
-    const double *px, *py, *pz, *dt, *tS, *sig;
-    const int32_t *rayid, *ray_off;
-    int R, Rp, KC;
-    int P, Ppad;
-    tonga_params prm;
-    // chain state (global)
-    int32_t *K;
-    double *cells;  // [n][4][KC]
-    double *phi, *noise, *beta;
-    uint8_t *owner;  // [n][Ppad]
-    double *tstar;   // [n][Rp]
-    long long *counts;  // [n][3][5] proposed / accepted / evaluated
-    int32_t *pending_slot;  // [n] history slot awaiting its next_action, or -1
-    // run
-    long long iter0, nIter;
-    int mode;  // 0 generate, 1 replay
-    const tonga_proposal *recs_in;
-    tonga_proposal *recs_out;
-    int8_t *tr_accept;
-    double *tr_phi;
-    int32_t *tr_K;
-    unsigned long long seed;
-    long long chain_id0;
-    // history
-    int hist_cap;
-    int32_t *n_hist;
-    long long *model_num;
-    int32_t *hist_K;
-    double *hist_cells, *hist_phi, *hist_ptS;
-    long long *hist_iter;
-    int32_t *hist_action, *hist_accept, *hist_next;
-};
+}  // namespace tg
 
-struct Prop {  // proposal of the current iteration, broadcast through shared memory
-    int action, idx, do_eval, valid, accept, K, keep, pad;
-    double x, y, z, zeta, u;
-    double aux;    // birth: czeta (:81); death: zetanew (:146)
-    double phi, phin, noise, beta;
-};
+#include "sampler_kernel.cuh"
 
-struct SmemLayout {
-    size_t o_owner, o_mask, o_tstar, o_tnew, o_dirty, o_nuc, o_zlut, o_scr, o_prop, o_bar, total;
-};
-__host__ __device__ inline SmemLayout smem_layout(int Ppad, int Rp, int KC) {
-    SmemLayout L;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    L.o_owner = take((size_t)Ppad);
-    L.o_mask = take((size_t)Ppad / 8);
-    L.o_tstar = take(8 * (size_t)Rp);
-    L.o_tnew = take(8 * (size_t)Rp);
-    L.o_dirty = take(4 * (size_t)((Rp + 31) / 32));
-    L.o_nuc = take(8 * 4 * (size_t)KC);
-    L.o_zlut = take(8 * 256);
-    L.o_scr = take(8 * 8);
-    L.o_prop = take(sizeof(Prop));
-    L.o_bar = take(16);
-    L.total = o;
-    return L;
-}
-
-// ---- TMA bulk copies (SASS: UBLKCP) -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(dst)),
-                 "l"(src), "r"(bytes), "r"(s2u(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s2u(src)), "r"(bytes) : "memory");
-}
-
-// ---- warp-cooperative v_nearest (MCsub.jl:247-263) over the nuclei in shared memory, skipping index `skip` ---------
-__device__ __forceinline__ int warp_nearest(const double *nx, const double *ny, const double *nz, int K, int skip,
-                                            double x, double y, double z, int lane) {
-    double best = 1e9;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < K; i += 32) {
-        if (i == skip) continue;
-        const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);
-        if (d < best) { best = d; bi = i; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
-    }
-    return bi == 0x7fffffff ? -1 : bi;
-}
-
-__device__ __forceinline__ double jl_min1(double a) {  // min([1 a]...) in Julia: NaN propagates
-    return (a != a) ? a : (a < 1.0 ? a : 1.0);
-}
-
-__device__ __forceinline__ void mark_dirty(uint32_t *dirty, const int32_t *__restrict__ rayid, int p) {
-    const int r = rayid[p];
-    atomicOr(&dirty[r >> 5], 1u << (r & 31));
-}
-
-__global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(a.Ppad, a.Rp, a.KC);
-    uint8_t *s_owner = smem + L.o_owner;
-    uint32_t *s_own32 = reinterpret_cast<uint32_t *>(s_owner);
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + L.o_mask);
-    double *s_tstar = reinterpret_cast<double *>(smem + L.o_tstar);
-    double *s_tnew = reinterpret_cast<double *>(smem + L.o_tnew);
-    uint32_t *s_dirty = reinterpret_cast<uint32_t *>(smem + L.o_dirty);
-    double *s_nx = reinterpret_cast<double *>(smem + L.o_nuc);
-    double *s_ny = s_nx + a.KC, *s_nz = s_ny + a.KC, *s_zeta = s_nz + a.KC;
-    double *s_zlut = reinterpret_cast<double *>(smem + L.o_zlut);
-    double *s_scr = reinterpret_cast<double *>(smem + L.o_scr);
-    Prop *s_prop = reinterpret_cast<Prop *>(smem + L.o_prop);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.o_bar);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chain = blockIdx.x;
-    const int KC = a.KC, R = a.R;
-    const int nOwnWords = a.Ppad / 4, nMaskWords = a.Ppad / 32, nDirtyWords = (a.Rp + 31) / 32;
-
-    // ---- load the chain state: three TMA bulk copies on one mbarrier
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s2u(s_bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t b_owner = (uint32_t)a.Ppad, b_ts = (uint32_t)(8 * a.Rp), b_nuc = (uint32_t)(32 * KC);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(s_bar)), "r"(b_owner + b_ts + b_nuc) : "memory");
-        bulk_load(s_owner, a.owner + (size_t)chain * a.Ppad, b_owner, s_bar);
-        bulk_load(s_tstar, a.tstar + (size_t)chain * a.Rp, b_ts, s_bar);
-        bulk_load(s_nx, a.cells + (size_t)chain * 4 * KC, b_nuc, s_bar);
-    }
-    for (int i = tid; i < nMaskWords; i += ST) s_mask[i] = 0u;
-    for (int i = tid; i < nDirtyWords; i += ST) s_dirty[i] = 0u;
-    {
-        asm volatile(
-            "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
-                s2u(s_bar))
-            : "memory");
-    }
-    __syncthreads();
-
-    int K = a.K[chain];
-    double phi = a.phi[chain];
-    double noise = a.noise[chain];
-    const double beta = a.beta[chain];
-    int n_hist = a.n_hist[chain];
-    long long model_num = a.model_num[chain];
-    int pending_slot = a.pending_slot[chain];
-    long long cnt_prop[5] = {0, 0, 0, 0, 0}, cnt_acc[5] = {0, 0, 0, 0, 0}, cnt_eval[5] = {0, 0, 0, 0, 0};  // thread 0 only
-
-    const tonga_params &pm = a.prm;
-    // TD_inversion_function.jl:22-23,30-32
-    const double sig_zeta = pm.zeta_scale * pm.sig / 100;
-    const double sig_sig = pm.max_sig * pm.sig / 100;
-    const double xr = (pm.sig / 100) * (pm.xmax - pm.xmin);
-    const double yr = (pm.sig / 100) * (pm.ymax - pm.ymin);
-    const double zr = (pm.sig / 100) * (pm.zmax - pm.zmin);
-    const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
-    const double PI = 3.141592653589793;
-    const unsigned long long gid = (unsigned long long)(a.chain_id0 + chain);
-    const Philox philox{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-
-    for (long long it = 0; it < a.nIter; it++) {
-        const long long iter = a.iter0 + it;
-        // ================================================================ A: proposal (warp 0, warp-uniform values)
-        if (warp == 0) {
-            Prop pr;
-            pr.do_eval = 0; pr.valid = 0; pr.accept = 0; pr.K = K; pr.keep = 0; pr.pad = 0;
-            pr.idx = 0; pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = 0.0;
-            pr.phi = phi; pr.phin = phi; pr.noise = noise; pr.beta = beta;
-            double uu[8];
-            if (a.mode == 0) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                if (lane < 4) philox((uint32_t)iter, (uint32_t)((unsigned long long)iter >> 32), (uint32_t)gid, (uint32_t)lane | ((uint32_t)(gid >> 32) << 8), w);
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
-                    const uint32_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
-                    uu[2 * s] = u53(w0, w1);
-                    uu[2 * s + 1] = u53(w2, w3);
-                }
-                int act = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
-                pr.action = act > nact ? nact : act;
-            } else {
-                const tonga_proposal rec = a.recs_in[(size_t)chain * a.nIter + it];
-                pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
-            }
-            // Box-Muller normals from (open) uniforms; only evaluated in generate mode
-            auto normal_pair = [&](double u1, double u2, double &n0, double &n1) {
-                const double rr = sqrt(-2.0 * log(u1 + 0x1.0p-54));
-                double sn, cs;
-                sincospi(2.0 * u2, &sn, &cs);
-                n0 = rr * cs;
-                n1 = rr * sn;
-            };
-            const int act = pr.action;
-            if (act == 1) {  // ---- birth :76-125
-                if (K < pm.max_cells) {
-                    if (a.mode == 0) {
-                        pr.x = uu[2] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
-                        pr.y = uu[3] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
-                        pr.z = uu[4] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
-                    }
-                    const int ci = warp_nearest(s_nx, s_ny, s_nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
-                    const double czeta = ci < 0 ? 0.0 : s_zeta[ci];
-                    pr.aux = czeta;
-                    if (a.mode == 0) {
-                        double n0, n1;
-                        normal_pair(uu[5], uu[6], n0, n1);
-                        pr.zeta = czeta + sig_zeta * n0;  // :82
-                        pr.u = uu[7];                     // :121
-                    }
-                    if (pm.prior == 1) pr.valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
-                    else if (pm.prior == 2) pr.valid = 1;
-                    else pr.valid = (pr.zeta > 0);  // :111
-                    pr.do_eval = pr.valid;
-                }
-            } else if (act == 2) {  // ---- death :126-181
-                if (K > pm.min_cells) {
-                    if (a.mode == 0) {
-                        int k = (int)floor(uu[1] * K);  // :128
-                        pr.idx = k >= K ? K - 1 : k;
-                        pr.u = uu[7];  // :176
-                    }
-                    const int kill = pr.idx;
-                    if (kill >= 0 && kill < K) {
-                        const int zi = warp_nearest(s_nx, s_ny, s_nz, K, kill, s_nx[kill], s_ny[kill], s_nz[kill], lane);  // :146
-                        pr.aux = zi < 0 ? 0.0 : s_zeta[zi];
-                        pr.valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
-                        pr.do_eval = pr.valid;
-                    }
-                }
-            } else if (act == 3) {  // ---- change :183-218
-                if (a.mode == 0) {
-                    int k = (int)floor(uu[1] * K);  // :184
-                    pr.idx = k >= K ? K - 1 : k;
-                    double n0, n1;
-                    normal_pair(uu[2], uu[3], n0, n1);
-                    pr.zeta = s_zeta[pr.idx] + sig_zeta * n0;  // :188
-                    pr.u = uu[7];                              // :214
-                }
-                if (pr.idx >= 0 && pr.idx < K) {
-                    if (pm.prior == 1) pr.valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
-                    else if (pm.prior == 2) pr.valid = 1;
-                    else pr.valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
-                    pr.do_eval = pr.valid;  // the reference evaluates first (:191) but discards the result when invalid
-                }
-            } else if (act == 4) {  // ---- move :220-251
-                if (K > 0) {
-                    if (a.mode == 0) {
-                        int k = (int)floor(uu[1] * K);  // :222
-                        pr.idx = k >= K ? K - 1 : k;
-                        double n0, n1, n2, n3;
-                        normal_pair(uu[2], uu[3], n0, n1);
-                        normal_pair(uu[4], uu[5], n2, n3);
-                        pr.x = s_nx[pr.idx] + xr * n0;  // :226
-                        pr.y = s_ny[pr.idx] + yr * n1;  // :227
-                        pr.z = s_nz[pr.idx] + zr * n2;  // :228
-                        pr.u = uu[7];                   // :247
-                    }
-                    if (pr.idx >= 0 && pr.idx < K)
-                        pr.valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
-                                    pr.z <= pm.zmax);  // :230-232
-                    pr.do_eval = pr.valid;
-                }
-            } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
-                if (a.mode == 0) {
-                    double n0, n1;
-                    normal_pair(uu[2], uu[3], n0, n1);
-                    pr.zeta = noise + sig_sig * n0;  // :254
-                    pr.u = uu[7];
-                }
-                pr.valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
-                pr.do_eval = pr.valid;
-            }
-            // zlut: owner byte -> zeta under the proposed model
-            if (pr.do_eval && act != 5) {
-                const double ztag = (act == 1) ? pr.zeta : (act == 4 ? s_zeta[pr.idx] : 0.0);
-                for (int o = lane; o < 128; o += 32) {
-                    double zv = (o < K) ? s_zeta[o] : 0.0;
-                    if (act == 3 && o == pr.idx) zv = pr.zeta;
-                    s_zlut[o] = zv;
-                    s_zlut[128 + o] = ztag;
-                }
-            }
-            if (lane == 0) {
-                *s_prop = pr;
-                if (a.mode == 0 && a.recs_out) {
-                    tonga_proposal rec;
-                    rec.action = pr.action; rec.idx = pr.idx; rec.x = pr.x; rec.y = pr.y; rec.z = pr.z; rec.zeta = pr.zeta; rec.u = pr.u;
-                    a.recs_out[(size_t)chain * a.nIter + it] = rec;
-                }
-                if (pending_slot >= 0) a.hist_next[(size_t)chain * a.hist_cap + pending_slot] = pr.action;
-            }
-        }
-        __syncthreads();
-        pending_slot = -1;
-        const int act = s_prop->action;
-        const int do_eval = s_prop->do_eval;
-        const int pidx = s_prop->idx;
-        double phin = phi;
-        int accepted = 0;
-
-        if (do_eval) {
-            if (act != 5) {
-                const double cx = s_prop->x, cy = s_prop->y, cz = s_prop->z;
-                // ======================================================== B: point pass
-                if (act == 1 || act == 4) {
-                    const int mv = (act == 4) ? pidx : -1;
-                    for (int w = tid; w < nOwnWords; w += ST) {
-                        uint32_t ow = s_own32[w];
-                        const double2 xa = *reinterpret_cast<const double2 *>(a.px + 4 * w), xb = *reinterpret_cast<const double2 *>(a.px + 4 * w + 2);
-                        const double2 ya = *reinterpret_cast<const double2 *>(a.py + 4 * w), yb = *reinterpret_cast<const double2 *>(a.py + 4 * w + 2);
-                        const double2 za = *reinterpret_cast<const double2 *>(a.pz + 4 * w), zb = *reinterpret_cast<const double2 *>(a.pz + 4 * w + 2);
-                        const double X[4] = {xa.x, xa.y, xb.x, xb.y}, Y[4] = {ya.x, ya.y, yb.x, yb.y}, Z[4] = {za.x, za.y, zb.x, zb.y};
-                        uint32_t tags = 0, mbits = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int o = (ow >> (8 * q)) & 0xFF;
-                            if (o == mv) {
-                                // move, type A: the point belongs to the moved nucleus -> rescan all nuclei (moved one at its new place)
-                                double best = 1e9;
-                                int bi = TG_OWNER_NONE;
-                                for (int i = 0; i < K; i++) {
-                                    const double d = (i == mv) ? dist2_exact(cx, cy, cz, X[q], Y[q], Z[q])
-                                                               : dist2_exact(s_nx[i], s_ny[i], s_nz[i], X[q], Y[q], Z[q]);
-                                    if (d < best) { best = d; bi = i; }
-                                }
-                                if (bi != mv) {
-                                    ow = (ow & ~(0xFFu << (8 * q))) | ((uint32_t)bi << (8 * q));
-                                    mbits |= 1u << q;
-                                }
-                            } else {
-                                const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], X[q], Y[q], Z[q]);
-                                const double d_c = dist2_exact(cx, cy, cz, X[q], Y[q], Z[q]);
-                                // birth: the new nucleus has the highest index -> strict <.  move: index mv also wins exact ties against o > mv.
-                                const bool sw = (d_c < d_o) || (act == 4 && d_c == d_o && mv < o && o != TG_OWNER_NONE);
-                                if (sw) tags |= 0x80u << (8 * q);
-                            }
-                        }
-                        if (tags | mbits) {
-                            s_own32[w] = ow | tags;
-                            if (mbits) atomicOr(&s_mask[w >> 3], mbits << ((w & 7) * 4));
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if ((tags >> (8 * q + 7) & 1u) | (mbits >> q & 1u)) mark_dirty(s_dirty, a.rayid, 4 * w + q);
-                        }
-                    }
-                } else if (act == 2) {
-                    const int kill = pidx;
-                    const uint32_t kk = (uint32_t)kill * 0x01010101u;
-                    for (int w = tid; w < nOwnWords; w += ST) {
-                        uint32_t ow = s_own32[w];
-                        const uint32_t eq = __vcmpeq4(ow, kk);
-                        if (eq) {
-                            uint32_t mbits = 0;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                if ((eq >> (8 * q)) & 1u) {
-                                    const int p = 4 * w + q;
-                                    const double x = a.px[p], y = a.py[p], z = a.pz[p];
-                                    double best = 1e9;
-                                    int bi = TG_OWNER_NONE;
-                                    for (int i = 0; i < K; i++) {
-                                        if (i == kill) continue;
-                                        const double d = dist2_exact(s_nx[i], s_ny[i], s_nz[i], x, y, z);
-                                        if (d < best) { best = d; bi = i; }
-                                    }
-                                    ow = (ow & ~(0xFFu << (8 * q))) | ((uint32_t)bi << (8 * q));  // old numbering; renumbered on accept
-                                    mbits |= 1u << q;
-                                    mark_dirty(s_dirty, a.rayid, p);
-                                }
-                            }
-                            s_own32[w] = ow;
-                            atomicOr(&s_mask[w >> 3], mbits << ((w & 7) * 4));
-                        }
-                    }
-                } else {  // act == 3: owners unchanged; rays through the changed cell are touched
-                    const uint32_t kk = (uint32_t)pidx * 0x01010101u;
-                    for (int w = tid; w < nOwnWords; w += ST) {
-                        const uint32_t eq = __vcmpeq4(s_own32[w], kk);
-                        if (eq) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if ((eq >> (8 * q)) & 1u) mark_dirty(s_dirty, a.rayid, 4 * w + q);
-                        }
-                    }
-                }
-                __syncthreads();
-                // ======================================================== C: re-integrate touched rays (canonical order)
-                auto zeta_of = [&](uint8_t o) -> double { return s_zlut[o]; };
-                for (int r = warp; r < R; r += ST / 32) {
-                    if ((s_dirty[r >> 5] >> (r & 31)) & 1u) {
-                        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-                        const double t = ray_tstar_canonical<uint8_t>(s_owner, a.dt, q0, n, lane, zeta_of);
-                        if (lane == 0) s_tnew[r] = t;
-                    }
-                }
-                __syncthreads();
-            }
-            // ============================================================ D: phi of the proposed model (canonical order)
-            const double nz = (act == 5) ? s_prop->zeta : noise;
-            phin = phi_canonical_128(R, tid, s_scr, [&](int r) {
-                const double t = ((s_dirty[r >> 5] >> (r & 31)) & 1u) ? s_tnew[r] : s_tstar[r];
-                return misfit_term(t, a.tS[r], a.sig[r], nz);
-            });
-            // ============================================================ E: acceptance (thread 0)
-            if (tid == 0) {
-                const double K0 = (double)K;
-                const double zn = s_prop->zeta, aux = s_prop->aux, u = s_prop->u;
-                const double dphi2 = beta * ((phin - phi) / 2);
-                double alpha = 0.0;
-                int acc = 0;
-                if (act == 1) {
-                    const double g = ((aux - zn) * (aux - zn)) / (2 * (sig_zeta * sig_zeta));
-                    if (pm.prior == 1)  // :96-97
-                        alpha = ((K0) / (K0 + 1)) * ((sig_zeta * sqrt(2 * PI)) / (pm.zeta_scale)) * exp(g - dphi2);
-                    else if (pm.prior == 2)  // :107-108
-                        alpha = ((K0) / (K0 + 1)) * (sig_zeta / pm.zeta_scale) * exp(-(zn * zn) / (pm.zeta_scale * pm.zeta_scale) + g - dphi2);
-                    else  // :113-114
-                        alpha = ((K0) / (K0 + 1)) * (sqrt(2 * PI) * sig_zeta / pm.zeta_scale) * exp(-zn / pm.zeta_scale + g - dphi2);
-                    alpha = jl_min1(alpha);
-                    acc = (u < alpha);
-                } else if (act == 2) {
-                    const double zk = s_zeta[pidx];
-                    const double g = ((zk - aux) * (zk - aux)) / (2 * (sig_zeta * sig_zeta));
-                    if (pm.prior == 1)  // :151-152
-                        alpha = ((K0) / (K0 - 1)) * ((pm.zeta_scale) / (sig_zeta * sqrt(2 * PI))) * exp(-g - dphi2);
-                    else if (pm.prior == 2)  // :160-162
-                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / sig_zeta) * exp((zk * zk) / (2 * (pm.zeta_scale * pm.zeta_scale)) - g - dphi2);
-                    else  // :166-168
-                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / (sqrt(2 * PI) * sig_zeta)) * exp(zk / pm.zeta_scale - g - dphi2);
-                    alpha = jl_min1(alpha);
-                    acc = (u < alpha);
-                } else if (act == 3) {
-                    const double zo = s_zeta[pidx];
-                    if (pm.prior == 1) alpha = exp(-dphi2);  // :196
-                    else if (pm.prior == 2) alpha = exp((zo * zo - zn * zn) / (2 * (pm.zeta_scale * pm.zeta_scale)) - dphi2);  // :202-203
-                    else alpha = exp((zo - zn) / pm.zeta_scale - dphi2);  // :207-208
-                    alpha = jl_min1(alpha);
-                    acc = (u < alpha);
-                } else if (act == 4) {
-                    alpha = jl_min1(exp(-dphi2));  // :241-242
-                    acc = (u < alpha);
-                } else {  // sigma: log form :264-267
-                    double la = log(noise / zn) * (double)R - dphi2;
-                    la = (la != la) ? la : (la < 0.0 ? la : 0.0);
-                    acc = (log(u) <= la);
-                }
-                s_prop->accept = acc;
-                s_prop->phin = phin;
-            }
-            __syncthreads();
-            accepted = s_prop->accept;
-            // ============================================================ F: commit / roll back
-            if (act == 1) {
-                const uint32_t newb = (uint32_t)K * 0x01010101u;
-                for (int w = tid; w < nOwnWords; w += ST) {
-                    const uint32_t ow = s_own32[w], t = ow & 0x80808080u;
-                    if (t) {
-                        const uint32_t m = (t >> 7) * 0xFFu;
-                        s_own32[w] = accepted ? ((ow & ~m) | (newb & m)) : (ow & 0x7F7F7F7Fu);
-                    }
-                }
-                if (accepted && tid == 0) {  // append!, :85-88
-                    s_nx[K] = s_prop->x; s_ny[K] = s_prop->y; s_nz[K] = s_prop->z; s_zeta[K] = s_prop->zeta;
-                }
-            } else if (act == 2) {
-                const int kill = pidx;
-                if (accepted) {
-                    for (int i = tid; i < nMaskWords; i += ST) s_mask[i] = 0u;
-                    const uint32_t kk = (uint32_t)kill * 0x01010101u;
-                    for (int w = tid; w < nOwnWords; w += ST) {  // deleteat! renumbering: indices above `kill` shift down (:132-135)
-                        const uint32_t ow = s_own32[w];
-                        const uint32_t gt = __vcmpgtu4(ow, kk) & ~__vcmpeq4(ow, 0x7F7F7F7Fu);
-                        if (gt) s_own32[w] = ow - (gt & 0x01010101u);
-                    }
-                    if (warp == 0) {  // order-preserving delete of the nucleus
-                        double vx[4], vy[4], vz[4], vt[4];
-#pragma unroll
-                        for (int s = 0; s < 4; s++) {
-                            const int i = kill + lane + 32 * s;
-                            if (i < K - 1) { vx[s] = s_nx[i + 1]; vy[s] = s_ny[i + 1]; vz[s] = s_nz[i + 1]; vt[s] = s_zeta[i + 1]; }
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int s = 0; s < 4; s++) {
-                            const int i = kill + lane + 32 * s;
-                            if (i < K - 1) { s_nx[i] = vx[s]; s_ny[i] = vy[s]; s_nz[i] = vz[s]; s_zeta[i] = vt[s]; }
-                        }
-                    }
-                } else {
-                    for (int i = tid; i < nMaskWords; i += ST) {
-                        uint32_t b = s_mask[i];
-                        if (b) {
-                            s_mask[i] = 0u;
-                            while (b) {
-                                const int j = __ffs(b) - 1;
-                                b &= b - 1;
-                                s_owner[32 * i + j] = (uint8_t)kill;
-                            }
-                        }
-                    }
-                }
-            } else if (act == 3) {
-                if (accepted && tid == 0) s_zeta[pidx] = s_prop->zeta;
-            } else if (act == 4) {
-                const int mv = pidx;
-                // masked bytes first (they never carry a tag), then tags
-                if (!accepted) {
-                    for (int i = tid; i < nMaskWords; i += ST) {
-                        uint32_t b = s_mask[i];
-                        if (b) {
-                            s_mask[i] = 0u;
-                            while (b) {
-                                const int j = __ffs(b) - 1;
-                                b &= b - 1;
-                                s_owner[32 * i + j] = (uint8_t)mv;
-                            }
-                        }
-                    }
-                } else {
-                    for (int i = tid; i < nMaskWords; i += ST) s_mask[i] = 0u;
-                }
-                __syncthreads();  // byte stores above and word updates below touch the same words
-                const uint32_t newb = (uint32_t)mv * 0x01010101u;
-                for (int w = tid; w < nOwnWords; w += ST) {
-                    const uint32_t ow = s_own32[w], t = ow & 0x80808080u;
-                    if (t) {
-                        const uint32_t m = (t >> 7) * 0xFFu;
-                        s_own32[w] = accepted ? ((ow & ~m) | (newb & m)) : (ow & 0x7F7F7F7Fu);
-                    }
-                }
-                if (accepted && tid == 0) { s_nx[mv] = s_prop->x; s_ny[mv] = s_prop->y; s_nz[mv] = s_prop->z; }
-            }
-            if (act != 5) {
-                if (accepted)
-                    for (int r = tid; r < R; r += ST)
-                        if ((s_dirty[r >> 5] >> (r & 31)) & 1u) s_tstar[r] = s_tnew[r];
-                __syncthreads();
-                for (int i = tid; i < nDirtyWords; i += ST) s_dirty[i] = 0u;
-            }
-            if (accepted) {
-                phi = phin;
-                if (act == 1) K += 1;
-                else if (act == 2) K -= 1;
-                else if (act == 5) noise = s_prop->zeta;
-            }
-        }
-        // ================================================================ G: bookkeeping, traces, thinning (:275-281)
-        int keep = 0;
-        if ((double)iter >= pm.burn_in) {
-            model_num += 1;
-            if (fmod((double)model_num, pm.keep_each) == 0) keep = 1;
-        }
-        if (tid == 0) {
-            if (act >= 1 && act <= 5) { cnt_prop[act - 1]++; cnt_acc[act - 1] += accepted; cnt_eval[act - 1] += do_eval; }
-            if (a.tr_accept) a.tr_accept[(size_t)chain * a.nIter + it] = (int8_t)accepted;
-            if (a.tr_phi) a.tr_phi[(size_t)chain * a.nIter + it] = phi;
-            if (a.tr_K) a.tr_K[(size_t)chain * a.nIter + it] = K;
-        }
-        __syncthreads();  // state (nuclei, tstar, owners) consistent before the next proposal / the history copy
-        if (keep) {
-            if (n_hist < a.hist_cap) {
-                const size_t h = (size_t)chain * a.hist_cap + n_hist;
-                double *hc = a.hist_cells + h * 4 * KC;
-                for (int i = tid; i < 4 * KC; i += ST) hc[i] = s_nx[i];
-                double *hp = a.hist_ptS + h * R;
-                for (int r = tid; r < R; r += ST) hp[r] = s_tstar[r];
-                if (tid == 0) {
-                    a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = iter;
-                    a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;
-                }
-                pending_slot = n_hist;
-            }
-            n_hist += 1;
-        }
-    }
-
-    // ---- write the chain state back (TMA bulk stores for the arrays)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the async proxy
-    __syncthreads();
-    if (tid == 0) {
-        bulk_store(a.owner + (size_t)chain * a.Ppad, s_owner, (uint32_t)a.Ppad);
-        bulk_store(a.tstar + (size_t)chain * a.Rp, s_tstar, (uint32_t)(8 * a.Rp));
-        bulk_store(a.cells + (size_t)chain * 4 * KC, s_nx, (uint32_t)(32 * KC));
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        a.K[chain] = K; a.phi[chain] = phi; a.noise[chain] = noise;
-        a.n_hist[chain] = n_hist; a.model_num[chain] = model_num; a.pending_slot[chain] = pending_slot;
-        for (int i = 0; i < 5; i++) {
-            a.counts[(size_t)chain * 15 + i] += cnt_prop[i];
-            a.counts[(size_t)chain * 15 + 5 + i] += cnt_acc[i];
-            a.counts[(size_t)chain * 15 + 10 + i] += cnt_eval[i];
-        }
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-}
+namespace tg {
 
 // ---- build_starting (MCsub.jl:76-121) on the device: one thread per chain draws nCells, then K x 4 uniforms
 __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigned long long seed, long long chain_id0, int32_t *K,
@@ -674,8 +77,9 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
     }
 }
 
-__global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const uint8_t *own_a, const uint8_t *own_b,
-                                 const double *ts_a /* [n][Rp] */, const double *ts_b /* [n][R] */, const double *phi_a, const double *phi_b,
+__global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
+                                 const uint8_t *own_b, const double *ts_a /* [n][Rp] sorted rays */,
+                                 const double *ts_b /* [n][R] caller's ray order */, const double *phi_a, const double *phi_b,
                                  unsigned long long *mism, double *maxd /* [2] as ordered uint64 bits */) {
     const int chain = blockIdx.y;
     unsigned long long local = 0;
@@ -685,7 +89,7 @@ __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, 
     if (blockIdx.x == 0) {
         double dm = 0.0;
         for (int r = threadIdx.x; r < R; r += blockDim.x) {
-            const double d = fabs(ts_a[(size_t)chain * Rp + r] - ts_b[(size_t)chain * R + r]);
+            const double d = fabs(ts_a[(size_t)chain * Rp + r] - ts_b[(size_t)chain * R + ray_orig[r]]);
             dm = (d > dm || d != d) ? d : dm;
         }
         if (dm != dm) dm = INFINITY;
@@ -698,11 +102,12 @@ __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, 
     }
 }
 
-__global__ void tg_copy_tstar_kernel(int n, int R, int Rp, const double *src /* [n][R] */, double *dst /* [n][Rp] */) {
+// evaluate's t* (caller's ray order) -> chain state rows (sorted ray order, padded to Rp)
+__global__ void tg_copy_tstar_kernel(int n, int R, int Rp, const int32_t *ray_orig, const double *src /* [n][R] */, double *dst /* [n][Rp] */) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < (size_t)n * Rp) {
         const size_t c = i / Rp, r = i % Rp;
-        dst[i] = r < (size_t)R ? src[c * R + r] : 0.0;
+        dst[i] = r < (size_t)R ? src[c * R + ray_orig[r]] : 0.0;
     }
 }
 
@@ -756,7 +161,7 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     ch->ctx = ctx;
     ch->n = nChains;
     ch->KC = ((pm.max_cells + 7) / 8) * 8;
-    ch->Rp = (ctx->R + 1) & ~1;
+    ch->Rp = ctx->Rp;
     ch->hist_cap = hist_cap;
     ch->chain_id0 = chain_id0;
     ch->seed = seed;
@@ -804,7 +209,8 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
         TG_CUDA(cudaMemcpyAsync(ch->d_noise, ones.data(), 8 * n, cudaMemcpyHostToDevice, s));
         TG_CUDA(cudaStreamSynchronize(s));
     }
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     TG_CUDA(cudaEventCreate(&ch->ev0));
     TG_CUDA(cudaEventCreate(&ch->ev1));
     *out = ch;
@@ -831,7 +237,7 @@ static int establish_state(tonga_chains *ch) {
     int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner);
     if (rc != TONGA_OK) return rc;
     const size_t tot = (size_t)ch->n * ch->Rp;
-    tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ch->d_ptS_tmp, ch->d_tstar);
+    tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_ptS_tmp, ch->d_tstar);
     TG_CUDA(cudaGetLastError());
     ch->have_models = true;
     return TONGA_OK;
@@ -904,8 +310,8 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     if (mode == 1) TG_CUDA(cudaMemcpyAsync(d + o_rec, recs, sizeof(tonga_proposal) * N, cudaMemcpyHostToDevice, s));
 
     tg::SamplerArgs a{};
-    a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dt = ctx->d_dt; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
-    a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off;
+    a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
+    a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig;
     a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
@@ -922,7 +328,8 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.hist_iter = ch->d_hist_iter; a.hist_action = ch->d_hist_action; a.hist_accept = ch->d_hist_accept; a.hist_next = ch->d_hist_next;
 
     TG_CUDA(cudaEventRecord(ch->ev0, s));
-    tg::tg_sampler_kernel<<<ch->n, tg::ST, ch->smem, s>>>(a);
+    if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t><<<ch->n, tg::ST, ch->smem, s>>>(a);
+    else tg::tg_sampler_kernel<uint32_t><<<ch->n, tg::ST, ch->smem, s>>>(a);
     TG_CUDA(cudaGetLastError());
     TG_CUDA(cudaEventRecord(ch->ev1, s));
     ch->iter_done += nIter;
@@ -978,14 +385,19 @@ extern "C" int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K
     }
     if (phi) TG_CUDA(cudaMemcpy(phi, ch->d_phi, 8 * n, cudaMemcpyDeviceToHost));
     if (noise) TG_CUDA(cudaMemcpy(noise, ch->d_noise, 8 * n, cudaMemcpyDeviceToHost));
-    if (ptS) TG_CUDA(cudaMemcpy2D(ptS, 8 * R, ch->d_tstar, 8 * Rp, 8 * R, n, cudaMemcpyDeviceToHost));
+    if (ptS) {  // device rows are in sorted ray order
+        std::vector<double> ht(n * Rp);
+        TG_CUDA(cudaMemcpy(ht.data(), ch->d_tstar, 8 * n * Rp, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++)
+            for (size_t rs = 0; rs < R; rs++) ptS[i * R + (size_t)ctx->h_ray_orig[rs]] = ht[i * Rp + rs];
+    }
     if (owners) {
         std::vector<uint8_t> ho(n * Pp);
         TG_CUDA(cudaMemcpy(ho.data(), ch->d_owner, n * Pp, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++)
-            for (size_t p = 0; p < P; p++) {
+            for (size_t p = 0; p < P; p++) {  // device order: sorted rays
                 const uint8_t o = ho[i * Pp + p];
-                owners[i * P + p] = (o == TG_OWNER_NONE) ? -1 : (int32_t)o;
+                owners[i * P + (size_t)ctx->h_point_orig[p]] = (o == TG_OWNER_NONE) ? -1 : (int32_t)o;
             }
     }
     return TONGA_OK;
@@ -1045,7 +457,7 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     TG_CUDA(cudaMemsetAsync(ch->d_mism, 0, 8, s));
     TG_CUDA(cudaMemsetAsync(ch->d_maxd, 0, 16, s));
     dim3 grid(8, ch->n);
-    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ctx->P, ctx->Ppad, ctx->R, ch->Rp, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
+    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
                                               ch->d_phi, ch->d_phi_tmp, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
     unsigned long long mm = 0;

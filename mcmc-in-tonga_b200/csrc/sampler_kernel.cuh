@@ -1,0 +1,615 @@
+// sampler_kernel.cuh -- tg_sampler_kernel: the device-resident proposal loop (TD_inversion_function.jl:70-302).
+// See sampler.cu for the overview.  Structure of one iteration (one CTA of 4 warps = one chain, state in shared memory):
+//   A  warp 0: proposal (Philox or replay), a-priori checks, v_nearest at the new / killed nucleus, zlut
+//   B  every warp owns the 128-point blocks b = warp, warp+4, ...:
+//        B1 flat pass, 4 points per lane: birth/move compare d(p,new) with d(p,owner) (exact FP64, no FMA);
+//           death/move flag the points owned by the killed/moved nucleus ("orphans") in the mask;
+//        B2 the warp compacts its orphans into a small queue and rescans them 32 at a time, one orphan per lane,
+//           so the K-long nucleus loop runs with full lanes and exists once in the code;
+//   C  t* of the touched rays, one thread per (length-sorted) ray, left-to-right;
+//   D  canonical phi;  E  alpha + accept (thread 0);  F  commit / roll back;  G  traces, thinning, history.
+#pragma once
+#include "tonga_internal.cuh"
+
+namespace tg {
+
+struct SamplerArgs {
+    // geometry (device order: rays sorted by length)
+    const double *px, *py, *pz, *dtT, *tS, *sig;
+    const int32_t *rayid, *ray_off, *ray_orig;
+    int R, Rp, KC;
+    int P, Ppad;
+    tonga_params prm;
+    // chain state (global)
+    int32_t *K;
+    double *cells;  // [n][4][KC]
+    double *phi, *noise, *beta;
+    uint8_t *owner;  // [n][Ppad]
+    double *tstar;   // [n][Rp]  (sorted ray order)
+    long long *counts;  // [n][3][5] proposed / accepted / evaluated
+    int32_t *pending_slot;  // [n] history slot awaiting its next_action, or -1
+    // run
+    long long iter0, nIter;
+    int mode;  // 0 generate, 1 replay
+    const tonga_proposal *recs_in;
+    tonga_proposal *recs_out;
+    int8_t *tr_accept;
+    double *tr_phi;
+    int32_t *tr_K;
+    unsigned long long seed;
+    long long chain_id0;
+    // history
+    int hist_cap;
+    int32_t *n_hist;
+    long long *model_num;
+    int32_t *hist_K;
+    double *hist_cells, *hist_phi, *hist_ptS;
+    long long *hist_iter;
+    int32_t *hist_action, *hist_accept, *hist_next;
+};
+
+struct Prop {  // proposal of the current iteration, broadcast through shared memory
+    int action, idx, do_eval, accept;
+    double x, y, z, zeta, u;
+    double aux;            // birth: czeta (:81); death: zetanew (:146)
+    double ox, oy, oz;     // move: the old position (the nucleus array holds the proposed one during B..E)
+};
+
+constexpr int SQ_CAP = 64;  // orphan queue entries per warp
+
+struct SmemLayout {
+    size_t o_owner, o_mask, o_tstar, o_tnew, o_dirty, o_nuc, o_zlut, o_scr, o_prop, o_queue, o_bar, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int Ppad, int Rp, int KC) {
+    SmemLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+    L.o_owner = take((size_t)Ppad);
+    L.o_mask = take((size_t)Ppad / 8);
+    L.o_tstar = take(8 * (size_t)Rp);
+    L.o_tnew = take(8 * (size_t)Rp);
+    L.o_dirty = take(4 * (size_t)((Rp + 31) / 32));
+    L.o_nuc = take(8 * 4 * (size_t)KC);
+    L.o_zlut = take(8 * 256);
+    L.o_scr = take(8 * 4);
+    L.o_prop = take(sizeof(Prop));
+    L.o_queue = take((size_t)(ST / 32) * SQ_CAP * (Ppad <= 65536 ? 2 : 4));
+    L.o_bar = take(8);
+    L.total = o;
+    return L;
+}
+
+// ---- TMA bulk copies (SASS: UBLKCP) -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(dst)),
+                 "l"(src), "r"(bytes), "r"(s2u(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s2u(src)), "r"(bytes) : "memory");
+}
+
+// ---- warp-cooperative v_nearest (MCsub.jl:247-263) over the nuclei in shared memory, skipping index `skip` ---------
+__device__ __noinline__ int warp_nearest(const double *nx, const double *ny, const double *nz, int K, int skip, double x,
+                                         double y, double z, int lane) {
+    double best = 1e9;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < K; i += 32) {
+        if (i == skip) continue;
+        const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);
+        if (d < best) { best = d; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    }
+    return bi == 0x7fffffff ? -1 : bi;
+}
+
+__device__ __forceinline__ double jl_min1(double a) {  // min([1 a]...) in Julia: NaN propagates
+    return (a != a) ? a : (a < 1.0 ? a : 1.0);
+}
+
+__device__ __forceinline__ void mark_dirty(uint32_t *dirty, const int32_t *__restrict__ rayid, int p) {
+    const int r = rayid[p];
+    atomicOr(&dirty[r >> 5], 1u << (r & 31));
+}
+
+// Box-Muller pair from two uniforms in [0,1)
+__device__ __noinline__ void normal_pair(double u1, double u2, double &n0, double &n1) {
+    const double rr = sqrt(-2.0 * log(u1 + 0x1.0p-54));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    n0 = rr * cs;
+    n1 = rr * sn;
+}
+
+// Orphan rescan: nearest nucleus of flat point p among all K nuclei except `skip` (strict <, ascending index).
+__device__ __noinline__ int rescan_point(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
+                                         const double *nx, const double *ny, const double *nz, int K, int skip, int p) {
+    const double x = px[p], y = py[p], z = pz[p];
+    double best = 1e9;
+    int bi = TG_OWNER_NONE;
+#pragma unroll 2
+    for (int i = 0; i < K; i++) {
+        const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);
+        if (d < best && i != skip) { best = d; bi = i; }
+    }
+    return bi;
+}
+
+template <typename QT>
+__global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemLayout L = smem_layout(a.Ppad, a.Rp, a.KC);
+    uint8_t *s_owner = smem + L.o_owner;
+    uint32_t *s_own32 = reinterpret_cast<uint32_t *>(s_owner);
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + L.o_mask);
+    double *s_tstar = reinterpret_cast<double *>(smem + L.o_tstar);
+    double *s_tnew = reinterpret_cast<double *>(smem + L.o_tnew);
+    uint32_t *s_dirty = reinterpret_cast<uint32_t *>(smem + L.o_dirty);
+    double *s_nx = reinterpret_cast<double *>(smem + L.o_nuc);
+    double *s_ny = s_nx + a.KC, *s_nz = s_ny + a.KC, *s_zeta = s_nz + a.KC;
+    double *s_zlut = reinterpret_cast<double *>(smem + L.o_zlut);
+    double *s_scr = reinterpret_cast<double *>(smem + L.o_scr);
+    Prop *s_prop = reinterpret_cast<Prop *>(smem + L.o_prop);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.o_bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    QT *s_queue = reinterpret_cast<QT *>(smem + L.o_queue) + warp * SQ_CAP;
+    const int chain = blockIdx.x;
+    const int KC = a.KC, R = a.R, Rp = a.Rp;
+    const int nOwnWords = a.Ppad / 4, nMaskWords = a.Ppad / 32, nDirtyWords = (a.Rp + 31) / 32;
+    const int nBlocks = a.Ppad / 128, nGroups = (R + 31) / 32;
+
+    // ---- load the chain state: three TMA bulk copies on one mbarrier
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s2u(s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t b_owner = (uint32_t)a.Ppad, b_ts = (uint32_t)(8 * a.Rp), b_nuc = (uint32_t)(32 * KC);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(s_bar)), "r"(b_owner + b_ts + b_nuc) : "memory");
+        bulk_load(s_owner, a.owner + (size_t)chain * a.Ppad, b_owner, s_bar);
+        bulk_load(s_tstar, a.tstar + (size_t)chain * a.Rp, b_ts, s_bar);
+        bulk_load(s_nx, a.cells + (size_t)chain * 4 * KC, b_nuc, s_bar);
+    }
+    for (int i = tid; i < nMaskWords; i += ST) s_mask[i] = 0u;
+    for (int i = tid; i < nDirtyWords; i += ST) s_dirty[i] = 0u;
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+            s2u(s_bar))
+        : "memory");
+    __syncthreads();
+
+    int K = a.K[chain];
+    double phi = a.phi[chain];
+    double noise = a.noise[chain];
+    const double beta = a.beta[chain];
+    int n_hist = a.n_hist[chain];
+    long long model_num = a.model_num[chain];
+    int pending_slot = a.pending_slot[chain];
+
+    const tonga_params &pm = a.prm;
+    // TD_inversion_function.jl:22-23,30-32
+    const double sig_zeta = pm.zeta_scale * pm.sig / 100;
+    const double PI = 3.141592653589793;
+    const unsigned long long gid = (unsigned long long)(a.chain_id0 + chain);
+
+#pragma unroll 1
+    for (long long it = 0; it < a.nIter; it++) {
+        const long long iter = a.iter0 + it;
+        // ================================================================ A: proposal (warp 0, warp-uniform values)
+        if (warp == 0) {
+            Prop pr;
+            pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
+            pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = 0.0;
+            double uu[8];
+            if (a.mode == 0) {
+                const Philox philox{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (lane < 4) philox((uint32_t)iter, (uint32_t)((unsigned long long)iter >> 32), (uint32_t)gid, (uint32_t)lane | ((uint32_t)(gid >> 32) << 8), w);
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
+                    const uint32_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
+                    uu[2 * s] = u53(w0, w1);
+                    uu[2 * s + 1] = u53(w2, w3);
+                }
+                const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
+                const int act0 = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
+                pr.action = act0 > nact ? nact : act0;
+            } else {
+                const tonga_proposal rec = a.recs_in[(size_t)chain * a.nIter + it];
+                pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
+            }
+            const int act = pr.action;
+            int valid = 0;
+            if (act == 1) {  // ---- birth :76-125
+                if (K < pm.max_cells) {
+                    if (a.mode == 0) {
+                        pr.x = uu[2] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
+                        pr.y = uu[3] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
+                        pr.z = uu[4] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
+                    }
+                    const int ci = warp_nearest(s_nx, s_ny, s_nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
+                    const double czeta = ci < 0 ? 0.0 : s_zeta[ci];
+                    pr.aux = czeta;
+                    if (a.mode == 0) {
+                        double n0, n1;
+                        normal_pair(uu[5], uu[6], n0, n1);
+                        pr.zeta = czeta + sig_zeta * n0;  // :82
+                        pr.u = uu[7];                     // :121
+                    }
+                    if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
+                    else if (pm.prior == 2) valid = 1;
+                    else valid = (pr.zeta > 0);  // :111
+                }
+            } else if (act == 2) {  // ---- death :126-181
+                if (K > pm.min_cells) {
+                    if (a.mode == 0) {
+                        const int k = (int)floor(uu[1] * K);  // :128
+                        pr.idx = k >= K ? K - 1 : k;
+                        pr.u = uu[7];  // :176
+                    }
+                    const int kill = pr.idx;
+                    if (kill >= 0 && kill < K) {
+                        const int zi = warp_nearest(s_nx, s_ny, s_nz, K, kill, s_nx[kill], s_ny[kill], s_nz[kill], lane);  // :146
+                        pr.aux = zi < 0 ? 0.0 : s_zeta[zi];
+                        valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
+                    }
+                }
+            } else if (act == 3) {  // ---- change :183-218
+                if (a.mode == 0) {
+                    const int k = (int)floor(uu[1] * K);  // :184
+                    pr.idx = k >= K ? K - 1 : k;
+                    double n0, n1;
+                    normal_pair(uu[2], uu[3], n0, n1);
+                    pr.zeta = s_zeta[pr.idx] + sig_zeta * n0;  // :188
+                    pr.u = uu[7];                              // :214
+                }
+                if (pr.idx >= 0 && pr.idx < K) {
+                    if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
+                    else if (pm.prior == 2) valid = 1;
+                    else valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
+                    // the reference evaluates first (:191) but discards the result when invalid
+                }
+            } else if (act == 4) {  // ---- move :220-251
+                if (K > 0) {
+                    if (a.mode == 0) {
+                        const int k = (int)floor(uu[1] * K);  // :222
+                        pr.idx = k >= K ? K - 1 : k;
+                        double n0, n1, n2, n3;
+                        normal_pair(uu[2], uu[3], n0, n1);
+                        normal_pair(uu[4], uu[5], n2, n3);
+                        pr.x = s_nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
+                        pr.y = s_ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
+                        pr.z = s_nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
+                        pr.u = uu[7];                                                        // :247
+                    }
+                    if (pr.idx >= 0 && pr.idx < K) {
+                        valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
+                                 pr.z <= pm.zmax);  // :230-232
+                        if (valid) {  // from here to the accept decision the nucleus array holds the PROPOSED position
+                            pr.ox = s_nx[pr.idx]; pr.oy = s_ny[pr.idx]; pr.oz = s_nz[pr.idx];
+                            __syncwarp();
+                            if (lane == 0) { s_nx[pr.idx] = pr.x; s_ny[pr.idx] = pr.y; s_nz[pr.idx] = pr.z; }
+                        }
+                    }
+                }
+            } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
+                if (a.mode == 0) {
+                    double n0, n1;
+                    normal_pair(uu[2], uu[3], n0, n1);
+                    pr.zeta = noise + (pm.max_sig * pm.sig / 100) * n0;  // :23,:254
+                    pr.u = uu[7];
+                }
+                valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
+            }
+            pr.do_eval = valid;
+            // zlut: owner byte -> zeta under the proposed model (bit 7 set = switches to the implicit new owner)
+            if (valid && act != 5) {
+                const double ztag = (act == 1) ? pr.zeta : (act == 4 ? s_zeta[pr.idx] : 0.0);
+                for (int o = lane; o < 128; o += 32) {
+                    double zv = (o < K) ? s_zeta[o] : 0.0;
+                    if (act == 3 && o == pr.idx) zv = pr.zeta;
+                    s_zlut[o] = zv;
+                    s_zlut[128 + o] = ztag;
+                }
+            }
+            if (lane == 0) {
+                *s_prop = pr;
+                if (a.mode == 0 && a.recs_out) {
+                    tonga_proposal rec;
+                    rec.action = pr.action; rec.idx = pr.idx; rec.x = pr.x; rec.y = pr.y; rec.z = pr.z; rec.zeta = pr.zeta; rec.u = pr.u;
+                    a.recs_out[(size_t)chain * a.nIter + it] = rec;
+                }
+                if (pending_slot >= 0) a.hist_next[(size_t)chain * a.hist_cap + pending_slot] = pr.action;
+            }
+        }
+        __syncthreads();
+        pending_slot = -1;
+        const int act = s_prop->action;
+        const int do_eval = s_prop->do_eval;
+        const int pidx = s_prop->idx;
+        const uint32_t kk = (uint32_t)pidx * 0x01010101u;
+        double phin = phi;
+        int accepted = 0;
+
+        if (do_eval) {
+            if (act != 5) {
+                const double cx = s_prop->x, cy = s_prop->y, cz = s_prop->z;
+                // ======================================================== B1: flat pass over this warp's 128-point blocks
+#pragma unroll 1
+                for (int blk = warp; blk < nBlocks; blk += ST / 32) {
+                    const int w = blk * 32 + lane;
+                    uint32_t ow = s_own32[w];
+                    uint32_t mbits = 0;
+                    if (act == 1 || act == 4) {
+                        const double2 xa = *reinterpret_cast<const double2 *>(a.px + 4 * w), xb = *reinterpret_cast<const double2 *>(a.px + 4 * w + 2);
+                        const double2 ya = *reinterpret_cast<const double2 *>(a.py + 4 * w), yb = *reinterpret_cast<const double2 *>(a.py + 4 * w + 2);
+                        const double2 za = *reinterpret_cast<const double2 *>(a.pz + 4 * w), zb = *reinterpret_cast<const double2 *>(a.pz + 4 * w + 2);
+                        const double X[4] = {xa.x, xa.y, xb.x, xb.y}, Y[4] = {ya.x, ya.y, yb.x, yb.y}, Z[4] = {za.x, za.y, zb.x, zb.y};
+                        const int mv = (act == 4) ? pidx : -1;
+                        uint32_t tags = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int o = (ow >> (8 * q)) & 0xFF;
+                            if (o == mv) {
+                                mbits |= 1u << q;  // move, type A: owned by the moved nucleus -> rescan in B2
+                            } else {
+                                const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], X[q], Y[q], Z[q]);
+                                const double d_c = dist2_exact(cx, cy, cz, X[q], Y[q], Z[q]);
+                                // birth: the new nucleus has the highest index -> strict <.  move: index mv also wins exact ties against o > mv.
+                                const bool sw = (d_c < d_o) || (act == 4 && d_c == d_o && mv < o && o != TG_OWNER_NONE);
+                                if (sw) tags |= 0x80u << (8 * q);
+                            }
+                        }
+                        if (tags) {
+                            s_own32[w] = ow | tags;
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if ((tags >> (8 * q + 7)) & 1u) mark_dirty(s_dirty, a.rayid, 4 * w + q);
+                        }
+                    } else {
+                        const uint32_t eq = __vcmpeq4(ow, kk);  // bytes owned by the killed / changed nucleus
+                        if (eq) {
+                            if (act == 2) {
+                                mbits = (eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u);
+                            } else {  // act == 3: owners unchanged; rays through the changed cell are touched
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if ((eq >> (8 * q)) & 1u) mark_dirty(s_dirty, a.rayid, 4 * w + q);
+                            }
+                        }
+                    }
+                    if (act == 2 || act == 4) {  // assemble the block's 4 mask words (8 lanes x 4 bits each)
+                        uint32_t nib = mbits << ((lane & 7) * 4);
+                        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+                        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+                        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+                        if ((lane & 7) == 0) s_mask[w >> 3] = nib;
+                    }
+                }
+                // ======================================================== B2: rescan this warp's orphans, 32 at a time
+                if (act == 2 || act == 4) {
+                    __syncwarp();
+                    const int skip = (act == 2) ? pidx : -1;
+                    int qn = 0;
+                    auto drain = [&](int cnt) {  // lanes < cnt take the top `cnt` queue entries
+                        if (lane < cnt) {
+                            const int p = (int)s_queue[qn - cnt + lane];
+                            const int bi = rescan_point(a.px, a.py, a.pz, s_nx, s_ny, s_nz, K, skip, p);
+                            s_owner[p] = (uint8_t)bi;  // death: old numbering, renumbered on accept
+                            if (act == 2 || bi != pidx) mark_dirty(s_dirty, a.rayid, p);
+                        }
+                        qn -= cnt;
+                        __syncwarp();
+                    };
+#pragma unroll 1
+                    for (int blk = warp; blk < nBlocks; blk += ST / 32) {
+#pragma unroll 1
+                        for (int k4 = 0; k4 < 4; k4++) {
+                            const int mw = blk * 4 + k4;
+                            const uint32_t bits = s_mask[mw];
+                            if (bits) {
+                                if ((bits >> lane) & 1u) s_queue[qn + __popc(bits & ((1u << lane) - 1u))] = (QT)(mw * 32 + lane);
+                                qn += __popc(bits);
+                                __syncwarp();
+                                if (qn >= 32) drain(32);
+                            }
+                        }
+                    }
+                    if (qn > 0) drain(qn);
+                }
+                __syncthreads();
+                // ======================================================== C: t* of touched rays, one thread per sorted ray
+#pragma unroll 1
+                for (int g = warp; g < nGroups; g += ST / 32) {
+                    const uint32_t bits = s_dirty[g];
+                    if (bits) {
+                        const int r = g * 32 + lane;
+                        if ((bits >> lane) & 1u) {
+                            const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
+                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, Rp, r, q0, n, [&](uint8_t o) -> double { return s_zlut[o]; });
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // ============================================================ D: phi of the proposed model (canonical order)
+            const double nz = (act == 5) ? s_prop->zeta : noise;
+            phin = phi_canonical_128(R, tid, s_scr, [&](int r) {
+                const double t = ((s_dirty[r >> 5] >> (r & 31)) & 1u) ? s_tnew[r] : s_tstar[r];
+                return misfit_term(t, a.tS[r], a.sig[r], nz);
+            });
+            // ============================================================ E: acceptance (thread 0)
+            if (tid == 0) {
+                const double K0 = (double)K;
+                const double zn = s_prop->zeta, aux = s_prop->aux, u = s_prop->u;
+                const double dphi2 = beta * ((phin - phi) / 2);
+                double alpha = 0.0;
+                int acc = 0;
+                if (act == 1) {
+                    const double g = ((aux - zn) * (aux - zn)) / (2 * (sig_zeta * sig_zeta));
+                    if (pm.prior == 1)  // :96-97
+                        alpha = ((K0) / (K0 + 1)) * ((sig_zeta * sqrt(2 * PI)) / (pm.zeta_scale)) * exp(g - dphi2);
+                    else if (pm.prior == 2)  // :107-108
+                        alpha = ((K0) / (K0 + 1)) * (sig_zeta / pm.zeta_scale) * exp(-(zn * zn) / (pm.zeta_scale * pm.zeta_scale) + g - dphi2);
+                    else  // :113-114
+                        alpha = ((K0) / (K0 + 1)) * (sqrt(2 * PI) * sig_zeta / pm.zeta_scale) * exp(-zn / pm.zeta_scale + g - dphi2);
+                    acc = (u < jl_min1(alpha));
+                } else if (act == 2) {
+                    const double zk = s_zeta[pidx];
+                    const double g = ((zk - aux) * (zk - aux)) / (2 * (sig_zeta * sig_zeta));
+                    if (pm.prior == 1)  // :151-152
+                        alpha = ((K0) / (K0 - 1)) * ((pm.zeta_scale) / (sig_zeta * sqrt(2 * PI))) * exp(-g - dphi2);
+                    else if (pm.prior == 2)  // :160-162
+                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / sig_zeta) * exp((zk * zk) / (2 * (pm.zeta_scale * pm.zeta_scale)) - g - dphi2);
+                    else  // :166-168
+                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / (sqrt(2 * PI) * sig_zeta)) * exp(zk / pm.zeta_scale - g - dphi2);
+                    acc = (u < jl_min1(alpha));
+                } else if (act == 3) {
+                    const double zo = s_zeta[pidx];
+                    if (pm.prior == 1) alpha = exp(-dphi2);  // :196
+                    else if (pm.prior == 2) alpha = exp((zo * zo - zn * zn) / (2 * (pm.zeta_scale * pm.zeta_scale)) - dphi2);  // :202-203
+                    else alpha = exp((zo - zn) / pm.zeta_scale - dphi2);  // :207-208
+                    acc = (u < jl_min1(alpha));
+                } else if (act == 4) {
+                    acc = (u < jl_min1(exp(-dphi2)));  // :241-242
+                } else {  // sigma: log form :264-267
+                    double la = log(noise / zn) * (double)R - dphi2;
+                    la = (la != la) ? la : (la < 0.0 ? la : 0.0);
+                    acc = (log(u) <= la);
+                }
+                s_prop->accept = acc;
+            }
+            __syncthreads();
+            accepted = s_prop->accept;
+            // ============================================================ F: commit / roll back
+            if (act == 2 || act == 4) {  // masked bytes: overwritten orphans (old owner = pidx)
+#pragma unroll 1
+                for (int i = tid; i < nMaskWords; i += ST) {
+                    uint32_t b = s_mask[i];
+                    if (b) {
+                        s_mask[i] = 0u;
+                        if (!accepted)
+                            while (b) {
+                                const int j = __ffs(b) - 1;
+                                b &= b - 1;
+                                s_owner[32 * i + j] = (uint8_t)pidx;
+                            }
+                    }
+                }
+                if (act == 4) __syncthreads();  // byte stores above and word updates below may touch the same words
+            }
+            if (act == 1 || act == 4) {  // tagged bytes: switch to the new / moved nucleus
+                const uint32_t newb = (uint32_t)(act == 1 ? K : pidx) * 0x01010101u;
+#pragma unroll 1
+                for (int w = tid; w < nOwnWords; w += ST) {
+                    const uint32_t ow = s_own32[w], t = ow & 0x80808080u;
+                    if (t) {
+                        const uint32_t m = (t >> 7) * 0xFFu;
+                        s_own32[w] = accepted ? ((ow & ~m) | (newb & m)) : (ow & 0x7F7F7F7Fu);
+                    }
+                }
+            }
+            if (act == 2 && accepted) {  // deleteat! renumbering: indices above `kill` shift down (:132-135)
+#pragma unroll 1
+                for (int w = tid; w < nOwnWords; w += ST) {
+                    const uint32_t ow = s_own32[w];
+                    const uint32_t gt = __vcmpgtu4(ow, kk) & ~__vcmpeq4(ow, 0x7F7F7F7Fu);
+                    if (gt) s_own32[w] = ow - (gt & 0x01010101u);
+                }
+                if (warp == 0) {  // order-preserving delete of the nucleus
+                    double vx[4], vy[4], vz[4], vt[4];
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        const int i = pidx + lane + 32 * s;
+                        if (i < K - 1) { vx[s] = s_nx[i + 1]; vy[s] = s_ny[i + 1]; vz[s] = s_nz[i + 1]; vt[s] = s_zeta[i + 1]; }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        const int i = pidx + lane + 32 * s;
+                        if (i < K - 1) { s_nx[i] = vx[s]; s_ny[i] = vy[s]; s_nz[i] = vz[s]; s_zeta[i] = vt[s]; }
+                    }
+                }
+            }
+            if (tid == 0) {
+                if (act == 1 && accepted) {  // append!, :85-88
+                    s_nx[K] = s_prop->x; s_ny[K] = s_prop->y; s_nz[K] = s_prop->z; s_zeta[K] = s_prop->zeta;
+                } else if (act == 3 && accepted) {
+                    s_zeta[pidx] = s_prop->zeta;
+                } else if (act == 4 && !accepted) {
+                    s_nx[pidx] = s_prop->ox; s_ny[pidx] = s_prop->oy; s_nz[pidx] = s_prop->oz;
+                }
+            }
+            if (act != 5) {
+                if (accepted)
+                    for (int r = tid; r < R; r += ST)
+                        if ((s_dirty[r >> 5] >> (r & 31)) & 1u) s_tstar[r] = s_tnew[r];
+                __syncthreads();
+                for (int i = tid; i < nDirtyWords; i += ST) s_dirty[i] = 0u;
+            }
+            if (accepted) {
+                phi = phin;
+                if (act == 1) K += 1;
+                else if (act == 2) K -= 1;
+                else if (act == 5) noise = s_prop->zeta;
+            }
+        }
+        // ================================================================ G: bookkeeping, traces, thinning (:275-281)
+        int keep = 0;
+        if ((double)iter >= pm.burn_in) {
+            model_num += 1;
+            if (fmod((double)model_num, pm.keep_each) == 0) keep = 1;
+        }
+        if (tid == 0) {
+            if (act >= 1 && act <= 5) {
+                unsigned long long *c = reinterpret_cast<unsigned long long *>(a.counts) + (size_t)chain * 15 + (act - 1);
+                atomicAdd(c, 1ULL);  // RED: fire and forget
+                if (accepted) atomicAdd(c + 5, 1ULL);
+                if (do_eval) atomicAdd(c + 10, 1ULL);
+            }
+            if (a.tr_accept) a.tr_accept[(size_t)chain * a.nIter + it] = (int8_t)accepted;
+            if (a.tr_phi) a.tr_phi[(size_t)chain * a.nIter + it] = phi;
+            if (a.tr_K) a.tr_K[(size_t)chain * a.nIter + it] = K;
+        }
+        __syncthreads();  // state (nuclei, tstar, owners) consistent before the next proposal / the history copy
+        if (keep) {
+            if (n_hist < a.hist_cap) {
+                const size_t h = (size_t)chain * a.hist_cap + n_hist;
+                double *hc = a.hist_cells + h * 4 * KC;
+                for (int i = tid; i < 4 * KC; i += ST) hc[i] = s_nx[i];
+                double *hp = a.hist_ptS + h * R;
+                for (int r = tid; r < R; r += ST) hp[a.ray_orig[r]] = s_tstar[r];  // caller's ray order
+                if (tid == 0) {
+                    a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = iter;
+                    a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;
+                }
+                pending_slot = n_hist;
+            }
+            n_hist += 1;
+        }
+    }
+
+    // ---- write the chain state back (TMA bulk stores for the arrays)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the async proxy
+    __syncthreads();
+    if (tid == 0) {
+        bulk_store(a.owner + (size_t)chain * a.Ppad, s_owner, (uint32_t)a.Ppad);
+        bulk_store(a.tstar + (size_t)chain * a.Rp, s_tstar, (uint32_t)(8 * a.Rp));
+        bulk_store(a.cells + (size_t)chain * 4 * KC, s_nx, (uint32_t)(32 * KC));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        a.K[chain] = K; a.phi[chain] = phi; a.noise[chain] = noise;
+        a.n_hist[chain] = n_hist; a.model_num[chain] = model_num; a.pending_slot[chain] = pending_slot;
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+}  // namespace tg

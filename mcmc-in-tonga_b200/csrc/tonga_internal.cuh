@@ -6,9 +6,11 @@
 //   * per-segment term exactly as MCsub.jl:147,153: (rayl*rayu) * ((0.5*(za+zb)) / 1000); the division is done
 //     with a 3-op FMA sequence that returns the correctly rounded quotient (checked against `/` on 3e8 samples);
 //   * per-ray misfit term exactly as MCsub.jl:171: ((d*d)*1.0) / (sig*sig);
-//   * ONE canonical summation order for t* (per ray) and phi (per model), shared by the full evaluate kernel and
-//     the incremental sampler kernel, so "incremental == full" holds bit for bit on the device.  The reference's
-//     own order (Julia `sum`, SIMD pairwise) is unspecified; parity with the oracle is 1e-9 relative.
+//   * ONE canonical summation order, shared by the full evaluate kernel and the incremental sampler kernel, so
+//     "incremental == full" holds bit for bit on the device: t* of a ray is the plain left-to-right sum over its
+//     segments (the reference's own order -- Julia `sum`, SIMD pairwise -- is unspecified); phi is a fixed 128-lane
+//     strided sum + butterfly over the rays in length-sorted order (the reference sums k = 1..R sequentially), hence
+//     a 1e-9 relative tolerance on phi, none on the owners, and t* equal to a left-to-right CPU sum bit for bit.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -72,18 +74,24 @@ __device__ __forceinline__ double warp_sum_canonical(double v) {
     return v;
 }
 
-// Canonical t* of one ray by one warp.  zlut maps an owner byte/code to zeta.  p0 = first flat point, n = #points.
-// lane l sums terms j = l, l+32, ... (ascending), then the xor butterfly.
+// Canonical t* of one ray: the plain left-to-right sum over its segments (the order the CPU oracle uses too, so t* is
+// bit-identical to the oracle's).  One THREAD walks one ray; rays are sorted by length so the 32 rays of a warp finish
+// together, and dt is stored segment-major (dtT[j][ray]) so the warp's loads coalesce.  n = #points of the ray,
+// `last` = common trip bound of the warp (max n over its active lanes) to keep the loop warp-uniform.
 template <typename OwnerT, typename ZetaOf>
-__device__ __forceinline__ double ray_tstar_canonical(const OwnerT *__restrict__ owner, const double *__restrict__ dt,
-                                                      int p0, int n, int lane, ZetaOf zeta_of) {
+__device__ __forceinline__ double ray_tstar_seq(const OwnerT *__restrict__ owner, const double *__restrict__ dtT, int Rp, int r,
+                                                int p0, int n, ZetaOf zeta_of) {
     double acc = 0.0;
-    for (int j = lane; j < n - 1; j += 32) {
-        const double za = zeta_of(owner[p0 + j]);
-        const double zb = zeta_of(owner[p0 + j + 1]);
-        acc = __dadd_rn(acc, seg_term(dt[p0 + j], za, zb));
+    if (n > 1) {
+        double za = zeta_of(owner[p0]);
+#pragma unroll 4
+        for (int j = 0; j < n - 1; j++) {
+            const double zb = zeta_of(owner[p0 + j + 1]);
+            acc = __dadd_rn(acc, seg_term(dtT[(size_t)j * Rp + r], za, zb));
+            za = zb;
+        }
     }
-    return warp_sum_canonical(acc);
+    return acc;
 }
 
 // Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES (=128) threads (4 warps).
@@ -144,14 +152,21 @@ struct tonga_ctx {
     int max_npts = 0;
     // device geometry (SoA, flat point order, padded with NaN coordinates / zero dt)
     double *d_px = nullptr, *d_py = nullptr, *d_pz = nullptr;  // [Ppad]
-    double *d_dt = nullptr;                                    // [Ppad] dt of the segment starting at p (0 at ray ends)
-    int32_t *d_rayid = nullptr;                                // [Ppad]
-    int32_t *d_ray_off = nullptr;                              // [R+1]
-    double *d_tS = nullptr, *d_sig = nullptr;                  // [R]
+    // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
+    // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.
+    double *d_dtT = nullptr;                                   // [max(m-1,1)][Rp] dt = rayL*rayU, segment-major (0 beyond a ray's end)
+    int32_t *d_rayid = nullptr;                                // [Ppad] sorted ray index of each flat point
+    int32_t *d_ray_off = nullptr;                              // [R+1]  CSR offsets over sorted rays
+    int32_t *d_ray_orig = nullptr;                             // [R]    sorted ray index -> caller's ray index
+    int32_t *d_point_orig = nullptr;                           // [Ppad] sorted flat point -> caller's flat point (-1 for padding)
+    double *d_tS = nullptr, *d_sig = nullptr;                  // [R]    in sorted ray order
+    int Rp = 0;                                                // R rounded up to a multiple of 2 (16-byte rows)
     tg::Tile *d_tiles = nullptr;
     int n_tiles = 0;
     int tile_pts = 0;
-    std::vector<int32_t> h_ray_off;
+    std::vector<int32_t> h_ray_off;     // caller's order (tonga_ray_offsets)
+    std::vector<int32_t> h_ray_orig;    // sorted -> caller's ray
+    std::vector<int32_t> h_point_orig;  // sorted flat point -> caller's flat point
     double like_const = 0.0;  // MCsub.jl:179 for noise = 1
     double sum_neglog = 0.0;  // sum_k -log(allSig_k*sqrt(2pi))
     int sm_count = 0;
