@@ -105,7 +105,8 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     const double qnan = std::nan("");
     std::vector<double> px(Ppad, qnan), py(Ppad, qnan), pz(Ppad, qnan);
     const int nsegmax = m > 1 ? m - 1 : 1;
-    std::vector<double> dtT((size_t)nsegmax * (Rp > 0 ? Rp : 2), 0.0);
+    const int ldT = ((R + 127) / 128) * 128 + (R == 0 ? 128 : 0);
+    std::vector<double> dtT((size_t)nsegmax * ldT, 0.0);
     std::vector<int32_t> rayid(Ppad, 0), point_orig(Ppad, -1);
     std::vector<double> tS_s(R), sig_s(R);
     int64_t S = 0;
@@ -123,7 +124,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
             point_orig[dst] = ray_off[i] + k;
             if (k < np - 1) {
                 const size_t sg = (size_t)i * (m - 1) + k;
-                dtT[(size_t)k * Rp + rs] = rayL[sg] * rayU[sg];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction)
+                dtT[(size_t)k * ldT + tg::dt_col(rs)] = rayL[sg] * rayU[sg];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction)
                 S++;
             }
         }
@@ -156,6 +157,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     ctx->h_ray_orig = ray_orig;
     ctx->h_point_orig = point_orig;
     ctx->Rp = Rp;
+    ctx->ldT = ldT;
     ctx->n_tiles = (int)tiles.size();
     ctx->tile_pts = tile_pts;
     cudaDeviceProp prop;

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(EVAL_THREADS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
-               const int32_t *__restrict__ point_orig, int R, int Rp, int64_t P, int64_t Ppad, int tile_pts,
+               const int32_t *__restrict__ point_orig, int R, int ldT, int64_t P, int64_t Ppad, int tile_pts,
                double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int model = blockIdx.y;
@@ -119,7 +119,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16 ? 0.0 : s_zeta[o]; };
     for (int r = tile.r0 + threadIdx.x; r < tile.r1; r += EVAL_THREADS) {
         const int q0 = ray_off[r], n = ray_off[r + 1] - q0;
-        const double t = ray_tstar_seq<uint16_t>(s_owner - tile.p0, dtT, Rp, r, q0, n, zeta_of);
+        const double t = ray_tstar_seq<uint16_t>(s_owner - tile.p0, dtT, ldT, r, q0, n, zeta_of);
         ptS[(size_t)model * R + ray_orig[r]] = t;  // caller's ray order
     }
 }
@@ -158,7 +158,7 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
                                                                   ctx->d_pz, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
-                                                                  ctx->R, ctx->Rp, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
+                                                                  ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev);
         TG_CUDA(cudaGetLastError());
     }

@@ -312,7 +312,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     tg::SamplerArgs a{};
     a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
     a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig;
-    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
+    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
     a.owner = ch->d_owner; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;

@@ -17,7 +17,7 @@ struct SamplerArgs {
     // geometry (device order: rays sorted by length)
     const double *px, *py, *pz, *dtT, *tS, *sig;
     const int32_t *rayid, *ray_off, *ray_orig;
-    int R, Rp, KC;
+    int R, Rp, KC, ldT;
     int P, Ppad;
     tonga_params prm;
     // chain state (global)
@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     QT *s_queue = reinterpret_cast<QT *>(smem + L.o_queue) + warp * SQ_CAP;
     const int chain = blockIdx.x;
-    const int KC = a.KC, R = a.R, Rp = a.Rp;
+    const int KC = a.KC, R = a.R;
     const int nOwnWords = a.Ppad / 4, nMaskWords = a.Ppad / 32, nDirtyWords = (a.Rp + 31) / 32;
-    const int nBlocks = a.Ppad / 128, nGroups = (R + 31) / 32;
+    const int nBlocks = a.Ppad / 128;
 
     // ---- load the chain state: three TMA bulk copies on one mbarrier
     if (tid == 0) {
@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                         const double2 ya = *reinterpret_cast<const double2 *>(a.py + 4 * w), yb = *reinterpret_cast<const double2 *>(a.py + 4 * w + 2);
                         const double2 za = *reinterpret_cast<const double2 *>(a.pz + 4 * w), zb = *reinterpret_cast<const double2 *>(a.pz + 4 * w + 2);
                         const double X[4] = {xa.x, xa.y, xb.x, xb.y}, Y[4] = {ya.x, ya.y, yb.x, yb.y}, Z[4] = {za.x, za.y, zb.x, zb.y};
+                        const int4 rid = *reinterpret_cast<const int4 *>(a.rayid + 4 * w);  // loaded with the coordinates: no dependent load later
+                        const int RID[4] = {rid.x, rid.y, rid.z, rid.w};
                         const int mv = (act == 4) ? pidx : -1;
                         uint32_t tags = 0;
 #pragma unroll
@@ -373,7 +375,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                             s_own32[w] = ow | tags;
 #pragma unroll
                             for (int q = 0; q < 4; q++)
-                                if ((tags >> (8 * q + 7)) & 1u) mark_dirty(s_dirty, a.rayid, 4 * w + q);
+                                if (((tags >> (8 * q + 7)) & 1u) && (q == 0 || RID[q] != RID[q - 1] || !((tags >> (8 * q - 1)) & 1u)))
+                                    atomicOr(&s_dirty[RID[q] >> 5], 1u << (RID[q] & 31));
                         }
                     } else {
                         const uint32_t eq = __vcmpeq4(ow, kk);  // bytes owned by the killed / changed nucleus
@@ -429,13 +432,13 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 __syncthreads();
                 // ======================================================== C: t* of touched rays, one thread per sorted ray
 #pragma unroll 1
-                for (int g = warp; g < nGroups; g += ST / 32) {
-                    const uint32_t bits = s_dirty[g];
-                    if (bits) {
-                        const int r = g * 32 + lane;
-                        if ((bits >> lane) & 1u) {
+                for (int slot = 0; slot * 128 < R; slot++) {  // sorted rays dealt round-robin to the 4 warps: rank = slot*128 + lane*4 + warp
+                    const int r = slot * 128 + lane * 4 + warp;
+                    const bool on = r < R && ((s_dirty[r >> 5] >> (r & 31)) & 1u);
+                    if (__any_sync(0xffffffffu, on)) {
+                        if (on) {
                             const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, Rp, r, q0, n, [&](uint8_t o) -> double { return s_zlut[o]; });
+                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, a.ldT, r, q0, n, [&](uint8_t o) -> double { return s_zlut[o]; });
                         }
                     }
                 }

@@ -78,16 +78,33 @@ __device__ __forceinline__ double warp_sum_canonical(double v) {
 // bit-identical to the oracle's).  One THREAD walks one ray; rays are sorted by length so the 32 rays of a warp finish
 // together, and dt is stored segment-major (dtT[j][ray]) so the warp's loads coalesce.  n = #points of the ray,
 // `last` = common trip bound of the warp (max n over its active lanes) to keep the loop warp-uniform.
+// Column of (length-sorted) ray r in dtT.  The sampler deals sorted rays to its 4 warps round-robin (rank = slot*128 +
+// lane*4 + warp) so that every warp gets the same mix of ray lengths; dtT columns are stored in thread order
+// (slot*128 + warp*32 + lane) so that the warp's loads still coalesce.
+__host__ __device__ __forceinline__ int dt_col(int r) { return (r & ~127) | ((r & 3) << 5) | ((r & 127) >> 2); }
+
 template <typename OwnerT, typename ZetaOf>
-__device__ __forceinline__ double ray_tstar_seq(const OwnerT *__restrict__ owner, const double *__restrict__ dtT, int Rp, int r,
+__device__ __forceinline__ double ray_tstar_seq(const OwnerT *__restrict__ owner, const double *__restrict__ dtT, int ldT, int r,
                                                 int p0, int n, ZetaOf zeta_of) {
     double acc = 0.0;
     if (n > 1) {
+        const double *__restrict__ col = dtT + dt_col(r);
         double za = zeta_of(owner[p0]);
-#pragma unroll 4
-        for (int j = 0; j < n - 1; j++) {
+        int j = 0;
+        for (; j + 8 <= n - 1; j += 8) {  // 8 independent dt loads in flight, then the ordered adds
+            double d[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) d[u] = col[(size_t)(j + u) * ldT];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double zb = zeta_of(owner[p0 + j + u + 1]);
+                acc = __dadd_rn(acc, seg_term(d[u], za, zb));
+                za = zb;
+            }
+        }
+        for (; j < n - 1; j++) {
             const double zb = zeta_of(owner[p0 + j + 1]);
-            acc = __dadd_rn(acc, seg_term(dtT[(size_t)j * Rp + r], za, zb));
+            acc = __dadd_rn(acc, seg_term(col[(size_t)j * ldT], za, zb));
             za = zb;
         }
     }
@@ -154,7 +171,8 @@ struct tonga_ctx {
     double *d_px = nullptr, *d_py = nullptr, *d_pz = nullptr;  // [Ppad]
     // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
     // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.
-    double *d_dtT = nullptr;                                   // [max(m-1,1)][Rp] dt = rayL*rayU, segment-major (0 beyond a ray's end)
+    double *d_dtT = nullptr;                                   // [max(m-1,1)][ldT] dt = rayL*rayU, segment-major, column dt_col(r)
+    int ldT = 0;                                               // R rounded up to a multiple of 128
     int32_t *d_rayid = nullptr;                                // [Ppad] sorted ray index of each flat point
     int32_t *d_ray_off = nullptr;                              // [R+1]  CSR offsets over sorted rays
     int32_t *d_ray_orig = nullptr;                             // [R]    sorted ray index -> caller's ray index
