@@ -248,7 +248,12 @@ def main():
         frac_fp = ach_tf / fp64_peak if fp64_peak > 0 else None
         frac_hbm = ach_gb / peaks["hbm_gbs"]
         props_rank = float(n) * args.iters * args.steps
-        roof = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": frac_hbm, "traffic": None,
+        try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch's proposal count
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["dram_bytes_per_proposal"] * float(n) * args.iters
+        except Exception:
+            traffic = None
+        roof = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": frac_hbm, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
                 "kernel": "tg_sampler_kernel", "launch_ms": dev_ms / args.steps,
                 "algorithmic_bytes_per_proposal": bytes_ / props_rank, "algorithmic_flop_per_proposal": flops / props_rank,

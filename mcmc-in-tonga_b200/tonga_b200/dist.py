@@ -1,0 +1,86 @@
+"""Chain sharding across the GPUs of one box + gathering the posterior ensembles.
+
+The reference's only parallelism is `pmap` over independent chains (main_inversion.jl:15): chains never interact, so the
+path shards with NO data-path collective.  One process per GPU (torchrun); rank g owns the contiguous block of chains
+`shard(n_total, world, g)`; device Philox streams are keyed by the GLOBAL chain id, so every chain produces the same
+samples whatever the GPU count.  torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is used only to
+gather the thinned ensembles (model_hist) -- the analogue of pmap returning `models` to the master.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard(n_total: int, world: int, rank: int):
+    """Contiguous block of chains for `rank`: (first global chain index, count).  Sizes differ by at most one."""
+    base, rem = divmod(n_total, world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+class DeviceArray:
+    """Zero-copy view of library-owned device memory for torch (`torch.as_tensor(DeviceArray(...), device='cuda')`)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def history_tensors(chains, device):
+    """The packed on-device history of a `Chains` batch as torch tensors (zero-copy views of the library's buffers)."""
+    import torch
+    p = chains.device_ptrs()
+    n, H, KC, R = chains.n, chains.hist_cap, chains.KC, chains.ctx.R
+    mk = lambda key, shape, ts: torch.as_tensor(DeviceArray(p[key], shape, ts), device=device)
+    return {"n_hist": mk("n_hist", (n,), "<i4"), "K": mk("hist_K", (n, H), "<i4"), "cells": mk("hist_cells", (n, H, 4, KC), "<f8"),
+            "phi": mk("hist_phi", (n, H), "<f8"), "ptS": mk("hist_ptS", (n, H, R), "<f8")}
+
+
+def gather_ensembles(local: dict, counts, group=None):
+    """All-gather per-rank ensembles whose leading dimension is the rank's chain count (ragged across ranks).
+
+    local : dict name -> tensor [n_local, ...] (CPU tensors under gloo, CUDA tensors under NCCL)
+    counts: chains per rank (len = world).  Returns dict name -> tensor [sum(counts), ...] in global chain order.
+    Ragged blocks are padded to max(counts) for the collective (all_gather needs equal shapes) and trimmed after."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return {k: v.clone() for k, v in local.items()}
+    nmax = int(max(counts))
+    out = {}
+    for k, v in local.items():
+        pad = torch.zeros((nmax,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        pad[:v.shape[0]] = v
+        buf = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(buf, pad.contiguous(), group=group)
+        out[k] = torch.cat([b[:int(c)] for b, c in zip(buf, counts)], dim=0)
+    return out
+
+
+def run_sharded(TD_parameters, dataStruct, n_chains_total: int, seed: int = 20260000, first_chain: int = 1, gather: bool = True):
+    """The whole chain farm on all ranks of the current process group: build_starting, n_iter iterations, thinning, then
+    (optionally) the gathered ensemble on every rank.  Call under torchrun with one process per GPU."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from .api import Chains, Context
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    start, count = shard(n_chains_total, world, rank)
+    ctx = Context(dataStruct, TD_parameters, device=local_rank)
+    ch = Chains(ctx, count, chain_id0=first_chain + start, seed=seed)
+    ch.build_starting()
+    ch.run(int(TD_parameters.n_iter))
+    if not gather:
+        return ch, None
+    dev = torch.device("cuda", local_rank)
+    local = {k: v.clone() for k, v in history_tensors(ch, dev).items()}
+    counts = [shard(n_chains_total, world, r)[1] for r in range(world)]
+    return ch, gather_ensembles(local, counts)
+
+
+def ensemble_to_numpy(ens: dict) -> dict:
+    return {k: v.detach().cpu().numpy() for k, v in ens.items()}

@@ -1,0 +1,70 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo processes exercise chain sharding and the ensemble gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_partitions_exactly():
+    from tonga_b200.dist import shard
+    for n in (1, 7, 8, 1024, 8192, 1000):
+        for w in (1, 2, 3, 4, 8):
+            blocks = [shard(n, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+            for (s0, c0), (s1, _) in zip(blocks, blocks[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_history(global_ids, H=3, KC=8, R=5):
+    """Deterministic per-chain 'history' that depends only on the GLOBAL chain id (as the Philox streams do)."""
+    n = len(global_ids)
+    g = np.asarray(global_ids, dtype=np.float64)
+    return {"n_hist": torch.full((n,), H, dtype=torch.int32),
+            "K": torch.from_numpy((5 + (np.asarray(global_ids)[:, None] + np.arange(H)[None]) % 4).astype(np.int32)),
+            "cells": torch.from_numpy(g[:, None, None, None] + np.arange(H)[None, :, None, None] * 0.5 + np.zeros((n, H, 4, KC))),
+            "phi": torch.from_numpy(100.0 + g[:, None] + np.arange(H)[None] * 0.25),
+            "ptS": torch.from_numpy(g[:, None, None] * 0.1 + np.zeros((n, H, R)))}
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tonga_b200.dist import gather_ensembles, shard
+        start, count = shard(n_total, world, rank)
+        local = _fake_history(list(range(start, start + count)))
+        counts = [shard(n_total, world, r)[1] for r in range(world)]
+        ens = gather_ensembles(local, counts)
+        q.put((rank, {k: v.numpy() for k, v in ens.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [7, 8])
+def test_gather_is_independent_of_world_size(n_total):
+    """the gathered ensemble on every rank equals the single-process result (ragged split too)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ref = {k: v.numpy() for k, v in _fake_history(list(range(n_total))).items()}
+    for _rank, ens in got:
+        for k in ref:
+            assert ens[k].shape == ref[k].shape and np.array_equal(ens[k], ref[k]), k
