@@ -117,6 +117,10 @@ int tonga_chains_build_starting(tonga_chains *ch);
 /* ... or from the host (e.g. a checkpoint, TD_inversion_function.jl:56): K[nChains], cells[nChains][4][Kcap],
  * noise[nChains] or NULL.  Both run a full evaluate to establish owners, t*, phi. */
 int tonga_chains_set_models(tonga_chains *ch, int32_t Kcap, const int32_t *K, const double *cells, const double *noise);
+/* Distance arithmetic of the incremental update.  0 (default): FP32 screening of every nearest-nucleus comparison with an
+ * exact FP64 recheck of all comparisons that fall inside a rigorous rounding-error band (cell indices stay bit-exact);
+ * 1: every comparison in exact FP64 (same results, slower; used by the tests to prove the screening changes nothing). */
+int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only);
 /* per-chain inverse temperature (parallel tempering extension; 1.0 = reference); NULL resets to 1 */
 int tonga_chains_set_beta(tonga_chains *ch, const double *beta);
 

@@ -189,6 +189,26 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     chk(upload(&ctx->d_px, px, ctx->stream));
     chk(upload(&ctx->d_py, py, ctx->stream));
     chk(upload(&ctx->d_pz, pz, ctx->stream));
+    {   // fl32 copies + the rigorous screening band: with u = 2^-24 and M = max |coordinate| (points and box),
+        // |D32 - D| <= 11u*D32 + 7.5u*M^2 for any evaluation order; alpha = 16u and beta = 12u*M^2 leave a 1.4x margin.
+        std::vector<float> xf(Ppad), yf(Ppad), zf(Ppad);
+        double M = 0.0;
+        for (int64_t i = 0; i < Ppad; i++) {
+            xf[i] = (float)px[i]; yf[i] = (float)py[i]; zf[i] = (float)pz[i];
+            if (i < P) {
+                for (double v : {px[i], py[i], pz[i]})
+                    if (std::fabs(v) > M) M = std::fabs(v);  // NaN never compares greater
+            }
+        }
+        for (double v : {params->xmin, params->xmax, params->ymin, params->ymax, params->zmin, params->zmax})
+            if (std::fabs(v) > M) M = std::fabs(v);
+        const double u = 5.9604644775390625e-08;
+        ctx->tol_alpha = (float)(16.0 * u);
+        ctx->tol_beta2 = (float)(2.0 * 12.0 * u * M * M * 1.0000002);
+        chk(upload(&ctx->d_pxf, xf, ctx->stream));
+        chk(upload(&ctx->d_pyf, yf, ctx->stream));
+        chk(upload(&ctx->d_pzf, zf, ctx->stream));
+    }
     chk(upload(&ctx->d_dtT, dtT, ctx->stream));
     chk(upload(&ctx->d_rayid, rayid, ctx->stream));
     chk(upload(&ctx->d_ray_off, sray_off, ctx->stream));
@@ -211,6 +231,7 @@ extern "C" void tonga_destroy(tonga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dtT);
+    cudaFree(ctx->d_pxf); cudaFree(ctx->d_pyf); cudaFree(ctx->d_pzf);
     cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_ray_orig); cudaFree(ctx->d_point_orig);
     cudaFree(ctx->d_tS); cudaFree(ctx->d_sig);
     cudaFree(ctx->d_tiles);

@@ -121,6 +121,7 @@ struct tonga_chains {
     unsigned long long seed = 0;
     long long iter_done = 0;
     bool have_models = false;
+    int exact_only = 0;
     size_t smem = 0;
     // device state
     int32_t *d_K = nullptr;
@@ -281,6 +282,12 @@ extern "C" int tonga_chains_set_models(tonga_chains *ch, int32_t Kcap, const int
     return TONGA_OK;
 }
 
+extern "C" int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_exact_only: NULL");
+    ch->exact_only = exact_only ? 1 : 0;
+    return TONGA_OK;
+}
+
 extern "C" int tonga_chains_set_beta(tonga_chains *ch, const double *beta) {
     if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_beta: NULL");
     std::lock_guard<std::mutex> lk(ch->ctx->mu);
@@ -311,6 +318,8 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
 
     tg::SamplerArgs a{};
     a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
+    a.pxf = ctx->d_pxf; a.pyf = ctx->d_pyf; a.pzf = ctx->d_pzf; a.tol_alpha = ctx->tol_alpha; a.tol_beta2 = ctx->tol_beta2;
+    a.exact_only = ch->exact_only;
     a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig;
     a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
     a.prm = ctx->prm;

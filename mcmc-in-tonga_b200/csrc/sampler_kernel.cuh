@@ -16,6 +16,9 @@ namespace tg {
 struct SamplerArgs {
     // geometry (device order: rays sorted by length)
     const double *px, *py, *pz, *dtT, *tS, *sig;
+    const float *pxf, *pyf, *pzf;   // fl32 copies (screening)
+    float tol_alpha, tol_beta2;     // screening band
+    int exact_only;                 // 1 = skip the FP32 screening (pure FP64 path; used by tests)
     const int32_t *rayid, *ray_off, *ray_orig;
     int R, Rp, KC, ldT;
     int P, Ppad;
@@ -53,12 +56,13 @@ struct Prop {  // proposal of the current iteration, broadcast through shared me
     double x, y, z, zeta, u;
     double aux;            // birth: czeta (:81); death: zetanew (:146)
     double ox, oy, oz;     // move: the old position (the nucleus array holds the proposed one during B..E)
+    double ztag;           // zeta of the implicit new owner of tagged bytes (birth: zetanew; move: zeta[idx])
 };
 
 constexpr int SQ_CAP = 64;  // orphan queue entries per warp
 
 struct SmemLayout {
-    size_t o_owner, o_mask, o_tstar, o_tnew, o_dirty, o_nuc, o_zlut, o_scr, o_prop, o_queue, o_bar, total;
+    size_t o_owner, o_mask, o_tstar, o_tnew, o_dirty, o_nuc, o_nucf, o_zlut, o_scr, o_prop, o_queue, o_bar, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int Ppad, int Rp, int KC) {
     SmemLayout L;
@@ -70,7 +74,8 @@ __host__ __device__ inline SmemLayout smem_layout(int Ppad, int Rp, int KC) {
     L.o_tnew = take(8 * (size_t)Rp);
     L.o_dirty = take(4 * (size_t)((Rp + 31) / 32));
     L.o_nuc = take(8 * 4 * (size_t)KC);
-    L.o_zlut = take(8 * 256);
+    L.o_nucf = take(4 * 3 * (size_t)KC);
+    L.o_zlut = take(8 * 128);
     L.o_scr = take(8 * 4);
     L.o_prop = take(sizeof(Prop));
     L.o_queue = take((size_t)(ST / 32) * SQ_CAP * (Ppad <= 65536 ? 2 : 4));
@@ -127,6 +132,27 @@ __device__ __noinline__ void normal_pair(double u1, double u2, double &n0, doubl
     n1 = rr * sn;
 }
 
+// FP32 screening of the orphan rescan: best and second-best squared distance; returns the winner, or -1 if the two
+// are closer than the error band (or the winner is within the band of the 1e9 "no nucleus" threshold) -> exact rescan.
+__device__ __noinline__ int rescan_point_f32(const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf,
+                                             const float *fx, const float *fy, const float *fz, int K, int skip, int p,
+                                             float tol_alpha, float tol_beta2) {
+    const float x = pxf[p], y = pyf[p], z = pzf[p];
+    float d1 = 1e9f, d2 = 1e9f;
+    int i1 = TG_OWNER_NONE;
+#pragma unroll 4
+    for (int i = 0; i < K; i++) {
+        const float d = (i == skip) ? 3e38f : dist2_f32(fx[i], fy[i], fz[i], x, y, z);
+        const bool lt = d < d1;
+        d2 = lt ? d1 : fminf(d2, d);
+        i1 = lt ? i : i1;
+        d1 = lt ? d : d1;
+    }
+    const float tol = fmaf(tol_alpha, d1 + d2, tol_beta2);
+    if (!(d2 - d1 > tol)) return -1;  // ambiguous (or NaN coordinates)
+    return i1;
+}
+
 // Orphan rescan: nearest nucleus of flat point p among all K nuclei except `skip` (strict <, ascending index).
 __device__ __noinline__ int rescan_point(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                                          const double *nx, const double *ny, const double *nz, int K, int skip, int p) {
@@ -153,6 +179,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     uint32_t *s_dirty = reinterpret_cast<uint32_t *>(smem + L.o_dirty);
     double *s_nx = reinterpret_cast<double *>(smem + L.o_nuc);
     double *s_ny = s_nx + a.KC, *s_nz = s_ny + a.KC, *s_zeta = s_nz + a.KC;
+    float *s_fx = reinterpret_cast<float *>(smem + L.o_nucf);
+    float *s_fy = s_fx + a.KC, *s_fz = s_fy + a.KC;
     double *s_zlut = reinterpret_cast<double *>(smem + L.o_zlut);
     double *s_scr = reinterpret_cast<double *>(smem + L.o_scr);
     Prop *s_prop = reinterpret_cast<Prop *>(smem + L.o_prop);
@@ -185,6 +213,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             s2u(s_bar))
         : "memory");
     __syncthreads();
+    for (int i = tid; i < 3 * KC; i += ST) s_fx[i] = (float)s_nx[i];  // fl32 copies of the nuclei (x, y, z)
+    __syncthreads();
 
     int K = a.K[chain];
     double phi = a.phi[chain];
@@ -207,7 +237,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         if (warp == 0) {
             Prop pr;
             pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
-            pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = 0.0;
+            pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
             double uu[8];
             if (a.mode == 0) {
                 const Philox philox{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
@@ -297,7 +327,10 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                         if (valid) {  // from here to the accept decision the nucleus array holds the PROPOSED position
                             pr.ox = s_nx[pr.idx]; pr.oy = s_ny[pr.idx]; pr.oz = s_nz[pr.idx];
                             __syncwarp();
-                            if (lane == 0) { s_nx[pr.idx] = pr.x; s_ny[pr.idx] = pr.y; s_nz[pr.idx] = pr.z; }
+                            if (lane == 0) {
+                                s_nx[pr.idx] = pr.x; s_ny[pr.idx] = pr.y; s_nz[pr.idx] = pr.z;
+                                s_fx[pr.idx] = (float)pr.x; s_fy[pr.idx] = (float)pr.y; s_fz[pr.idx] = (float)pr.z;
+                            }
                         }
                     }
                 }
@@ -313,12 +346,11 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             pr.do_eval = valid;
             // zlut: owner byte -> zeta under the proposed model (bit 7 set = switches to the implicit new owner)
             if (valid && act != 5) {
-                const double ztag = (act == 1) ? pr.zeta : (act == 4 ? s_zeta[pr.idx] : 0.0);
+                pr.ztag = (act == 1) ? pr.zeta : (act == 4 ? s_zeta[pr.idx] : 0.0);
                 for (int o = lane; o < 128; o += 32) {
                     double zv = (o < K) ? s_zeta[o] : 0.0;
                     if (act == 3 && o == pr.idx) zv = pr.zeta;
                     s_zlut[o] = zv;
-                    s_zlut[128 + o] = ztag;
                 }
             }
             if (lane == 0) {
@@ -343,6 +375,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         if (do_eval) {
             if (act != 5) {
                 const double cx = s_prop->x, cy = s_prop->y, cz = s_prop->z;
+                const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
                 // ======================================================== B1: flat pass over this warp's 128-point blocks
 #pragma unroll 1
                 for (int blk = warp; blk < nBlocks; blk += ST / 32) {
@@ -350,22 +383,52 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     uint32_t ow = s_own32[w];
                     uint32_t mbits = 0;
                     if (act == 1 || act == 4) {
-                        const double2 xa = *reinterpret_cast<const double2 *>(a.px + 4 * w), xb = *reinterpret_cast<const double2 *>(a.px + 4 * w + 2);
-                        const double2 ya = *reinterpret_cast<const double2 *>(a.py + 4 * w), yb = *reinterpret_cast<const double2 *>(a.py + 4 * w + 2);
-                        const double2 za = *reinterpret_cast<const double2 *>(a.pz + 4 * w), zb = *reinterpret_cast<const double2 *>(a.pz + 4 * w + 2);
-                        const double X[4] = {xa.x, xa.y, xb.x, xb.y}, Y[4] = {ya.x, ya.y, yb.x, yb.y}, Z[4] = {za.x, za.y, zb.x, zb.y};
                         const int4 rid = *reinterpret_cast<const int4 *>(a.rayid + 4 * w);  // loaded with the coordinates: no dependent load later
                         const int RID[4] = {rid.x, rid.y, rid.z, rid.w};
                         const int mv = (act == 4) ? pidx : -1;
-                        uint32_t tags = 0;
+                        uint32_t tags = 0, amb = 0;
+                        if (!a.exact_only) {
+                            // FP32 screening (packed FADD2/FMUL2/FFMA2 for the candidate distance); points whose two distances are
+                            // closer than the rigorous error band go to the exact FP64 comparison below.
+                            const float4 xf = *reinterpret_cast<const float4 *>(a.pxf + 4 * w);
+                            const float4 yf = *reinterpret_cast<const float4 *>(a.pyf + 4 * w);
+                            const float4 zf = *reinterpret_cast<const float4 *>(a.pzf + 4 * w);
+                            const float2 ncx = make_float2(-cxf, -cxf), ncy = make_float2(-cyf, -cyf), ncz = make_float2(-czf, -czf);
+                            float2 ex = __fadd2_rn(make_float2(xf.x, xf.y), ncx), ey = __fadd2_rn(make_float2(yf.x, yf.y), ncy), ez = __fadd2_rn(make_float2(zf.x, zf.y), ncz);
+                            const float2 dc01 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+                            ex = __fadd2_rn(make_float2(xf.z, xf.w), ncx); ey = __fadd2_rn(make_float2(yf.z, yf.w), ncy); ez = __fadd2_rn(make_float2(zf.z, zf.w), ncz);
+                            const float2 dc23 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+                            const float X[4] = {xf.x, xf.y, xf.z, xf.w}, Y[4] = {yf.x, yf.y, yf.z, yf.w}, Z[4] = {zf.x, zf.y, zf.z, zf.w};
+                            const float DC[4] = {dc01.x, dc01.y, dc23.x, dc23.y};
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int o = (ow >> (8 * q)) & 0xFF;
-                            if (o == mv) {
-                                mbits |= 1u << q;  // move, type A: owned by the moved nucleus -> rescan in B2
-                            } else {
-                                const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], X[q], Y[q], Z[q]);
-                                const double d_c = dist2_exact(cx, cy, cz, X[q], Y[q], Z[q]);
+                            for (int q = 0; q < 4; q++) {
+                                const int o = (ow >> (8 * q)) & 0xFF;
+                                if (o == mv) {
+                                    mbits |= 1u << q;  // move, type A: owned by the moved nucleus -> rescan in B2
+                                } else {
+                                    const float d_o = (o == TG_OWNER_NONE) ? 1e9f : dist2_f32(s_fx[o], s_fy[o], s_fz[o], X[q], Y[q], Z[q]);
+                                    const float diff = DC[q] - d_o;
+                                    const float tol = fmaf(a.tol_alpha, DC[q] + d_o, a.tol_beta2);
+                                    if (diff < -tol) tags |= 0x80u << (8 * q);
+                                    else if (!(diff > tol) && DC[q] == DC[q]) amb |= 1u << q;  // inside the band (NaN coordinates never switch)
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                if ((int)((ow >> (8 * q)) & 0xFF) == mv) mbits |= 1u << q;
+                                else amb |= 1u << q;
+                            }
+                        }
+                        if (amb) {  // exact FP64 comparison, MCsub.jl:254-255 semantics
+#pragma unroll 1
+                            for (int q = 0; q < 4; q++) {
+                                if (!((amb >> q) & 1u)) continue;
+                                const int o = (ow >> (8 * q)) & 0xFF;
+                                const int p = 4 * w + q;
+                                const double x = a.px[p], y = a.py[p], z = a.pz[p];
+                                const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], x, y, z);
+                                const double d_c = dist2_exact(cx, cy, cz, x, y, z);
                                 // birth: the new nucleus has the highest index -> strict <.  move: index mv also wins exact ties against o > mv.
                                 const bool sw = (d_c < d_o) || (act == 4 && d_c == d_o && mv < o && o != TG_OWNER_NONE);
                                 if (sw) tags |= 0x80u << (8 * q);
@@ -406,7 +469,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     auto drain = [&](int cnt) {  // lanes < cnt take the top `cnt` queue entries
                         if (lane < cnt) {
                             const int p = (int)s_queue[qn - cnt + lane];
-                            const int bi = rescan_point(a.px, a.py, a.pz, s_nx, s_ny, s_nz, K, skip, p);
+                            int bi = a.exact_only ? -1 : rescan_point_f32(a.pxf, a.pyf, a.pzf, s_fx, s_fy, s_fz, K, skip, p, a.tol_alpha, a.tol_beta2);
+                            if (bi < 0) bi = rescan_point(a.px, a.py, a.pz, s_nx, s_ny, s_nz, K, skip, p);  // exact FP64
                             s_owner[p] = (uint8_t)bi;  // death: old numbering, renumbered on accept
                             if (act == 2 || bi != pidx) mark_dirty(s_dirty, a.rayid, p);
                         }
@@ -431,6 +495,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 }
                 __syncthreads();
                 // ======================================================== C: t* of touched rays, one thread per sorted ray
+                const double ztag = s_prop->ztag;
 #pragma unroll 1
                 for (int slot = 0; slot * 128 < R; slot++) {  // sorted rays dealt round-robin to the 4 warps: rank = slot*128 + lane*4 + warp
                     const int r = slot * 128 + lane * 4 + warp;
@@ -438,7 +503,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     if (__any_sync(0xffffffffu, on)) {
                         if (on) {
                             const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, a.ldT, r, q0, n, [&](uint8_t o) -> double { return s_zlut[o]; });
+                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, a.ldT, r, q0, n,
+                                                               [&](uint8_t o) -> double { return (o & 0x80) ? ztag : s_zlut[o]; });
                         }
                     }
                 }
@@ -539,17 +605,22 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
                         const int i = pidx + lane + 32 * s;
-                        if (i < K - 1) { s_nx[i] = vx[s]; s_ny[i] = vy[s]; s_nz[i] = vz[s]; s_zeta[i] = vt[s]; }
+                        if (i < K - 1) {
+                            s_nx[i] = vx[s]; s_ny[i] = vy[s]; s_nz[i] = vz[s]; s_zeta[i] = vt[s];
+                            s_fx[i] = (float)vx[s]; s_fy[i] = (float)vy[s]; s_fz[i] = (float)vz[s];
+                        }
                     }
                 }
             }
             if (tid == 0) {
                 if (act == 1 && accepted) {  // append!, :85-88
                     s_nx[K] = s_prop->x; s_ny[K] = s_prop->y; s_nz[K] = s_prop->z; s_zeta[K] = s_prop->zeta;
+                    s_fx[K] = (float)s_prop->x; s_fy[K] = (float)s_prop->y; s_fz[K] = (float)s_prop->z;
                 } else if (act == 3 && accepted) {
                     s_zeta[pidx] = s_prop->zeta;
                 } else if (act == 4 && !accepted) {
                     s_nx[pidx] = s_prop->ox; s_ny[pidx] = s_prop->oy; s_nz[pidx] = s_prop->oz;
+                    s_fx[pidx] = (float)s_prop->ox; s_fy[pidx] = (float)s_prop->oy; s_fz[pidx] = (float)s_prop->oz;
                 }
             }
             if (act != 5) {

@@ -47,6 +47,12 @@ __device__ __forceinline__ double dist2_exact(double mx, double my, double mz, d
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// FP32 screening distance (any rounding / FMA order is fine: the error band of DESIGN.md 4.3 covers it)
+__device__ __forceinline__ float dist2_f32(float mx, float my, float mz, float x, float y, float z) {
+    const float dx = mx - x, dy = my - y, dz = mz - z;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
 __device__ __forceinline__ double div1000_exact(double a) {
     // correctly rounded a / 1000 (Markstein: y = RN(1/b), q0 = a*y, r = a - b*q0 exactly, q = q0 + r*y)
     const double y = 0.001;
@@ -169,6 +175,8 @@ struct tonga_ctx {
     int max_npts = 0;
     // device geometry (SoA, flat point order, padded with NaN coordinates / zero dt)
     double *d_px = nullptr, *d_py = nullptr, *d_pz = nullptr;  // [Ppad]
+    float *d_pxf = nullptr, *d_pyf = nullptr, *d_pzf = nullptr; // [Ppad] fl32 copies for the FP32 screening pass
+    float tol_alpha = 0.f, tol_beta2 = 0.f;                    // screening band: |dc - do| <= alpha*(dc+do) + beta2 -> exact FP64 recheck
     // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
     // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.
     double *d_dtT = nullptr;                                   // [max(m-1,1)][ldT] dt = rayL*rayU, segment-major, column dt_col(r)

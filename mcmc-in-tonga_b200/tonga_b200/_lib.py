@@ -58,6 +58,7 @@ SYMBOLS = {
     "tonga_chains_destroy": (None, [_P]),
     "tonga_chains_build_starting": (C.c_int, [_P]),
     "tonga_chains_set_models": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp]),
+    "tonga_chains_set_exact_only": (C.c_int, [_P, C.c_int32]),
     "tonga_chains_set_beta": (C.c_int, [_P, c_dp]),
     "tonga_chains_run": (C.c_int, [_P, C.c_int64, C.c_int32, _P, c_bp, c_dp, c_ip]),
     "tonga_chains_get_state": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),

@@ -161,6 +161,10 @@ class Chains:
         noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
         check(self.lib.tonga_chains_set_models(self._h, cells.shape[2], ip(K), dp(cells), dp(noise)))
 
+    def set_exact_only(self, flag: bool):
+        """True: every nearest-nucleus comparison in exact FP64 (default: FP32 screening + exact recheck of near ties)."""
+        check(self.lib.tonga_chains_set_exact_only(self._h, 1 if flag else 0))
+
     def set_beta(self, beta):
         beta = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
         check(self.lib.tonga_chains_set_beta(self._h, dp(beta)))

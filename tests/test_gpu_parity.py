@@ -373,3 +373,46 @@ def test_sharded_chains_match_unsharded(tonga):
         parts.append(h)
     for k in ("n_hist", "K", "cells", "phi", "ptS", "iter", "action", "accept"):
         assert np.array_equal(np.concatenate([parts[0][k], parts[1][k]]), hf[k]), k
+
+
+def test_fp32_screening_changes_nothing(tonga):
+    """The FP32 screening pass + exact FP64 recheck of near ties must give the same chain, bit for bit, as the pure FP64
+    path (owners, t*, phi, nuclei, accept decisions) -- on the Tonga set and on a set engineered to be hard for FP32:
+    coordinates offset by 5e4 km (large |x| -> coarse fl32 grid) with nuclei mirrored about ray points (exact ties)."""
+    import copy
+    from tonga_b200.api import Chains, Context, pack_models
+    from tonga_b200.data import make_datastruct
+    from tonga_b200.structs import StepRangeLen
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 800.0, 400.0, 10.0
+    # hard set: shift everything far from the origin
+    off = 5.0e4
+    dsh = make_datastruct(ds.rayX + off, ds.rayY + off, ds.rayZ, ds.U, ds.tS, ds.allSig, p,
+                          box=(StepRangeLen(ds.xVec.min() + off, 20, ds.xVec.max() + off), StepRangeLen(ds.yVec.min() + off, 20, ds.yVec.max() + off), ds.zVec))
+    for data in (ds, dsh):
+        ctx = Context(data, p)
+        outs = []
+        for exact in (False, True):
+            ch = Chains(ctx, 24, seed=5)
+            ch.set_exact_only(exact)
+            ch.build_starting()
+            if data is dsh:  # plant exact ties: nucleus 1 = mirror image of nucleus 0 about a ray point
+                st = ch.state(want_ptS=False)
+                K, cells = st["K"].copy(), st["cells"].copy()
+                pt = np.array([data.rayX[3, 7], data.rayY[3, 7], data.rayZ[3, 7]])
+                for c in range(len(K)):
+                    cells[c, :3, 1] = 2 * pt - cells[c, :3, 0]
+                    cells[c, 2, 1] = min(max(cells[c, 2, 1], 0.0), 660.0)
+                ch.set_models(K, cells)
+            out = ch.run(800, record=True, trace=True)
+            st = ch.state(want_owners=True)
+            assert ch.verify() == (0, 0.0, 0.0)
+            outs.append((out, st))
+            ch.close()
+        (o0, s0), (o1, s1) = outs
+        assert np.array_equal(o0["accept"], o1["accept"]) and np.array_equal(o0["phi"], o1["phi"]) and np.array_equal(o0["K"], o1["K"])
+        assert np.array_equal(o0["recs"], o1["recs"])
+        for k in ("K", "cells", "phi", "ptS", "owners"):
+            assert np.array_equal(s0[k], s1[k]), k
+        ctx.close()
