@@ -214,8 +214,11 @@ def main():
     value = total_props / (dev_ms_max * 1e-3)
 
     # ---- end-to-end arm through host buffers
+    from tonga_b200.api import pinned_empty
     st = ch.state(want_ptS=False)
-    K0, cells0 = st["K"].copy(), st["cells"].copy()
+    K0 = pinned_empty(st["K"].shape, np.int32); K0[:] = st["K"]
+    cells0 = pinned_empty(st["cells"].shape, np.float64); cells0[:] = st["cells"]
+    hist_buf, state_buf = ch.alloc_buffers(pinned=True)  # page-locked host buffers, reused every step
     h2d = K0.nbytes + cells0.nbytes
     d2h = 0
     e2e_t = 0.0
@@ -226,8 +229,8 @@ def main():
         ch.reset()
         ch.set_models(K0, cells0)          # H2D of the start models + full evaluate
         ch.run(args.iters)                 # the proposal loop
-        hist = ch.history()                # D2H of model_hist (nuclei, zeta, phi, ptS of every kept model)
-        fin = ch.state(want_ptS=True)      # D2H of the final models
+        hist = ch.history(out=hist_buf)    # D2H of model_hist (nuclei, zeta, phi, ptS of every kept model)
+        fin = ch.state(out=state_buf)      # D2H of the final models
         t1 = time.perf_counter()
         tt = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -160,6 +160,11 @@ int tonga_chains_kcap(const tonga_chains *ch);
 int tonga_chains_device_ptrs(tonga_chains *ch, void **n_hist, void **hist_K, void **hist_cells, void **hist_phi,
                              void **hist_ptS, void **state_K, void **state_cells, void **state_phi);
 
+/* Page-locked host buffers for callers that want full-speed host<->device copies (optional: every entry point also
+ * accepts ordinary pageable memory). */
+int tonga_host_alloc(void **ptr, uint64_t bytes);
+int tonga_host_free(void *ptr);
+
 /* ---- measurement helpers (bench.py): peak FP64 / FP32 FMA rate of this device in TFLOP/s (FMA = 2 flop). */
 int tonga_peak_flops(tonga_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
 

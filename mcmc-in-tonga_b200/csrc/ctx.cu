@@ -256,6 +256,17 @@ extern "C" int tonga_ray_offsets(const tonga_ctx *ctx, int32_t *ray_off) {
     return TONGA_OK;
 }
 
+extern "C" int tonga_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return tg::fail(TONGA_ERR_ARG, "tonga_host_alloc: NULL");
+    *ptr = nullptr;
+    TG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return TONGA_OK;
+}
+extern "C" int tonga_host_free(void *ptr) {
+    if (ptr) TG_CUDA(cudaFreeHost(ptr));
+    return TONGA_OK;
+}
+
 extern "C" int tonga_synchronize(tonga_ctx *ctx) {
     if (!ctx) return tg::fail(TONGA_ERR_ARG, "tonga_synchronize: ctx is NULL");
     TG_CUDA(cudaSetDevice(ctx->device));

@@ -50,6 +50,26 @@ def pack_models(models, Kcap=None):
     return K, cells
 
 
+class _Pinned:
+    def __init__(self, nbytes):
+        self.lib = _lib.load()
+        self.ptr = C.c_void_p()
+        check(self.lib.tonga_host_alloc(C.byref(self.ptr), nbytes))
+        self.nbytes = nbytes
+        self._fin = weakref.finalize(self, self.lib.tonga_host_free, self.ptr)
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory (tonga_host_alloc): full-speed H2D / D2H for the host-buffer entry points.
+    The memory is released when the array (and every view of it) is garbage collected."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    pin = _Pinned(max(count * dtype.itemsize, 1))
+    buf = (C.c_char * pin.nbytes).from_address(pin.ptr.value)
+    buf._pin = pin  # ctypes instances carry a __dict__: the numpy array keeps `buf` (its base) alive, `buf` keeps `pin` alive
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
 class Context:
     """Device-resident ray geometry + observations: what `dataStruct` is to evaluate()."""
 
@@ -184,14 +204,17 @@ class Chains:
         check(self.lib.tonga_chains_run(self._h, n_iter, mode, None if recs is None else recs.ctypes.data, bp(acc), dp(phi), ip(K)))
         return dict(recs=recs, accept=acc, phi=phi, K=K)
 
-    def state(self, want_ptS=True, want_owners=False):
+    def state(self, want_ptS=True, want_owners=False, out: dict | None = None):
         n, KC = self.n, self.KC
-        K = np.zeros(n, np.int32)
-        cells = np.zeros((n, 4, KC))
-        phi = np.zeros(n)
-        noise = np.zeros(n)
-        ptS = np.zeros((n, self.ctx.R)) if want_ptS else None
-        owners = np.zeros((n, self.ctx.P), np.int32) if want_owners else None
+        if out is not None:  # caller-owned (e.g. pinned) buffers, reused across calls
+            K, cells, phi, noise, ptS, owners = out["K"], out["cells"], out["phi"], out["noise"], out.get("ptS"), out.get("owners")
+        else:
+            K = np.zeros(n, np.int32)
+            cells = np.zeros((n, 4, KC))
+            phi = np.zeros(n)
+            noise = np.zeros(n)
+            ptS = np.zeros((n, self.ctx.R)) if want_ptS else None
+            owners = np.zeros((n, self.ctx.P), np.int32) if want_owners else None
         check(self.lib.tonga_chains_get_state(self._h, KC, ip(K), dp(cells), dp(phi), dp(ptS), dp(noise), ip(owners)))
         return dict(K=K, cells=cells, phi=phi, ptS=ptS, noise=noise, owners=owners)
 
@@ -209,11 +232,23 @@ class Chains:
         check(self.lib.tonga_chains_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
-    def history(self, want_ptS=True):
+    def alloc_buffers(self, pinned=True, want_ptS=True):
+        """Reusable output buffers for history() / state() (page-locked by default)."""
         n, H, KC, R = self.n, self.hist_cap, self.KC, self.ctx.R
-        out = dict(n_hist=np.zeros(n, np.int32), K=np.zeros((n, H), np.int32), cells=np.zeros((n, H, 4, KC)),
-                   phi=np.zeros((n, H)), ptS=np.zeros((n, H, R)) if want_ptS else None, iter=np.zeros((n, H), np.int64),
-                   action=np.zeros((n, H), np.int32), accept=np.zeros((n, H), np.int32), next_action=np.zeros((n, H), np.int32))
+        mk = pinned_empty if pinned else (lambda shape, dt: np.zeros(shape, dt))
+        hist = dict(n_hist=mk((n,), np.int32), K=mk((n, H), np.int32), cells=mk((n, H, 4, KC), np.float64), phi=mk((n, H), np.float64),
+                    ptS=mk((n, H, R), np.float64) if want_ptS else None, iter=mk((n, H), np.int64), action=mk((n, H), np.int32),
+                    accept=mk((n, H), np.int32), next_action=mk((n, H), np.int32))
+        state = dict(K=mk((n,), np.int32), cells=mk((n, 4, KC), np.float64), phi=mk((n,), np.float64), noise=mk((n,), np.float64),
+                     ptS=mk((n, R), np.float64) if want_ptS else None, owners=None)
+        return hist, state
+
+    def history(self, want_ptS=True, out: dict | None = None):
+        n, H, KC, R = self.n, self.hist_cap, self.KC, self.ctx.R
+        if out is None:
+            out = dict(n_hist=np.zeros(n, np.int32), K=np.zeros((n, H), np.int32), cells=np.zeros((n, H, 4, KC)),
+                       phi=np.zeros((n, H)), ptS=np.zeros((n, H, R)) if want_ptS else None, iter=np.zeros((n, H), np.int64),
+                       action=np.zeros((n, H), np.int32), accept=np.zeros((n, H), np.int32), next_action=np.zeros((n, H), np.int32))
         check(self.lib.tonga_chains_get_history(self._h, KC, ip(out["n_hist"]), ip(out["K"]), dp(out["cells"]), dp(out["phi"]),
                                                 dp(out["ptS"]), lp(out["iter"]), ip(out["action"]), ip(out["accept"]),
                                                 ip(out["next_action"])))
