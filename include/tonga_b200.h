@@ -150,6 +150,14 @@ int tonga_chains_last_kernel_ms(tonga_chains *ch, float *ms);
 int tonga_chains_get_history(tonga_chains *ch, int32_t Kcap, int32_t *n_hist, int32_t *hist_K, double *hist_cells,
                              double *hist_phi, double *hist_ptS, int64_t *hist_iter, int32_t *hist_action,
                              int32_t *hist_accept, int32_t *hist_next_action);
+/* Posterior rasterisation, the compute part of plot_model_hist (MCsub.jl:753-825): for every kept model of every chain
+ * evaluate v_nearest (MCsub.jl:247-263, exact FP64) at n_nodes points (X, Y, Z: e.g. xVec x zVec at y = ySlice, :766-768, or
+ * xVec x yVec at z = zSlice, :800-802) and accumulate per node: sum_out[n_nodes] = sum of zeta, sumsq_out[n_nodes] = sum of zeta^2,
+ * *count_out = number of models.  Deterministic: models are summed in (chain, kept index) order.  mean = sum/count;
+ * std (Julia `std`, :775) = sqrt((sumsq - sum^2/count)/(count-1)); mask where std > 5 (:777-781).  Multi-GPU: add the
+ * three outputs across ranks (they are plain sums). */
+int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const double *X, const double *Y, const double *Z, double *sum_out,
+                        double *sumsq_out, int64_t *count_out);
 /* Consistency check on the device: re-run the full evaluate for every chain's current model and compare it with the
  * incrementally maintained state.  owner_mismatch = number of points whose owner differs; max_dphi / max_dts =
  * largest |difference| in phi / t* (the two paths share their reduction order, so both should be exactly 0). */

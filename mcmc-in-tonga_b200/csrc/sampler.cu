@@ -18,6 +18,7 @@
 //   F  commit (accept) or roll back (reject) the pending owner changes;  G  traces / thinning / history.
 // The same canonical t* / phi reductions are used by evaluate.cu, so incremental state == full evaluate bit for bit
 // (tonga_chains_verify checks that on the device).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -100,6 +101,53 @@ __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, 
             atomicMax((unsigned long long *)&maxd[0], (unsigned long long)__double_as_longlong(dp));
         }
     }
+}
+
+// ---- posterior rasterisation (plot_model_hist, MCsub.jl:753-825): CTA = (tile of 256 nodes, chain); the chain's kept models
+// are visited in order, each staged in shared memory; one thread per node runs v_nearest (exact FP64) and keeps sum, sum^2.
+__global__ void __launch_bounds__(256)
+tg_raster_kernel(int n_nodes, const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z, int KC, int hist_cap,
+                 const int32_t *__restrict__ n_hist, const int32_t *__restrict__ hist_K, const double *__restrict__ hist_cells,
+                 double *__restrict__ part /* [nChains][2][n_nodes] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_c = reinterpret_cast<double *>(smem_raw);  // [4][KC]
+    const int chain = blockIdx.y;
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = node < n_nodes;
+    const double x = on ? X[node] : 0.0, y = on ? Y[node] : 0.0, z = on ? Z[node] : 0.0;
+    double s1 = 0.0, s2 = 0.0;
+    const int nh = min(n_hist[chain], hist_cap);
+    for (int j = 0; j < nh; j++) {
+        const size_t h = (size_t)chain * hist_cap + j;
+        const double *c = hist_cells + h * 4 * KC;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * KC; i += blockDim.x) s_c[i] = c[i];
+        __syncthreads();
+        const int K = hist_K[h];
+        double best = 1e9, v = 0.0;
+        for (int i = 0; i < K; i++) {
+            const double d = dist2_exact(s_c[i], s_c[KC + i], s_c[2 * KC + i], x, y, z);
+            if (d < best) { best = d; v = s_c[3 * KC + i]; }
+        }
+        s1 = __dadd_rn(s1, v);
+        s2 = __dadd_rn(s2, __dmul_rn(v, v));
+    }
+    if (on) {
+        part[((size_t)chain * 2 + 0) * n_nodes + node] = s1;
+        part[((size_t)chain * 2 + 1) * n_nodes + node] = s2;
+    }
+}
+
+__global__ void tg_raster_reduce_kernel(int n_nodes, int nChains, const double *__restrict__ part, double *__restrict__ sum, double *__restrict__ sumsq) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n_nodes) return;
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < nChains; c++) {  // fixed chain order -> deterministic
+        a = __dadd_rn(a, part[((size_t)c * 2 + 0) * n_nodes + node]);
+        b = __dadd_rn(b, part[((size_t)c * 2 + 1) * n_nodes + node]);
+    }
+    sum[node] = a;
+    sumsq[node] = b;
 }
 
 // evaluate's t* (caller's ray order) -> chain state rows (sorted ray order, padded to Rp)
@@ -477,6 +525,45 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     if (owner_mismatch) *owner_mismatch = (int64_t)mm;
     if (max_dphi) *max_dphi = md[0];
     if (max_dts) *max_dts = md[1];
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const double *X, const double *Y, const double *Z, double *sum_out,
+                                   double *sumsq_out, int64_t *count_out) {
+    if (!ch || n_nodes < 0 || (n_nodes > 0 && (!X || !Y || !Z || !sum_out || !sumsq_out)))
+        return tg::fail(TONGA_ERR_ARG, "tonga_chains_raster: bad argument");
+    tonga_ctx *ctx = ch->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)ch->n, nn = (size_t)n_nodes;
+    std::vector<int32_t> nh(n);
+    TG_CUDA(cudaStreamSynchronize(s));
+    TG_CUDA(cudaMemcpy(nh.data(), ch->d_n_hist, 4 * n, cudaMemcpyDeviceToHost));
+    long long cnt = 0;
+    for (size_t i = 0; i < n; i++) cnt += std::min<long long>(nh[i], ch->hist_cap);
+    if (count_out) *count_out = cnt;
+    if (n_nodes == 0) return TONGA_OK;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_X = 0, o_Y = o_X + al(8 * nn), o_Z = o_Y + al(8 * nn), o_part = o_Z + al(8 * nn), o_sum = o_part + al(8 * n * 2 * nn),
+                 o_sq = o_sum + al(8 * nn), total = o_sq + al(8 * nn);
+    int rc = tg::ensure_scratch(ctx, total);
+    if (rc != TONGA_OK) return rc;
+    char *d = (char *)ctx->d_scratch;
+    TG_CUDA(cudaMemcpyAsync(d + o_X, X, 8 * nn, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(d + o_Y, Y, 8 * nn, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(d + o_Z, Z, 8 * nn, cudaMemcpyHostToDevice, s));
+    dim3 grid((unsigned)((nn + 255) / 256), (unsigned)ch->n);
+    tg::tg_raster_kernel<<<grid, 256, 8 * 4 * (size_t)ch->KC, s>>>(n_nodes, (const double *)(d + o_X), (const double *)(d + o_Y),
+                                                                  (const double *)(d + o_Z), ch->KC, ch->hist_cap, ch->d_n_hist, ch->d_hist_K,
+                                                                  ch->d_hist_cells, (double *)(d + o_part));
+    TG_CUDA(cudaGetLastError());
+    tg::tg_raster_reduce_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(n_nodes, ch->n, (const double *)(d + o_part), (double *)(d + o_sum),
+                                                                          (double *)(d + o_sq));
+    TG_CUDA(cudaGetLastError());
+    TG_CUDA(cudaMemcpyAsync(sum_out, d + o_sum, 8 * nn, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaMemcpyAsync(sumsq_out, d + o_sq, 8 * nn, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaStreamSynchronize(s));
     return TONGA_OK;
 }
 

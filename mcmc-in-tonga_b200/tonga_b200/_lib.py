@@ -66,6 +66,7 @@ SYMBOLS = {
     "tonga_chains_reset": (C.c_int, [_P]),
     "tonga_chains_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "tonga_chains_get_history": (C.c_int, [_P, C.c_int32, c_ip, c_ip, c_dp, c_dp, c_dp, c_lp, c_ip, c_ip, c_ip]),
+    "tonga_chains_raster": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_lp]),
     "tonga_chains_verify": (C.c_int, [_P, c_lp, c_dp, c_dp]),
     "tonga_chains_kcap": (C.c_int, [_P]),
     "tonga_chains_device_ptrs": (C.c_int, [_P] + [c_vpp] * 8),

@@ -254,6 +254,15 @@ class Chains:
                                                 ip(out["next_action"])))
         return out
 
+    def raster(self, X, Y, Z):
+        """plot_model_hist's accumulation (MCsub.jl:753-825) at arbitrary nodes -> (sum, sumsq, count) over all kept models."""
+        X, Y, Z = (np.ascontiguousarray(a, dtype=np.float64).ravel() for a in (X, Y, Z))
+        assert len(X) == len(Y) == len(Z)
+        s1, s2 = np.zeros(len(X)), np.zeros(len(X))
+        cnt = C.c_int64()
+        check(self.lib.tonga_chains_raster(self._h, len(X), dp(X), dp(Y), dp(Z), dp(s1), dp(s2), C.byref(cnt)))
+        return s1, s2, cnt.value
+
     def verify(self):
         """Full re-evaluate of every chain on the device vs the incrementally maintained state."""
         mm, dphi, dts = C.c_int64(), C.c_double(), C.c_double()
@@ -369,3 +378,43 @@ def run_chains(TD_parameters: parameters, dataStruct: DataStruct, chains, seed: 
 def TD_inversion_function(TD_parameters: parameters, dataStruct1: DataStruct, chain: int, seed: int = 20260000):  # noqa: N802
     """TD_inversion_function.jl:7-305 for one chain -> model_hist (list of Model).  Prefer run_chains() for many."""
     return run_chains(TD_parameters, dataStruct1, [chain], seed=seed)[0]
+
+
+def slice_nodes(dataStruct: DataStruct, TD_parameters: parameters):
+    """The node sets plot_model_hist rasterises (MCsub.jl:756,766-768,791,800-802): for every l0 in ySlice the grid
+    xVec x zVec at y = l0 ("xz"), for every l0 in zSlice the grid xVec x yVec at z = l0 ("xy").
+    -> list of (kind, l0, shape, X, Y, Z) with X/Y/Z flattened in Julia's comprehension order (first index fastest)."""
+    xv, yv, zv = dataStruct.xVec.vec(), dataStruct.yVec.vec(), dataStruct.zVec.vec()
+    out = []
+    if TD_parameters.xzMap:
+        for l0 in TD_parameters.ySlice:
+            Xg, Zg = np.meshgrid(xv, zv, indexing="ij")
+            out.append(("xz", float(l0), Xg.shape, Xg.ravel(order="F"), np.full(Xg.size, float(l0)), Zg.ravel(order="F")))
+    if TD_parameters.xyMap:
+        for l0 in TD_parameters.zSlice:
+            Xg, Yg = np.meshgrid(xv, yv, indexing="ij")
+            out.append(("xy", float(l0), Xg.shape, Xg.ravel(order="F"), Yg.ravel(order="F"), np.full(Xg.size, float(l0))))
+    return out
+
+
+def finish_maps(s1, s2, count, shape):
+    """mean / std / masked mean exactly as MCsub.jl:774-782 (Julia `std` is the n-1 sample standard deviation)."""
+    mean = s1 / count
+    var = np.maximum(s2 - s1 * s1 / count, 0.0) / max(count - 1, 1)
+    std = np.sqrt(var)
+    mask = np.where(std > 5, np.nan, 1.0)  # :777-781
+    f = lambda a: a.reshape(shape, order="F")
+    return dict(mean=f(mean), std=f(std), masked=f(mask * mean), count=count)
+
+
+def plot_model_hist(chains: "Chains", dataStruct: DataStruct, TD_parameters: parameters, reduce=None):
+    """The numerical content of plot_model_hist(model_hist, dataStruct, TD_parameters, cmax) (MCsub.jl:753-825) from the
+    device-resident history of `chains`: {("xz", 700.0): {mean, std, masked}, ...}.  `reduce(s1, s2, count)` may add the
+    sums across ranks (tonga_b200.dist.allreduce_sums) before the statistics are formed; plotting itself is out of scope."""
+    out = {}
+    for kind, l0, shape, X, Y, Z in slice_nodes(dataStruct, TD_parameters):
+        s1, s2, cnt = chains.raster(X, Y, Z)
+        if reduce is not None:
+            s1, s2, cnt = reduce(s1, s2, cnt)
+        out[(kind, l0)] = finish_maps(s1, s2, cnt, shape)
+    return out

@@ -84,3 +84,17 @@ def run_sharded(TD_parameters, dataStruct, n_chains_total: int, seed: int = 2026
 
 def ensemble_to_numpy(ens: dict) -> dict:
     return {k: v.detach().cpu().numpy() for k, v in ens.items()}
+
+
+def allreduce_sums(s1, s2, count, device=None, group=None):
+    """Sum the posterior accumulators of tonga_chains_raster across ranks (plain sums -> one all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return s1, s2, count
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    t = torch.from_numpy(np.concatenate([s1, s2, [float(count)]])).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t = t.cpu().numpy()
+    n = len(s1)
+    return t[:n], t[n:2 * n], int(round(t[-1]))

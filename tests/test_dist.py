@@ -46,6 +46,9 @@ def _worker(rank, world, port, n_total, q):
         local = _fake_history(list(range(start, start + count)))
         counts = [shard(n_total, world, r)[1] for r in range(world)]
         ens = gather_ensembles(local, counts)
+        from tonga_b200.dist import allreduce_sums
+        s1, s2, cnt = allreduce_sums(np.arange(5.0) + rank, np.ones(5) * (rank + 1), 10 + rank)
+        assert np.array_equal(s1, 2 * np.arange(5.0) + 1) and np.array_equal(s2, np.full(5, 3.0)) and cnt == 21
         q.put((rank, {k: v.numpy() for k, v in ens.items()}))
     finally:
         dist.destroy_process_group()

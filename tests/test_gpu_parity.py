@@ -416,3 +416,75 @@ def test_fp32_screening_changes_nothing(tonga):
         for k in ("K", "cells", "phi", "ptS", "owners"):
             assert np.array_equal(s0[k], s1[k]), k
         ctx.close()
+
+
+def test_posterior_raster_matches_oracle(tonga):
+    """plot_model_hist's numerics (MCsub.jl:753-825): mean / std / mask of v_nearest over the kept models on the reference's
+    own slices (xVec x zVec at y in ySlice, xVec x yVec at z in zSlice) against the oracle's Interpolation per model."""
+    import copy
+    import oracle as O
+    from tonga_b200 import api
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 200.0, 100.0, 10.0
+    p.ySlice = [100, 300]  # inside this data set's frame (the reference's 700/800 belong to another frame, SURVEY 5.9)
+    ctx = api.Context(ds, p)
+    ch = api.Chains(ctx, 6, seed=3)
+    ch.build_starting(); ch.run(200)
+    hist = ch.history()
+    maps = api.plot_model_hist(ch, ds, p)
+    assert set(maps) == {("xz", 100.0), ("xz", 300.0), ("xy", 50.0), ("xy", 300.0), ("xy", 500.0)}
+    for kind, l0, shape, X, Y, Z in api.slice_nodes(ds, p):
+        vals = []
+        for c in range(6):
+            for j in range(hist["n_hist"][c]):
+                k = hist["K"][c, j]
+                v, _ = O.interpolation(*[hist["cells"][c, j, a, :k] for a in range(4)], X, Y, Z)
+                vals.append(v)
+        vals = np.array(vals)
+        m = maps[(kind, l0)]
+        assert m["count"] == len(vals) == 60 and m["mean"].shape == shape == ((58, 34))
+        ref_mean, ref_std = vals.mean(0).reshape(shape, order="F"), vals.std(0, ddof=1).reshape(shape, order="F")
+        assert np.allclose(m["mean"], ref_mean, rtol=1e-12, atol=1e-12) and np.allclose(m["std"], ref_std, rtol=1e-9, atol=1e-9)
+        sure = np.abs(ref_std - 5) > 1e-6
+        assert np.array_equal(np.isnan(m["masked"])[sure], (ref_std > 5)[sure])
+    ch.close(); ctx.close()
+
+
+def test_posterior_agrees_with_oracle_within_monte_carlo_error():
+    """north_star: 'posterior mean/sigma of 1000/Q agree within Monte-Carlo error'.  Device chains (Philox) and oracle chains
+    (its own RNG) sample the same posterior on a small problem; means of nCells, phi and of zeta at fixed nodes must agree
+    within 5 standard errors (between-chain scatter)."""
+    import copy
+    import oracle as O
+    from tonga_b200 import api
+    ds, p0 = random_ragged(11, R=31, m=15)
+    p = copy.copy(p0)
+    p.min_cells, p.max_cells = 2, 8
+    p.n_iter, p.burn_in, p.keep_each = 6000.0, 2000.0, 10.0
+    n = 48
+    ctx = api.Context(ds, p)
+    ch = api.Chains(ctx, n, seed=77)
+    ch.build_starting(); ch.run(6000)
+    hist = ch.history()
+    rng = np.random.default_rng(0)
+    bx = box_of(ds)
+    X, Y, Z = rng.uniform(bx[0], bx[1], 40), rng.uniform(bx[2], bx[3], 40), rng.uniform(bx[4], bx[5], 40)
+    def chain_stats(K, phi, cells):  # per-chain means over kept models
+        z = np.mean([O.interpolation(*[cells[j, a, :K[j]] for a in range(4)], X, Y, Z)[0] for j in range(len(K))], axis=0)
+        return np.concatenate([[K.mean(), phi.mean()], z])
+    dev = np.array([chain_stats(hist["K"][c, :hist["n_hist"][c]], hist["phi"][c, :hist["n_hist"][c]], hist["cells"][c]) for c in range(n)])
+    op = O.make_params(bx, n_iter=6000, burn_in=2000, keep_each=10, min_cells=2, max_cells=8)
+    od = O.Data(ds.rayX, ds.rayY, ds.rayZ, ds.rayL, ds.rayU, ds.tS, ds.allSig)
+    orc = []
+    for c in range(n):
+        g = O.rng(500 + c)
+        mb = O.build_starting(op, od, g)
+        r = O.chain_run(op, od, mb, 6000, g=g, hist_cap=400)
+        orc.append(chain_stats(r.hist_K[:r.n_hist], r.hist_phi[:r.n_hist], r.hist_cells))
+    orc = np.array(orc)
+    assert hist["n_hist"].min() == 400
+    se = np.sqrt(dev.var(0, ddof=1) / n + orc.var(0, ddof=1) / n)
+    zscore = np.abs(dev.mean(0) - orc.mean(0)) / np.maximum(se, 1e-12)
+    assert zscore.max() < 5.0, (zscore.max(), dev.mean(0)[:2], orc.mean(0)[:2])
+    ch.close(); ctx.close()
