@@ -121,7 +121,8 @@ int tonga_chains_set_models(tonga_chains *ch, int32_t Kcap, const int32_t *K, co
  * exact FP64 recheck of all comparisons that fall inside a rigorous rounding-error band (cell indices stay bit-exact);
  * 1: every comparison in exact FP64 (same results, slower; used by the tests to prove the screening changes nothing). */
 int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only);
-/* per-chain inverse temperature (parallel tempering extension; 1.0 = reference); NULL resets to 1 */
+/* per-chain inverse temperature beta (parallel-tempering extension; 1.0 = reference; NULL resets to 1): the misfit term
+ * of every acceptance ratio is scaled by beta, and only chains at beta == 1 append to the history. */
 int tonga_chains_set_beta(tonga_chains *ch, const double *beta);
 
 /* The proposal loop, TD_inversion_function.jl:70-302, nIter iterations for every chain, entirely on the device

@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 } else if (act == 4) {
                     acc = (u < jl_min1(exp(-dphi2)));  // :241-242
                 } else {  // sigma: log form :264-267
-                    double la = log(noise / zn) * (double)R - dphi2;
+                    double la = beta * (log(noise / zn) * (double)R) - dphi2;  // beta = 1: TD_inversion_function.jl:264
                     la = (la != la) ? la : (la < 0.0 ? la : 0.0);
                     acc = (log(u) <= la);
                 }
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             if (a.tr_K) a.tr_K[(size_t)chain * a.nIter + it] = K;
         }
         __syncthreads();  // state (nuclei, tstar, owners) consistent before the next proposal / the history copy
-        if (keep) {
+        if (keep && beta == 1.0) {  // tempered replicas (beta < 1, extension) do not contribute to the posterior
             if (n_hist < a.hist_cap) {
                 const size_t h = (size_t)chain * a.hist_cap + n_hist;
                 double *hc = a.hist_cells + h * 4 * KC;
