@@ -9,6 +9,8 @@
 //   C  t* of the touched rays, one thread per (length-sorted) ray, left-to-right;
 //   D  canonical phi;  E  alpha + accept (thread 0);  F  commit / roll back;  G  traces, thinning, history.
 #pragma once
+#include <type_traits>
+
 #include "tonga_internal.cuh"
 
 namespace tg {
@@ -74,7 +76,7 @@ __host__ __device__ inline SmemLayout smem_layout(int Ppad, int Rp, int KC) {
     L.o_tnew = take(8 * (size_t)Rp);
     L.o_dirty = take(4 * (size_t)((Rp + 31) / 32));
     L.o_nuc = take(8 * 4 * (size_t)KC);
-    L.o_nucf = take(4 * 3 * (size_t)KC);
+    L.o_nucf = take(4 * 3 * 128);  // fl32 nuclei, SoA with a fixed stride of 128; unused slots (and 0x7F = none) hold +inf
     L.o_zlut = take(8 * 128);
     L.o_scr = take(8 * 4);
     L.o_prop = take(sizeof(Prop));
@@ -132,21 +134,27 @@ __device__ __noinline__ void normal_pair(double u1, double u2, double &n0, doubl
     n1 = rr * sn;
 }
 
-// FP32 screening of the orphan rescan: best and second-best squared distance; returns the winner, or -1 if the two
-// are closer than the error band (or the winner is within the band of the 1e9 "no nucleus" threshold) -> exact rescan.
+// FP32 screening of the orphan rescan: best and second-best squared distance over the fl32 nuclei (4 per step; unused
+// slots and a killed nucleus hold +inf); returns the winner, or -1 if best and second best are closer than the error band
+// (this also covers a winner within the band of the 1e9 "no nucleus" threshold, d2 starts at 1e9) -> exact FP64 rescan.
 __device__ __noinline__ int rescan_point_f32(const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf,
-                                             const float *fx, const float *fy, const float *fz, int K, int skip, int p,
-                                             float tol_alpha, float tol_beta2) {
+                                             const float *sf, int K, int p, float tol_alpha, float tol_beta2) {
     const float x = pxf[p], y = pyf[p], z = pzf[p];
     float d1 = 1e9f, d2 = 1e9f;
     int i1 = TG_OWNER_NONE;
-#pragma unroll 4
-    for (int i = 0; i < K; i++) {
-        const float d = (i == skip) ? 3e38f : dist2_f32(fx[i], fy[i], fz[i], x, y, z);
-        const bool lt = d < d1;
-        d2 = lt ? d1 : fminf(d2, d);
-        i1 = lt ? i : i1;
-        d1 = lt ? d : d1;
+#pragma unroll 1
+    for (int i = 0; i < K; i += 4) {
+        const float4 fx = *reinterpret_cast<const float4 *>(sf + i), fy = *reinterpret_cast<const float4 *>(sf + 128 + i),
+                     fz = *reinterpret_cast<const float4 *>(sf + 256 + i);
+        const float d[4] = {dist2_f32(fx.x, fy.x, fz.x, x, y, z), dist2_f32(fx.y, fy.y, fz.y, x, y, z), dist2_f32(fx.z, fy.z, fz.z, x, y, z),
+                            dist2_f32(fx.w, fy.w, fz.w, x, y, z)};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool lt = d[u] < d1;
+            d2 = lt ? d1 : fminf(d2, d[u]);
+            i1 = lt ? i + u : i1;
+            d1 = lt ? d[u] : d1;
+        }
     }
     const float tol = fmaf(tol_alpha, d1 + d2, tol_beta2);
     if (!(d2 - d1 > tol)) return -1;  // ambiguous (or NaN coordinates)
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     double *s_nx = reinterpret_cast<double *>(smem + L.o_nuc);
     double *s_ny = s_nx + a.KC, *s_nz = s_ny + a.KC, *s_zeta = s_nz + a.KC;
     float *s_fx = reinterpret_cast<float *>(smem + L.o_nucf);
-    float *s_fy = s_fx + a.KC, *s_fz = s_fy + a.KC;
+    float *s_fy = s_fx + 128, *s_fz = s_fx + 256;
     double *s_zlut = reinterpret_cast<double *>(smem + L.o_zlut);
     double *s_scr = reinterpret_cast<double *>(smem + L.o_scr);
     Prop *s_prop = reinterpret_cast<Prop *>(smem + L.o_prop);
@@ -213,7 +221,13 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             s2u(s_bar))
         : "memory");
     __syncthreads();
-    for (int i = tid; i < 3 * KC; i += ST) s_fx[i] = (float)s_nx[i];  // fl32 copies of the nuclei (x, y, z)
+    {   // fl32 copies of the nuclei; slots >= K hold +inf so that they never win a comparison
+        const int K0 = a.K[chain];
+        for (int i = tid; i < 3 * 128; i += ST) {
+            const int ax = i >> 7, k = i & 127;
+            s_fx[i] = (k < K0) ? (float)s_nx[ax * KC + k] : __int_as_float(0x7f800000);
+        }
+    }
     __syncthreads();
 
     int K = a.K[chain];
@@ -291,6 +305,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                         const int zi = warp_nearest(s_nx, s_ny, s_nz, K, kill, s_nx[kill], s_ny[kill], s_nz[kill], lane);  // :146
                         pr.aux = zi < 0 ? 0.0 : s_zeta[zi];
                         valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
+                        if (valid && lane == 0) s_fx[kill] = __int_as_float(0x7f800000);  // fl32 screening must not see the killed nucleus
                     }
                 }
             } else if (act == 3) {  // ---- change :183-218
@@ -377,23 +392,35 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 const double cx = s_prop->x, cy = s_prop->y, cz = s_prop->z;
                 const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
                 // ======================================================== B1: flat pass over this warp's 128-point blocks
+                const float ta = a.tol_alpha, tb = a.tol_beta2;
+                unsigned long long blkmask = 0ull;  // warp-iterations whose block holds orphans (bit it; it >= 64 -> always scanned)
+                // birth / move: FP32 screening of d(p,new) against d(p,owner); ACT is a compile-time constant so that the birth
+                // path carries no move logic.  Branch-free per point; near ties (inside the error band) go to the exact FP64 compare.
+                auto b1_switch = [&](auto actc) {
+                    constexpr int ACT = decltype(actc)::value;
+                    const int mv = (ACT == 4) ? pidx : -1;
+                    const float2 ncx = make_float2(-cxf, -cxf), ncy = make_float2(-cyf, -cyf), ncz = make_float2(-czf, -czf);
+                    int it = 0;
+                    // software pipeline: the next block's coordinates are in flight while the current block is screened
+                    float4 nxf = *reinterpret_cast<const float4 *>(a.pxf + 4 * (warp * 32 + lane));
+                    float4 nyf = *reinterpret_cast<const float4 *>(a.pyf + 4 * (warp * 32 + lane));
+                    float4 nzf = *reinterpret_cast<const float4 *>(a.pzf + 4 * (warp * 32 + lane));
+                    int4 nrid = *reinterpret_cast<const int4 *>(a.rayid + 4 * (warp * 32 + lane));
 #pragma unroll 1
-                for (int blk = warp; blk < nBlocks; blk += ST / 32) {
-                    const int w = blk * 32 + lane;
-                    uint32_t ow = s_own32[w];
-                    uint32_t mbits = 0;
-                    if (act == 1 || act == 4) {
-                        const int4 rid = *reinterpret_cast<const int4 *>(a.rayid + 4 * w);  // loaded with the coordinates: no dependent load later
-                        const int RID[4] = {rid.x, rid.y, rid.z, rid.w};
-                        const int mv = (act == 4) ? pidx : -1;
-                        uint32_t tags = 0, amb = 0;
+                    for (int blk = warp; blk < nBlocks; blk += ST / 32, it++) {
+                        const int w = blk * 32 + lane;
+                        const uint32_t ow = s_own32[w];
+                        uint32_t tags = 0, amb = 0, mbits = 0;
+                        const float4 xf = nxf, yf = nyf, zf = nzf;
+                        const int4 rid = nrid;
+                        if (blk + ST / 32 < nBlocks) {
+                            const int wn = w + (ST / 32) * 32;
+                            nxf = *reinterpret_cast<const float4 *>(a.pxf + 4 * wn);
+                            nyf = *reinterpret_cast<const float4 *>(a.pyf + 4 * wn);
+                            nzf = *reinterpret_cast<const float4 *>(a.pzf + 4 * wn);
+                            nrid = *reinterpret_cast<const int4 *>(a.rayid + 4 * wn);
+                        }
                         if (!a.exact_only) {
-                            // FP32 screening (packed FADD2/FMUL2/FFMA2 for the candidate distance); points whose two distances are
-                            // closer than the rigorous error band go to the exact FP64 comparison below.
-                            const float4 xf = *reinterpret_cast<const float4 *>(a.pxf + 4 * w);
-                            const float4 yf = *reinterpret_cast<const float4 *>(a.pyf + 4 * w);
-                            const float4 zf = *reinterpret_cast<const float4 *>(a.pzf + 4 * w);
-                            const float2 ncx = make_float2(-cxf, -cxf), ncy = make_float2(-cyf, -cyf), ncz = make_float2(-czf, -czf);
                             float2 ex = __fadd2_rn(make_float2(xf.x, xf.y), ncx), ey = __fadd2_rn(make_float2(yf.x, yf.y), ncy), ez = __fadd2_rn(make_float2(zf.x, zf.y), ncz);
                             const float2 dc01 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
                             ex = __fadd2_rn(make_float2(xf.z, xf.w), ncx); ey = __fadd2_rn(make_float2(yf.z, yf.w), ncy); ez = __fadd2_rn(make_float2(zf.z, zf.w), ncz);
@@ -402,16 +429,19 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                             const float DC[4] = {dc01.x, dc01.y, dc23.x, dc23.y};
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
-                                const int o = (ow >> (8 * q)) & 0xFF;
-                                if (o == mv) {
-                                    mbits |= 1u << q;  // move, type A: owned by the moved nucleus -> rescan in B2
-                                } else {
-                                    const float d_o = (o == TG_OWNER_NONE) ? 1e9f : dist2_f32(s_fx[o], s_fy[o], s_fz[o], X[q], Y[q], Z[q]);
-                                    const float diff = DC[q] - d_o;
-                                    const float tol = fmaf(a.tol_alpha, DC[q] + d_o, a.tol_beta2);
-                                    if (diff < -tol) tags |= 0x80u << (8 * q);
-                                    else if (!(diff > tol) && DC[q] == DC[q]) amb |= 1u << q;  // inside the band (NaN coordinates never switch)
+                                const int o = (ow >> (8 * q)) & 0xFF;  // no tags are pending here; 0x7F (none) reads +inf
+                                const float d_o = dist2_f32(s_fx[o], s_fx[128 + o], s_fx[256 + o], X[q], Y[q], Z[q]);
+                                const float diff = DC[q] - d_o;
+                                const float tol = fmaf(ta, DC[q] + d_o, tb);
+                                bool sw = diff < -tol, am = fabsf(diff) <= tol;
+                                if (ACT == 4) {
+                                    const bool mine = (o == mv);  // move, type A: owned by the moved nucleus -> rescan in B2
+                                    mbits |= mine ? (1u << q) : 0u;
+                                    sw = sw && !mine;
+                                    am = am && !mine;
                                 }
+                                tags |= sw ? (0x80u << (8 * q)) : 0u;
+                                amb |= am ? (1u << q) : 0u;
                             }
                         } else {
 #pragma unroll
@@ -430,35 +460,53 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                                 const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], x, y, z);
                                 const double d_c = dist2_exact(cx, cy, cz, x, y, z);
                                 // birth: the new nucleus has the highest index -> strict <.  move: index mv also wins exact ties against o > mv.
-                                const bool sw = (d_c < d_o) || (act == 4 && d_c == d_o && mv < o && o != TG_OWNER_NONE);
+                                const bool sw = (d_c < d_o) || (ACT == 4 && d_c == d_o && mv < o && o != TG_OWNER_NONE);
                                 if (sw) tags |= 0x80u << (8 * q);
                             }
                         }
                         if (tags) {
                             s_own32[w] = ow | tags;
+                            const int RID[4] = {rid.x, rid.y, rid.z, rid.w};
 #pragma unroll
                             for (int q = 0; q < 4; q++)
-                                if (((tags >> (8 * q + 7)) & 1u) && (q == 0 || RID[q] != RID[q - 1] || !((tags >> (8 * q - 1)) & 1u)))
-                                    atomicOr(&s_dirty[RID[q] >> 5], 1u << (RID[q] & 31));
+                                if ((tags >> (8 * q + 7)) & 1u) atomicOr(&s_dirty[RID[q] >> 5], 1u << (RID[q] & 31));
                         }
-                    } else {
-                        const uint32_t eq = __vcmpeq4(ow, kk);  // bytes owned by the killed / changed nucleus
-                        if (eq) {
-                            if (act == 2) {
-                                mbits = (eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u);
-                            } else {  // act == 3: owners unchanged; rays through the changed cell are touched
-#pragma unroll
-                                for (int q = 0; q < 4; q++)
-                                    if ((eq >> (8 * q)) & 1u) mark_dirty(s_dirty, a.rayid, 4 * w + q);
-                            }
+                        if (ACT == 4 && __any_sync(0xffffffffu, mbits != 0u)) {  // assemble the block's 4 mask words (8 lanes x 4 bits each)
+                            uint32_t nib = mbits << ((lane & 7) * 4);
+                            nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+                            nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+                            nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+                            if ((lane & 7) == 0) s_mask[w >> 3] = nib;
+                            if (it < 64) blkmask |= 1ull << it;
                         }
                     }
-                    if (act == 2 || act == 4) {  // assemble the block's 4 mask words (8 lanes x 4 bits each)
-                        uint32_t nib = mbits << ((lane & 7) * 4);
-                        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
-                        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-                        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
-                        if ((lane & 7) == 0) s_mask[w >> 3] = nib;
+                };
+                if (act == 1) b1_switch(std::integral_constant<int, 1>{});
+                else if (act == 4) b1_switch(std::integral_constant<int, 4>{});
+                else {  // death: flag the orphans; change: mark the rays through the cell
+                    int it = 0;
+#pragma unroll 1
+                    for (int blk = warp; blk < nBlocks; blk += ST / 32, it++) {
+                        const int w = blk * 32 + lane;
+                        const uint32_t eq = __vcmpeq4(s_own32[w], kk);  // bytes owned by the killed / changed nucleus
+                        if (__any_sync(0xffffffffu, eq != 0u)) {
+                            if (act == 2) {
+                                const uint32_t mbits = (eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u);
+                                uint32_t nib = mbits << ((lane & 7) * 4);
+                                nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+                                nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+                                nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+                                if ((lane & 7) == 0) s_mask[w >> 3] = nib;
+                                if (it < 64) blkmask |= 1ull << it;
+                            } else if (eq) {
+                                const int4 rid = *reinterpret_cast<const int4 *>(a.rayid + 4 * w);
+                                const int RID[4] = {rid.x, rid.y, rid.z, rid.w};
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if (((eq >> (8 * q)) & 1u) && (q == 0 || RID[q] != RID[q - 1] || !((eq >> (8 * q - 8)) & 1u)))
+                                        atomicOr(&s_dirty[RID[q] >> 5], 1u << (RID[q] & 31));
+                            }
+                        }
                     }
                 }
                 // ======================================================== B2: rescan this warp's orphans, 32 at a time
@@ -469,16 +517,19 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     auto drain = [&](int cnt) {  // lanes < cnt take the top `cnt` queue entries
                         if (lane < cnt) {
                             const int p = (int)s_queue[qn - cnt + lane];
-                            int bi = a.exact_only ? -1 : rescan_point_f32(a.pxf, a.pyf, a.pzf, s_fx, s_fy, s_fz, K, skip, p, a.tol_alpha, a.tol_beta2);
+                            const int rid = a.rayid[p];  // in flight during the rescan
+                            int bi = a.exact_only ? -1 : rescan_point_f32(a.pxf, a.pyf, a.pzf, s_fx, K, p, ta, tb);
                             if (bi < 0) bi = rescan_point(a.px, a.py, a.pz, s_nx, s_ny, s_nz, K, skip, p);  // exact FP64
                             s_owner[p] = (uint8_t)bi;  // death: old numbering, renumbered on accept
-                            if (act == 2 || bi != pidx) mark_dirty(s_dirty, a.rayid, p);
+                            if (act == 2 || bi != pidx) atomicOr(&s_dirty[rid >> 5], 1u << (rid & 31));
                         }
                         qn -= cnt;
                         __syncwarp();
                     };
+                    int it = 0;
 #pragma unroll 1
-                    for (int blk = warp; blk < nBlocks; blk += ST / 32) {
+                    for (int blk = warp; blk < nBlocks; blk += ST / 32, it++) {
+                        if (it < 64 && !((blkmask >> it) & 1ull)) continue;
 #pragma unroll 1
                         for (int k4 = 0; k4 < 4; k4++) {
                             const int mw = blk * 4 + k4;
@@ -610,6 +661,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                             s_fx[i] = (float)vx[s]; s_fy[i] = (float)vy[s]; s_fz[i] = (float)vz[s];
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) { s_fx[K - 1] = s_fy[K - 1] = s_fz[K - 1] = __int_as_float(0x7f800000); }  // freed slot -> +inf
                 }
             }
             if (tid == 0) {
@@ -618,6 +671,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     s_fx[K] = (float)s_prop->x; s_fy[K] = (float)s_prop->y; s_fz[K] = (float)s_prop->z;
                 } else if (act == 3 && accepted) {
                     s_zeta[pidx] = s_prop->zeta;
+                } else if (act == 2 && !accepted) {
+                    s_fx[pidx] = (float)s_nx[pidx];  // un-hide the nucleus that was proposed for deletion
                 } else if (act == 4 && !accepted) {
                     s_nx[pidx] = s_prop->ox; s_ny[pidx] = s_prop->oy; s_nz[pidx] = s_prop->oz;
                     s_fx[pidx] = (float)s_prop->ox; s_fy[pidx] = (float)s_prop->oy; s_fz[pidx] = (float)s_prop->oz;
