@@ -547,16 +547,21 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 __syncthreads();
                 // ======================================================== C: t* of touched rays, one thread per sorted ray
                 const double ztag = s_prop->ztag;
+                {   // The touched rays are COMPACTED (they are ~20% of all rays): entry e of the compacted, still length-sorted list
+                    // goes to thread e, so every warp walks 32 rays of similar length with all lanes busy.  No list is stored:
+                    // thread e finds its ray as the e-th set bit of the dirty bitmap (popc prefix + __fns).
+                    const int nwords = (R + 31) >> 5;
+                    int nd = 0;
+                    for (int i = 0; i < nwords; i++) nd += __popc(s_dirty[i]);
 #pragma unroll 1
-                for (int slot = 0; slot * 128 < R; slot++) {  // sorted rays dealt round-robin to the 4 warps: rank = slot*128 + lane*4 + warp
-                    const int r = slot * 128 + lane * 4 + warp;
-                    const bool on = r < R && ((s_dirty[r >> 5] >> (r & 31)) & 1u);
-                    if (__any_sync(0xffffffffu, on)) {
-                        if (on) {
-                            const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-                            s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, a.ldT, r, q0, n,
-                                                               [&](uint8_t o) -> double { return (o & 0x80) ? ztag : s_zlut[o]; });
-                        }
+                    for (int e = tid; e < nd; e += ST) {
+                        int cum = 0, wi = 0;
+                        uint32_t bits = s_dirty[0];
+                        while (cum + __popc(bits) <= e) { cum += __popc(bits); bits = s_dirty[++wi]; }
+                        const int r = wi * 32 + (int)__fns(bits, 0, e - cum + 1);
+                        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
+                        s_tnew[r] = ray_tstar_seq<uint8_t>(s_owner, a.dtT, a.ldT, r, q0, n,
+                                                           [&](uint8_t o) -> double { return (o & 0x80) ? ztag : s_zlut[o]; });
                     }
                 }
                 __syncthreads();
