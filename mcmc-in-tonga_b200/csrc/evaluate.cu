@@ -50,7 +50,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
                const int32_t *__restrict__ point_orig, int R, int ldT, int64_t P, int64_t Ppad, int tile_pts,
-               double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8) {
+               double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int model = blockIdx.y;
     const Tile tile = tiles[blockIdx.x];
@@ -110,6 +110,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                 const int64_t p = tile.p0 + j;
                 if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi[q];  // caller's flat order
                 if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
+                if (dmin32) dmin32[(size_t)model * Ppad + p] = (float)best[q];  // owner distance cache of the sampler (1e9 = none)
             }
         }
     }
@@ -125,10 +126,13 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
 }
 
 // padded tail of the u8 chain-state owner arrays: NONE
-__global__ void tg_owner_pad_kernel(uint8_t *owners8, int64_t P, int64_t Ppad, int nModels) {
+__global__ void tg_owner_pad_kernel(uint8_t *owners8, float *dmin32, int64_t P, int64_t Ppad, int nModels) {
     const int64_t pad = Ppad - P;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < pad * nModels) owners8[(i / pad) * Ppad + P + (i % pad)] = (uint8_t)TG_OWNER_NONE;
+    if (i < pad * nModels) {
+        owners8[(i / pad) * Ppad + P + (i % pad)] = (uint8_t)TG_OWNER_NONE;
+        if (dmin32) dmin32[(i / pad) * Ppad + P + (i % pad)] = 1e9f;
+    }
 }
 
 __global__ void __launch_bounds__(TG_PHI_LANES)
@@ -148,7 +152,7 @@ tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, co
 }
 
 int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
-                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev) {
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev) {
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if (!ctx->prm.debug_prior && ctx->n_tiles > 0) {
@@ -159,12 +163,12 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
                                                                   ctx->d_pz, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
-                                                                  owners32_dev, owners8_dev);
+                                                                  owners32_dev, owners8_dev, dmin32_dev);
         TG_CUDA(cudaGetLastError());
     }
     if (owners8_dev && ctx->Ppad > ctx->P) {
         const int64_t n = (ctx->Ppad - ctx->P) * nModels;
-        tg_owner_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(owners8_dev, ctx->P, ctx->Ppad, nModels);
+        tg_owner_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(owners8_dev, dmin32_dev, ctx->P, ctx->Ppad, nModels);
         TG_CUDA(cudaGetLastError());
     }
     if (phi_dev) {
@@ -207,7 +211,7 @@ extern "C" int tonga_evaluate_batch_dev(tonga_ctx *ctx, int32_t nModels, int32_t
         return tg::fail(TONGA_ERR_ARG, "tonga_evaluate_batch_dev: bad argument (ptS_dev is required)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
-    return tg::launch_evaluate(ctx, nModels, Kcap, K_dev, cells_dev, noise_dev, ptS_dev, phi_dev, owners_dev, nullptr);
+    return tg::launch_evaluate(ctx, nModels, Kcap, K_dev, cells_dev, noise_dev, ptS_dev, phi_dev, owners_dev, nullptr, nullptr);
 }
 
 extern "C" int tonga_evaluate_batch(tonga_ctx *ctx, int32_t nModels, int32_t Kcap, const int32_t *K, const double *cells,
@@ -231,7 +235,7 @@ extern "C" int tonga_evaluate_batch(tonga_ctx *ctx, int32_t nModels, int32_t Kca
     if (noise) TG_CUDA(cudaMemcpyAsync(d + o_noise, noise, 8 * n, cudaMemcpyHostToDevice, s));
     rc = tg::launch_evaluate(ctx, nModels, Kcap, (const int32_t *)(d + o_K), (const double *)(d + o_cells),
                              noise ? (const double *)(d + o_noise) : nullptr, (double *)(d + o_pts), (double *)(d + o_phi),
-                             owners ? (int32_t *)(d + o_own) : nullptr, nullptr);
+                             owners ? (int32_t *)(d + o_own) : nullptr, nullptr, nullptr);
     if (rc != TONGA_OK) return rc;
     if (ptS && R && !ctx->prm.debug_prior) TG_CUDA(cudaMemcpyAsync(ptS, d + o_pts, 8 * n * R, cudaMemcpyDeviceToHost, s));
     if (phi) TG_CUDA(cudaMemcpyAsync(phi, d + o_phi, 8 * n, cudaMemcpyDeviceToHost, s));

@@ -81,11 +81,17 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
 __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
                                  const uint8_t *own_b, const double *ts_a /* [n][Rp] sorted rays */,
                                  const double *ts_b /* [n][R] caller's ray order */, const double *phi_a, const double *phi_b,
+                                 const float *dc_a, const float *dc_b, float tol_alpha, float tol_beta2,
                                  unsigned long long *mism, double *maxd /* [2] as ordered uint64 bits */) {
     const int chain = blockIdx.y;
     unsigned long long local = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+    {
         local += own_a[(size_t)chain * Ppad + p] != own_b[(size_t)chain * Ppad + p];
+        // the sampler's fl32 owner-distance cache must stay within a few ulp of the freshly computed distance
+        const float ca = dc_a[(size_t)chain * Ppad + p], cb = dc_b[(size_t)chain * Ppad + p];
+        local += !(fabsf(ca - cb) <= tol_alpha * (ca + cb) + tol_beta2);  // same rounding-error band as the screening
+    }
     if (local) atomicAdd(mism, local);
     if (blockIdx.x == 0) {
         double dm = 0.0;
@@ -175,6 +181,7 @@ struct tonga_chains {
     int32_t *d_K = nullptr;
     double *d_cells = nullptr, *d_phi = nullptr, *d_noise = nullptr, *d_beta = nullptr, *d_tstar = nullptr;
     uint8_t *d_owner = nullptr;
+    float *d_dcache = nullptr, *d_dcache_tmp = nullptr;  // [n][Ppad] fl32 squared distance of every point to its owner
     long long *d_counts = nullptr;
     int32_t *d_pending = nullptr;
     int32_t *d_n_hist = nullptr;
@@ -229,6 +236,8 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     TG_ALLOC(ch->d_beta, 8 * n);
     TG_ALLOC(ch->d_tstar, 8 * n * Rp);
     TG_ALLOC(ch->d_owner, n * Pp);
+    TG_ALLOC(ch->d_dcache, 4 * n * Pp);
+    TG_ALLOC(ch->d_dcache_tmp, 4 * n * Pp);
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
     TG_ALLOC(ch->d_n_hist, 4 * n);
@@ -270,7 +279,7 @@ extern "C" void tonga_chains_destroy(tonga_chains *ch) {
     if (!ch) return;
     cudaSetDevice(ch->ctx->device);
     cudaStreamSynchronize(ch->ctx->stream);
-    void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_counts, ch->d_pending,
+    void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
                     ch->d_maxd};
@@ -283,7 +292,7 @@ extern "C" void tonga_chains_destroy(tonga_chains *ch) {
 // full evaluate of the current device-resident models -> owners, t*, phi of the chain state
 static int establish_state(tonga_chains *ch) {
     tonga_ctx *ctx = ch->ctx;
-    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner);
+    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner, ch->d_dcache);
     if (rc != TONGA_OK) return rc;
     const size_t tot = (size_t)ch->n * ch->Rp;
     tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_ptS_tmp, ch->d_tstar);
@@ -372,7 +381,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
-    a.owner = ch->d_owner; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;
+    a.owner = ch->d_owner; a.dcache = ch->d_dcache; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;
     a.iter0 = ch->iter_done + 1; a.nIter = nIter; a.mode = mode;
     a.recs_in = (mode == 1) ? (const tonga_proposal *)(d + o_rec) : nullptr;
     a.recs_out = (mode == 0 && recs) ? (tonga_proposal *)(d + o_rec) : nullptr;
@@ -509,13 +518,13 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp);
+    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp, ch->d_dcache_tmp);
     if (rc != TONGA_OK) return rc;
     TG_CUDA(cudaMemsetAsync(ch->d_mism, 0, 8, s));
     TG_CUDA(cudaMemsetAsync(ch->d_maxd, 0, 16, s));
     dim3 grid(8, ch->n);
     tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
-                                              ch->d_phi, ch->d_phi_tmp, ch->d_mism, ch->d_maxd);
+                                              ch->d_phi, ch->d_phi_tmp, ch->d_dcache, ch->d_dcache_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
     unsigned long long mm = 0;
     double md[2] = {0, 0};

@@ -30,6 +30,7 @@ struct SamplerArgs {
     double *cells;  // [n][4][KC]
     double *phi, *noise, *beta;
     uint8_t *owner;  // [n][Ppad]
+    float *dcache;   // [n][Ppad] fl32 squared distance of every point to its current owner (1e9 = none); L2-resident
     double *tstar;   // [n][Rp]  (sorted ray order)
     long long *counts;  // [n][3][5] proposed / accepted / evaluated
     int32_t *pending_slot;  // [n] history slot awaiting its next_action, or -1
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     QT *s_queue = reinterpret_cast<QT *>(smem + L.o_queue) + warp * SQ_CAP;
     const int chain = blockIdx.x;
     const int KC = a.KC, R = a.R;
+    float *__restrict__ dcache = a.dcache + (size_t)chain * a.Ppad;
     const int nOwnWords = a.Ppad / 4, nMaskWords = a.Ppad / 32, nDirtyWords = (a.Rp + 31) / 32;
     const int nBlocks = a.Ppad / 128;
 
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     float4 nyf = *reinterpret_cast<const float4 *>(a.pyf + 4 * (warp * 32 + lane));
                     float4 nzf = *reinterpret_cast<const float4 *>(a.pzf + 4 * (warp * 32 + lane));
                     int4 nrid = *reinterpret_cast<const int4 *>(a.rayid + 4 * (warp * 32 + lane));
+                    float4 ndo = *reinterpret_cast<const float4 *>(dcache + 4 * (warp * 32 + lane));
 #pragma unroll 1
                     for (int blk = warp; blk < nBlocks; blk += ST / 32, it++) {
                         const int w = blk * 32 + lane;
@@ -413,24 +416,26 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                         uint32_t tags = 0, amb = 0, mbits = 0;
                         const float4 xf = nxf, yf = nyf, zf = nzf;
                         const int4 rid = nrid;
+                        const float4 dof = ndo;
                         if (blk + ST / 32 < nBlocks) {
                             const int wn = w + (ST / 32) * 32;
                             nxf = *reinterpret_cast<const float4 *>(a.pxf + 4 * wn);
                             nyf = *reinterpret_cast<const float4 *>(a.pyf + 4 * wn);
                             nzf = *reinterpret_cast<const float4 *>(a.pzf + 4 * wn);
                             nrid = *reinterpret_cast<const int4 *>(a.rayid + 4 * wn);
+                            ndo = *reinterpret_cast<const float4 *>(dcache + 4 * wn);
                         }
                         if (!a.exact_only) {
                             float2 ex = __fadd2_rn(make_float2(xf.x, xf.y), ncx), ey = __fadd2_rn(make_float2(yf.x, yf.y), ncy), ez = __fadd2_rn(make_float2(zf.x, zf.y), ncz);
                             const float2 dc01 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
                             ex = __fadd2_rn(make_float2(xf.z, xf.w), ncx); ey = __fadd2_rn(make_float2(yf.z, yf.w), ncy); ez = __fadd2_rn(make_float2(zf.z, zf.w), ncz);
                             const float2 dc23 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
-                            const float X[4] = {xf.x, xf.y, xf.z, xf.w}, Y[4] = {yf.x, yf.y, yf.z, yf.w}, Z[4] = {zf.x, zf.y, zf.z, zf.w};
                             const float DC[4] = {dc01.x, dc01.y, dc23.x, dc23.y};
+                            const float DO[4] = {dof.x, dof.y, dof.z, dof.w};  // cached distance to the current owner: no nucleus gather
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
-                                const int o = (ow >> (8 * q)) & 0xFF;  // no tags are pending here; 0x7F (none) reads +inf
-                                const float d_o = dist2_f32(s_fx[o], s_fx[128 + o], s_fx[256 + o], X[q], Y[q], Z[q]);
+                                const int o = (ow >> (8 * q)) & 0xFF;  // no tags are pending here
+                                const float d_o = DO[q];
                                 const float diff = DC[q] - d_o;
                                 const float tol = fmaf(ta, DC[q] + d_o, tb);
                                 bool sw = diff < -tol, am = fabsf(diff) <= tol;
@@ -622,15 +627,20 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     uint32_t b = s_mask[i];
                     if (b) {
                         s_mask[i] = 0u;
-                        if (!accepted)
-                            while (b) {
-                                const int j = __ffs(b) - 1;
-                                b &= b - 1;
-                                s_owner[32 * i + j] = (uint8_t)pidx;
+                        while (b) {
+                            const int j = __ffs(b) - 1;
+                            b &= b - 1;
+                            const int p = 32 * i + j;
+                            if (!accepted) {
+                                s_owner[p] = (uint8_t)pidx;
+                            } else {  // refresh the owner-distance cache (a move also changes it for points that stay with the nucleus)
+                                const int o = s_owner[p] & 0x7F;  // death: still the old numbering, as are the fl32 nuclei
+                                dcache[p] = (o == TG_OWNER_NONE) ? 1e9f : dist2_f32(s_fx[o], s_fy[o], s_fz[o], a.pxf[p], a.pyf[p], a.pzf[p]);
                             }
+                        }
                     }
                 }
-                if (act == 4) __syncthreads();  // byte stores above and word updates below may touch the same words
+                __syncthreads();  // move: byte stores above vs word updates below; death: the cache refresh above reads the nuclei the delete below shifts
             }
             if (act == 1 || act == 4) {  // tagged bytes: switch to the new / moved nucleus
                 const uint32_t newb = (uint32_t)(act == 1 ? K : pidx) * 0x01010101u;
@@ -640,6 +650,15 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     if (t) {
                         const uint32_t m = (t >> 7) * 0xFFu;
                         s_own32[w] = accepted ? ((ow & ~m) | (newb & m)) : (ow & 0x7F7F7F7Fu);
+                        if (accepted) {  // switched points: cache their distance to the new nucleus
+                            const float fx = (float)s_prop->x, fy = (float)s_prop->y, fz = (float)s_prop->z;
+#pragma unroll 1
+                            for (int q = 0; q < 4; q++)
+                                if ((t >> (8 * q + 7)) & 1u) {
+                                    const int p = 4 * w + q;
+                                    dcache[p] = dist2_f32(fx, fy, fz, a.pxf[p], a.pyf[p], a.pzf[p]);
+                                }
+                        }
                     }
                 }
             }
