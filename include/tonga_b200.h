@@ -169,6 +169,11 @@ int tonga_chains_kcap(const tonga_chains *ch);
 int tonga_chains_device_ptrs(tonga_chains *ch, void **n_hist, void **hist_K, void **hist_cells, void **hist_phi,
                              void **hist_ptS, void **state_K, void **state_cells, void **state_phi);
 
+/* Developer aid: per-phase clock64 totals of the sampler kernel (thread 0 of every chain): cycles[nChains][16] = proposal (A),
+ * point pass (B), t* (C), phi + accept (D+E), commit tail (F4), bookkeeping (G), F1 masks, F2 tags, F3 renumber, 7 unused.  enable != 0 (re)starts counting,
+ * enable == 0 stops it; cycles (may be NULL) receives the totals accumulated so far. */
+int tonga_chains_profile(tonga_chains *ch, int32_t enable, int64_t *cycles);
+
 /* Page-locked host buffers for callers that want full-speed host<->device copies (optional: every entry point also
  * accepts ordinary pageable memory). */
 int tonga_host_alloc(void **ptr, uint64_t bytes);

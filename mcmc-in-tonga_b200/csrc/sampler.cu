@@ -90,7 +90,7 @@ __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, 
         local += own_a[(size_t)chain * Ppad + p] != own_b[(size_t)chain * Ppad + p];
         // the sampler's fl32 owner-distance cache must stay within a few ulp of the freshly computed distance
         const float ca = dc_a[(size_t)chain * Ppad + p], cb = dc_b[(size_t)chain * Ppad + p];
-        local += !(fabsf(ca - cb) <= tol_alpha * (ca + cb) + tol_beta2);  // same rounding-error band as the screening
+        local += !(ca < 0.0f || fabsf(ca - cb) <= tol_alpha * (ca + cb) + tol_beta2);  // stale marker, or inside the screening's error band
     }
     if (local) atomicAdd(mism, local);
     if (blockIdx.x == 0) {
@@ -176,6 +176,7 @@ struct tonga_chains {
     long long iter_done = 0;
     bool have_models = false;
     int exact_only = 0;
+    long long *d_prof = nullptr;  // optional per-phase cycle counters (tonga_chains_profile)
     size_t smem = 0;
     // device state
     int32_t *d_K = nullptr;
@@ -261,14 +262,25 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     TG_CUDA(cudaMemsetAsync(ch->d_n_hist, 0, 4 * n, s));
     TG_CUDA(cudaMemsetAsync(ch->d_model_num, 0, 8 * n, s));
     TG_CUDA(cudaMemsetAsync(ch->d_cells, 0, 8 * n * 4 * KC, s));
+    // unused history slots read as zeros (get_history copies whole arrays)
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_K, 0, tg_nz(4 * n * H), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_cells, 0, tg_nz(8 * n * H * 4 * KC), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_phi, 0, tg_nz(8 * n * H), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_ptS, 0, tg_nz(8 * n * H * R), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_iter, 0, tg_nz(8 * n * H), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_action, 0, tg_nz(4 * n * H), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_accept, 0, tg_nz(4 * n * H), s));
+    TG_CUDA(cudaMemsetAsync(ch->d_hist_next, 0, tg_nz(4 * n * H), s));
     {
         std::vector<double> ones(n, 1.0);
         TG_CUDA(cudaMemcpyAsync(ch->d_beta, ones.data(), 8 * n, cudaMemcpyHostToDevice, s));
         TG_CUDA(cudaMemcpyAsync(ch->d_noise, ones.data(), 8 * n, cudaMemcpyHostToDevice, s));
         TG_CUDA(cudaStreamSynchronize(s));
     }
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     TG_CUDA(cudaEventCreate(&ch->ev0));
     TG_CUDA(cudaEventCreate(&ch->ev1));
     *out = ch;
@@ -284,6 +296,7 @@ extern "C" void tonga_chains_destroy(tonga_chains *ch) {
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
                     ch->d_maxd};
     for (void *p : ptrs) cudaFree(p);
+    if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
     delete ch;
@@ -345,6 +358,25 @@ extern "C" int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only)
     return TONGA_OK;
 }
 
+extern "C" int tonga_chains_profile(tonga_chains *ch, int32_t enable, int64_t *cycles /* [nChains][16] or NULL */) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_profile: NULL");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
+    const size_t bytes = 8 * (size_t)ch->n * 16;
+    if (cycles && ch->d_prof) TG_CUDA(cudaMemcpy(cycles, ch->d_prof, bytes, cudaMemcpyDeviceToHost));
+    if (enable && !ch->d_prof) {
+        TG_CUDA(cudaMalloc((void **)&ch->d_prof, bytes));
+        TG_CUDA(cudaMemset(ch->d_prof, 0, bytes));
+    } else if (enable) {
+        TG_CUDA(cudaMemset(ch->d_prof, 0, bytes));
+    } else if (ch->d_prof) {
+        cudaFree(ch->d_prof);
+        ch->d_prof = nullptr;
+    }
+    return TONGA_OK;
+}
+
 extern "C" int tonga_chains_set_beta(tonga_chains *ch, const double *beta) {
     if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_beta: NULL");
     std::lock_guard<std::mutex> lk(ch->ctx->mu);
@@ -377,8 +409,9 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
     a.pxf = ctx->d_pxf; a.pyf = ctx->d_pyf; a.pzf = ctx->d_pzf; a.tol_alpha = ctx->tol_alpha; a.tol_beta2 = ctx->tol_beta2;
     a.exact_only = ch->exact_only;
+    a.prof = ch->d_prof;
     a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig;
-    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
+    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad; a.n_sm = ctx->sm_count > 0 ? ctx->sm_count : 1;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
     a.owner = ch->d_owner; a.dcache = ch->d_dcache; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;
@@ -394,8 +427,13 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.hist_iter = ch->d_hist_iter; a.hist_action = ch->d_hist_action; a.hist_accept = ch->d_hist_accept; a.hist_next = ch->d_hist_next;
 
     TG_CUDA(cudaEventRecord(ch->ev0, s));
-    if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t><<<ch->n, tg::ST, ch->smem, s>>>(a);
-    else tg::tg_sampler_kernel<uint32_t><<<ch->n, tg::ST, ch->smem, s>>>(a);
+    if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
+        if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+        else tg::tg_sampler_kernel<uint32_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+    } else {
+        if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+        else tg::tg_sampler_kernel<uint32_t, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+    }
     TG_CUDA(cudaGetLastError());
     TG_CUDA(cudaEventRecord(ch->ev1, s));
     ch->iter_done += nIter;

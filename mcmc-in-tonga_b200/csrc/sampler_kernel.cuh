@@ -21,9 +21,11 @@ struct SamplerArgs {
     const float *pxf, *pyf, *pzf;   // fl32 copies (screening)
     float tol_alpha, tol_beta2;     // screening band
     int exact_only;                 // 1 = skip the FP32 screening (pure FP64 path; used by tests)
+    long long *prof;                // PROF instantiation only: [n][16] per-phase clock64 totals of thread 0
     const int32_t *rayid, *ray_off, *ray_orig;
     int R, Rp, KC, ldT;
     int P, Ppad;
+    int n_sm;  // SM count (leader-warp rotation)
     tonga_params prm;
     // chain state (global)
     int32_t *K;
@@ -176,7 +178,7 @@ __device__ __noinline__ int rescan_point(const double *__restrict__ px, const do
     return bi;
 }
 
-template <typename QT>
+template <typename QT, bool PROF>
 __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(a.Ppad, a.Rp, a.KC);
@@ -196,6 +198,11 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.o_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The serial phases (proposal, touched-ray integration, accept, bookkeeping) run on ONE warp per chain.  Warp w of every CTA
+    // lives on SM sub-partition w % 4, so the 7 chains of an SM would all queue their serial work on sub-partition 0:
+    // rotate the leader warp with the CTA's slot on its SM (CTAs b, b+nSM, b+2nSM, ... share an SM).
+    const int lead = 0;  // (rotating the leader with blockIdx.x / n_sm was measured: phase A shrinks, phase B grows by as much)
+    const int vtid = (tid - lead * 32) & (ST - 1), vwarp = vtid >> 5;  // virtual ids: the leader is virtual warp 0
     QT *s_queue = reinterpret_cast<QT *>(smem + L.o_queue) + warp * SQ_CAP;
     const int chain = blockIdx.x;
     const int KC = a.KC, R = a.R;
@@ -246,11 +253,16 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     const double PI = 3.141592653589793;
     const unsigned long long gid = (unsigned long long)(a.chain_id0 + chain);
 
+    long long pt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = PROF ? clock64() : 0;
+    auto tick = [&](int ph) {
+        if (PROF && tid == 0) { const long long t = clock64(); pt[ph] += t - tprev; tprev = t; }
+    };
 #pragma unroll 1
     for (long long it = 0; it < a.nIter; it++) {
         const long long iter = a.iter0 + it;
         // ================================================================ A: proposal (warp 0, warp-uniform values)
-        if (warp == 0) {
+        if (vwarp == 0) {
             Prop pr;
             pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
             pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
@@ -381,6 +393,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             }
         }
         __syncthreads();
+        tick(0);
         pending_slot = -1;
         const int act = s_prop->action;
         const int do_eval = s_prop->do_eval;
@@ -550,6 +563,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     if (qn > 0) drain(qn);
                 }
                 __syncthreads();
+                tick(1);
                 // ======================================================== C: t* of touched rays, one thread per sorted ray
                 const double ztag = s_prop->ztag;
                 {   // The touched rays are COMPACTED (they are ~20% of all rays): entry e of the compacted, still length-sorted list
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     int nd = 0;
                     for (int i = 0; i < nwords; i++) nd += __popc(s_dirty[i]);
 #pragma unroll 1
-                    for (int e = tid; e < nd; e += ST) {
+                    for (int e = vtid; e < nd; e += ST) {
                         int cum = 0, wi = 0;
                         uint32_t bits = s_dirty[0];
                         while (cum + __popc(bits) <= e) { cum += __popc(bits); bits = s_dirty[++wi]; }
@@ -570,6 +584,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     }
                 }
                 __syncthreads();
+                tick(2);
             }
             // ============================================================ D: phi of the proposed model (canonical order)
             const double nz = (act == 5) ? s_prop->zeta : noise;
@@ -577,8 +592,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 const double t = ((s_dirty[r >> 5] >> (r & 31)) & 1u) ? s_tnew[r] : s_tstar[r];
                 return misfit_term(t, a.tS[r], a.sig[r], nz);
             });
-            // ============================================================ E: acceptance (thread 0)
-            if (tid == 0) {
+            // ============================================================ E: acceptance (one thread of the leader warp)
+            if (vtid == 0) {
                 const double K0 = (double)K;
                 const double zn = s_prop->zeta, aux = s_prop->aux, u = s_prop->u;
                 const double dphi2 = beta * ((phin - phi) / 2);
@@ -619,6 +634,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 s_prop->accept = acc;
             }
             __syncthreads();
+            tick(3);
             accepted = s_prop->accept;
             // ============================================================ F: commit / roll back
             if (act == 2 || act == 4) {  // masked bytes: overwritten orphans (old owner = pidx)
@@ -642,6 +658,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 }
                 __syncthreads();  // move: byte stores above vs word updates below; death: the cache refresh above reads the nuclei the delete below shifts
             }
+            tick(6);
             if (act == 1 || act == 4) {  // tagged bytes: switch to the new / moved nucleus
                 const uint32_t newb = (uint32_t)(act == 1 ? K : pidx) * 0x01010101u;
 #pragma unroll 1
@@ -662,6 +679,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     }
                 }
             }
+            tick(7);
             if (act == 2 && accepted) {  // deleteat! renumbering: indices above `kill` shift down (:132-135)
 #pragma unroll 1
                 for (int w = tid; w < nOwnWords; w += ST) {
@@ -669,7 +687,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     const uint32_t gt = __vcmpgtu4(ow, kk) & ~__vcmpeq4(ow, 0x7F7F7F7Fu);
                     if (gt) s_own32[w] = ow - (gt & 0x01010101u);
                 }
-                if (warp == 0) {  // order-preserving delete of the nucleus
+                if (vwarp == 0) {  // order-preserving delete of the nucleus
                     double vx[4], vy[4], vz[4], vt[4];
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
@@ -689,7 +707,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                     if (lane == 0) { s_fx[K - 1] = s_fy[K - 1] = s_fz[K - 1] = __int_as_float(0x7f800000); }  // freed slot -> +inf
                 }
             }
-            if (tid == 0) {
+            if (vtid == 0) {
                 if (act == 1 && accepted) {  // append!, :85-88
                     s_nx[K] = s_prop->x; s_ny[K] = s_prop->y; s_nz[K] = s_prop->z; s_zeta[K] = s_prop->zeta;
                     s_fx[K] = (float)s_prop->x; s_fy[K] = (float)s_prop->y; s_fz[K] = (float)s_prop->z;
@@ -716,13 +734,14 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 else if (act == 5) noise = s_prop->zeta;
             }
         }
+        tick(4);
         // ================================================================ G: bookkeeping, traces, thinning (:275-281)
         int keep = 0;
         if ((double)iter >= pm.burn_in) {
             model_num += 1;
             if (fmod((double)model_num, pm.keep_each) == 0) keep = 1;
         }
-        if (tid == 0) {
+        if (vtid == 0) {
             if (act >= 1 && act <= 5) {
                 unsigned long long *c = reinterpret_cast<unsigned long long *>(a.counts) + (size_t)chain * 15 + (act - 1);
                 atomicAdd(c, 1ULL);  // RED: fire and forget
@@ -741,7 +760,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 for (int i = tid; i < 4 * KC; i += ST) hc[i] = s_nx[i];
                 double *hp = a.hist_ptS + h * R;
                 for (int r = tid; r < R; r += ST) hp[a.ray_orig[r]] = s_tstar[r];  // caller's ray order
-                if (tid == 0) {
+                if (vtid == 0) {
                     a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = iter;
                     a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;
                 }
@@ -749,8 +768,10 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             }
             n_hist += 1;
         }
+        tick(5);
     }
 
+    if (PROF && tid == 0) for (int i = 0; i < 9; i++) a.prof[(size_t)chain * 16 + i] += pt[i];
     // ---- write the chain state back (TMA bulk stores for the arrays)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the async proxy
     __syncthreads();

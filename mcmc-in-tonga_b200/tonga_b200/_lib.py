@@ -70,6 +70,7 @@ SYMBOLS = {
     "tonga_chains_verify": (C.c_int, [_P, c_lp, c_dp, c_dp]),
     "tonga_chains_kcap": (C.c_int, [_P]),
     "tonga_chains_device_ptrs": (C.c_int, [_P] + [c_vpp] * 8),
+    "tonga_chains_profile": (C.c_int, [_P, C.c_int32, c_lp]),
     "tonga_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "tonga_host_free": (C.c_int, [_P]),
     "tonga_peak_flops": (C.c_int, [_P, c_dp, c_dp]),

@@ -263,6 +263,12 @@ class Chains:
         check(self.lib.tonga_chains_raster(self._h, len(X), dp(X), dp(Y), dp(Z), dp(s1), dp(s2), C.byref(cnt)))
         return s1, s2, cnt.value
 
+    def profile(self, enable=True, read=False):
+        """Per-phase cycle totals of the sampler kernel: [n, 8] = A, B, C, D+E, F, G (developer aid)."""
+        cyc = np.zeros((self.n, 16), np.int64) if read else None
+        check(self.lib.tonga_chains_profile(self._h, 1 if enable else 0, lp(cyc)))
+        return cyc
+
     def verify(self):
         """Full re-evaluate of every chain on the device vs the incrementally maintained state."""
         mm, dphi, dts = C.c_int64(), C.c_double(), C.c_double()
