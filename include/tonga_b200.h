@@ -78,6 +78,10 @@ int tonga_info(const tonga_ctx *ctx, int32_t *R, int64_t *P, int64_t *S, int64_t
 /* ray_off[R+1]: CSR offsets of the flat point order (for interpreting `owners`) */
 int tonga_ray_offsets(const tonga_ctx *ctx, int32_t *ray_off);
 int tonga_synchronize(tonga_ctx *ctx);
+/* Distance arithmetic of the full evaluate.  0 (default): FP32 screening (best / second-best nucleus per point) with an exact
+ * FP64 re-scan of every point whose two best candidates fall inside a rigorous rounding-error band -- owners stay bit-exact;
+ * 1: every distance in exact FP64 (same results, slower). */
+int tonga_set_exact_only(tonga_ctx *ctx, int32_t exact_only);
 
 /* ---- evaluate(model, dataStruct, TD_parameters), MCsub.jl:123-185.
  * ptS_out[R] (model.ptS), *phi_out (model.phi), *like_out (model.likelihood: the model-independent constant of

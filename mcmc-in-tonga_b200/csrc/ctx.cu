@@ -256,6 +256,12 @@ extern "C" int tonga_ray_offsets(const tonga_ctx *ctx, int32_t *ray_off) {
     return TONGA_OK;
 }
 
+extern "C" int tonga_set_exact_only(tonga_ctx *ctx, int32_t exact_only) {
+    if (!ctx) return tg::fail(TONGA_ERR_ARG, "tonga_set_exact_only: ctx is NULL");
+    ctx->exact_only = exact_only ? 1 : 0;
+    return TONGA_OK;
+}
+
 extern "C" int tonga_host_alloc(void **ptr, uint64_t bytes) {
     if (!ptr) return tg::fail(TONGA_ERR_ARG, "tonga_host_alloc: NULL");
     *ptr = nullptr;

@@ -48,18 +48,21 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 __global__ void __launch_bounds__(EVAL_THREADS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
-               const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
+               const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, float tol_alpha,
+               float tol_beta2, int exact_only, const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
                const int32_t *__restrict__ point_orig, int R, int ldT, int64_t P, int64_t Ppad, int tile_pts,
                double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int model = blockIdx.y;
     const Tile tile = tiles[blockIdx.x];
     const int K = Ks[model];
-    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier | owner16[tile_pts]
+    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier | fl32 x,y,z [3][Kcap] | owner16[tile_pts]
     double *s_nx = reinterpret_cast<double *>(smem_raw);
     double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zeta + Kcap);
-    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_bar + 1);
+    float *s_fx = reinterpret_cast<float *>(s_bar + 1);
+    float *s_fy = s_fx + Kcap, *s_fz = s_fy + Kcap;
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_fz + Kcap);
 
     const double *mc = cells + (size_t)model * 4 * Kcap;
     const uint32_t nbytes = (uint32_t)(4 * Kcap * sizeof(double));
@@ -79,27 +82,72 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
         for (int i = threadIdx.x; i < 4 * Kcap; i += EVAL_THREADS) s_nx[i] = mc[i];
         __syncthreads();
     }
+    for (int i = threadIdx.x; i < 3 * Kcap; i += EVAL_THREADS) s_fx[i] = (float)s_nx[i];  // fl32 copies for the screening pass
+    __syncthreads();
 
-    // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263)
+    // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263).
+    // FP32 screening: best and second-best squared distance per point (4 points per thread, packed FADD2/FMUL2/FFMA2 over point
+    // pairs, each nucleus broadcast from shared memory); a point whose two best candidates are closer than the rigorous
+    // rounding-error band (or whose best is within the band of the 1e9 threshold) is re-scanned exactly in FP64, so the owners
+    // are bit-exact either way.
     const int npts = tile.p1 - tile.p0;
     for (int base = 0; base < npts; base += EVAL_THREADS * EVAL_PPT) {
-        double x[EVAL_PPT], y[EVAL_PPT], z[EVAL_PPT], best[EVAL_PPT];
         int bi[EVAL_PPT];
+        float dbest[EVAL_PPT];
+        uint32_t need_exact = 0;
+        int pidx[EVAL_PPT];
 #pragma unroll
         for (int q = 0; q < EVAL_PPT; q++) {
             const int j = base + q * EVAL_THREADS + threadIdx.x;
-            const int p = tile.p0 + (j < npts ? j : 0);
-            x[q] = px[p]; y[q] = py[p]; z[q] = pz[p];
-            best[q] = 1e9;  // mdist = 1e9, MCsub.jl:250
-            bi[q] = -1;
+            pidx[q] = tile.p0 + (j < npts ? j : 0);
         }
+        if (!exact_only) {
+            const float2 X01 = make_float2(pxf[pidx[0]], pxf[pidx[1]]), X23 = make_float2(pxf[pidx[2]], pxf[pidx[3]]);
+            const float2 Y01 = make_float2(pyf[pidx[0]], pyf[pidx[1]]), Y23 = make_float2(pyf[pidx[2]], pyf[pidx[3]]);
+            const float2 Z01 = make_float2(pzf[pidx[0]], pzf[pidx[1]]), Z23 = make_float2(pzf[pidx[2]], pzf[pidx[3]]);
+            float d1[EVAL_PPT], d2[EVAL_PPT];
+#pragma unroll
+            for (int q = 0; q < EVAL_PPT; q++) { d1[q] = 1e9f; d2[q] = 1e9f; bi[q] = -1; }
 #pragma unroll 2
-        for (int i = 0; i < K; i++) {
-            const double ax = s_nx[i], ay = s_ny[i], az = s_nz[i];
+            for (int i = 0; i < K; i++) {
+                const float ax = -s_fx[i], ay = -s_fy[i], az = -s_fz[i];
+                const float2 nax = make_float2(ax, ax), nay = make_float2(ay, ay), naz = make_float2(az, az);
+                float2 ex = __fadd2_rn(X01, nax), ey = __fadd2_rn(Y01, nay), ez = __fadd2_rn(Z01, naz);
+                const float2 da = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+                ex = __fadd2_rn(X23, nax); ey = __fadd2_rn(Y23, nay); ez = __fadd2_rn(Z23, naz);
+                const float2 db = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+                const float d[EVAL_PPT] = {da.x, da.y, db.x, db.y};
+#pragma unroll
+                for (int q = 0; q < EVAL_PPT; q++) {  // (a "rarely taken update branch" variant was measured: at warp level it is taken
+                    const bool lt = d[q] < d1[q];     //  almost every step, so the branch-free selects are as fast or faster)
+                    d2[q] = lt ? d1[q] : fminf(d2[q], d[q]);
+                    bi[q] = lt ? i : bi[q];
+                    d1[q] = lt ? d[q] : d1[q];
+                }
+            }
 #pragma unroll
             for (int q = 0; q < EVAL_PPT; q++) {
-                const double d = dist2_exact(ax, ay, az, x[q], y[q], z[q]);
-                if (d < best[q]) { best[q] = d; bi[q] = i; }  // strict <: lowest index wins ties (:255)
+                dbest[q] = d1[q];
+                const float tol = fmaf(tol_alpha, d1[q] + d2[q], tol_beta2);
+                if (!(d2[q] - d1[q] > tol)) need_exact |= 1u << q;  // ambiguous (d2 starts at 1e9: also covers the 1e9 threshold; NaN too)
+            }
+        } else {
+            need_exact = (1u << EVAL_PPT) - 1u;
+        }
+        if (need_exact) {
+#pragma unroll 1
+            for (int q = 0; q < EVAL_PPT; q++) {
+                if (!((need_exact >> q) & 1u)) continue;
+                const double x = px[pidx[q]], y = py[pidx[q]], z = pz[pidx[q]];
+                double best = 1e9;  // mdist = 1e9, MCsub.jl:250
+                int b = -1;
+#pragma unroll 2
+                for (int i = 0; i < K; i++) {
+                    const double d = dist2_exact(s_nx[i], s_ny[i], s_nz[i], x, y, z);
+                    if (d < best) { best = d; b = i; }  // strict <: lowest index wins ties (:255)
+                }
+                bi[q] = b;
+                dbest[q] = (float)best;
             }
         }
 #pragma unroll
@@ -110,7 +158,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                 const int64_t p = tile.p0 + j;
                 if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi[q];  // caller's flat order
                 if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
-                if (dmin32) dmin32[(size_t)model * Ppad + p] = (float)best[q];  // owner distance cache of the sampler (1e9 = none)
+                if (dmin32) dmin32[(size_t)model * Ppad + p] = bi[q] < 0 ? 1e9f : dbest[q];  // owner distance cache of the sampler
             }
         }
     }
@@ -156,12 +204,13 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if (!ctx->prm.debug_prior && ctx->n_tiles > 0) {
-        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + sizeof(uint16_t) * (size_t)ctx->tile_pts;
+        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + sizeof(float) * 3 * (size_t)Kcap + sizeof(uint16_t) * (size_t)ctx->tile_pts;
         if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
-                                                                  ctx->d_pz, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
+                                                                  ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->tol_alpha, ctx->tol_beta2,
+                                                                  ctx->exact_only, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev, dmin32_dev);
         TG_CUDA(cudaGetLastError());

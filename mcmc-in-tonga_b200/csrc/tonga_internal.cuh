@@ -176,6 +176,7 @@ struct tonga_ctx {
     // device geometry (SoA, flat point order, padded with NaN coordinates / zero dt)
     double *d_px = nullptr, *d_py = nullptr, *d_pz = nullptr;  // [Ppad]
     float *d_pxf = nullptr, *d_pyf = nullptr, *d_pzf = nullptr; // [Ppad] fl32 copies for the FP32 screening pass
+    int exact_only = 0;                                        // 1: full evaluate without FP32 screening (tonga_set_exact_only)
     float tol_alpha = 0.f, tol_beta2 = 0.f;                    // screening band: |dc - do| <= alpha*(dc+do) + beta2 -> exact FP64 recheck
     // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
     // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.

@@ -49,6 +49,7 @@ SYMBOLS = {
     "tonga_info": (C.c_int, [_P, c_ip, c_lp, c_lp, c_lp]),
     "tonga_ray_offsets": (C.c_int, [_P, c_ip]),
     "tonga_synchronize": (C.c_int, [_P]),
+    "tonga_set_exact_only": (C.c_int, [_P, C.c_int32]),
     "tonga_evaluate": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp, c_dp, c_dp]),
     "tonga_evaluate_batch": (C.c_int, [_P, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "tonga_evaluate_batch_dev": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),

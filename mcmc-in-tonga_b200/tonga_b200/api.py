@@ -137,6 +137,10 @@ class Context:
     def synchronize(self):
         check(self.lib.tonga_synchronize(self._h))
 
+    def set_exact_only(self, flag: bool):
+        """True: full evaluate entirely in exact FP64 (default: FP32 screening + exact re-scan of near ties)."""
+        check(self.lib.tonga_set_exact_only(self._h, 1 if flag else 0))
+
     def interpolate(self, mx, my, mz, mv, X, Y, Z):
         mx, my, mz, mv = (np.ascontiguousarray(a, dtype=np.float64) for a in (mx, my, mz, mv))
         X, Y, Z = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (X, Y, Z))

@@ -526,3 +526,45 @@ def test_parallel_tempering_keeps_the_cold_posterior():
         se = np.sqrt(a.var() * 20 / len(a) + b.var() * 20 / len(b))
         assert abs(a.mean() - b.mean()) < 8 * se, (a.mean(), b.mean(), se)
     pt.close(); plain.close(); ctx.close()
+
+
+def test_evaluate_screening_equals_exact(tonga_ctx):
+    """Full evaluate: FP32 screening + exact re-scan must give bit-identical owners / t* / phi to the pure FP64 pass, also with
+    planted exact ties (mirror-image nuclei) and K = 2000 (small cells: many near ties)."""
+    ctx, ds, p = tonga_ctx
+    rng = np.random.default_rng(9)
+    for K in (2, 7, 100, 2000):
+        mdl = list(random_model(rng, K, box_of(ds)))
+        if K >= 2:  # nucleus 1 = mirror image of nucleus 0 about a ray point -> exact tie at that point
+            pt = np.array([ds.rayX[5, 11], ds.rayY[5, 11], ds.rayZ[5, 11]])
+            for a in range(3):
+                mdl[a][1] = 2 * pt[a] - mdl[a][0]
+        Kb, cells = np.array([K], np.int32), np.stack(mdl)[None]
+        ctx.set_exact_only(False)
+        a = ctx.evaluate_batch(Kb, cells, want_owners=True)
+        ctx.set_exact_only(True)
+        b = ctx.evaluate_batch(Kb, cells, want_owners=True)
+        ctx.set_exact_only(False)
+        assert np.array_equal(a["owners"], b["owners"]) and np.array_equal(a["ptS"], b["ptS"]) and np.array_equal(a["phi"], b["phi"])
+
+
+def test_evaluate_synthetic_config3_shape():
+    """BASELINE config 3 style synthetic set (straight jittered rays, 150-250 points each, K up to 500) at reduced ray count:
+    owners bit-exact and t*/phi within 1e-9 of the oracle."""
+    import oracle as O
+    from tonga_b200.api import Context
+    from tonga_b200.data import synthetic_rays
+    from tonga_b200.structs import parameters
+    p = parameters()
+    ds = synthetic_rays(400, seed=3, p=p)
+    ctx = Context(ds, p)
+    assert ctx.P > 60000
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(4)
+    for K in (50, 500):
+        mdl = random_model(rng, K, box_of(ds))
+        ref = O.evaluate(op, od, *mdl, want_owners=True)
+        gb = ctx.evaluate_batch(np.array([K], np.int32), np.stack(mdl)[None], want_owners=True)
+        assert np.array_equal(gb["owners"][0], _flat_owners(ref["owners"], ctx))
+        assert _close(gb["ptS"][0], ref["ptS"]) and _close(gb["phi"][0], ref["phi"])
+    ctx.close()
