@@ -204,6 +204,8 @@ struct tonga_chains {
 static inline size_t tg_nz(size_t b) { return b ? b : 1; }
 #define TG_ALLOC(ptr, bytes) TG_CUDA(cudaMalloc((void **)&(ptr), tg_nz(bytes)))
 
+static void tonga_chains_destroy_unlocked(tonga_chains *ch);
+
 extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                                    int32_t hist_cap) {
     if (!ctx || !out || nChains < 1 || hist_cap < 0) return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: bad argument");
@@ -215,6 +217,11 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     tonga_chains *ch = new tonga_chains();
+    struct Guard {  // frees a half-built batch when an allocation below fails (TG_ALLOC / TG_CUDA return early)
+        tonga_chains *&c;
+        bool armed = true;
+        ~Guard() { if (armed && c) { tonga_chains *t = c; c = nullptr; tonga_chains_destroy_unlocked(t); } }
+    } guard{ch};
     ch->ctx = ctx;
     ch->n = nChains;
     ch->KC = ((pm.max_cells + 7) / 8) * 8;
@@ -225,7 +232,6 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     ch->smem = tg::smem_layout((int)ctx->Ppad, ch->Rp, ch->KC).total;
     if (ch->smem > ctx->smem_optin) {
         const size_t need = ch->smem;
-        delete ch;
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(need) +
                                                 " B) exceeds shared memory; the smem-resident sampler handles ray sets up to ~200k points");
     }
@@ -283,11 +289,20 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     TG_CUDA(cudaEventCreate(&ch->ev0));
     TG_CUDA(cudaEventCreate(&ch->ev1));
+    guard.armed = false;
     *out = ch;
     return TONGA_OK;
 }
 
+static void tonga_chains_destroy_unlocked(tonga_chains *ch);
+
 extern "C" void tonga_chains_destroy(tonga_chains *ch) {
+    if (!ch) return;
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    tonga_chains_destroy_unlocked(ch);
+}
+
+static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     if (!ch) return;
     cudaSetDevice(ch->ctx->device);
     cudaStreamSynchronize(ch->ctx->stream);

@@ -568,3 +568,45 @@ def test_evaluate_synthetic_config3_shape():
         assert np.array_equal(gb["owners"][0], _flat_owners(ref["owners"], ctx))
         assert _close(gb["ptS"][0], ref["ptS"]) and _close(gb["phi"][0], ref["phi"])
     ctx.close()
+
+
+def test_abi_error_paths_and_helpers(tonga):
+    """Error behaviour at the C ABI (codes + messages, no exceptions across it) and the small helper entry points."""
+    import copy
+    from tonga_b200 import _lib, api
+    ds, p0 = tonga
+    ctx = api.Context(ds, p0)
+    # evaluate: K outside [0, Kcap]
+    with pytest.raises(_lib.TongaError) as e:
+        ctx.evaluate_batch(np.array([9], np.int32), np.zeros((1, 4, 4)))
+    assert e.value.code == -1
+    # chains: run before start models -> TONGA_ERR_STATE; K above capacity -> TONGA_ERR_CAPACITY
+    ch = api.Chains(ctx, 2, hist_cap=0)
+    with pytest.raises(_lib.TongaError) as e:
+        ch.run(1)
+    assert e.value.code == -4
+    with pytest.raises(_lib.TongaError) as e:
+        ch.set_models(np.array([200, 5], np.int32), np.zeros((2, 4, 200)))
+    assert e.value.code == -3
+    ch.build_starting()
+    s1, s2, cnt = ch.raster([0.0, 1.0], [0.0, 1.0], [0.0, 1.0])  # no history kept -> count 0, zero sums
+    assert cnt == 0 and not s1.any() and not s2.any()
+    # profile counters and pinned buffers
+    ch.profile(True); ch.run(50); cyc = ch.profile(False, read=True)
+    assert cyc.shape == (2, 16) and (cyc[:, :6] > 0).all()
+    hist, state = ch.alloc_buffers(pinned=True)
+    st = ch.state(out=state)
+    assert st["K"] is state["K"] and (st["K"] >= p0.min_cells).all()
+    ch.close()
+    # u8 owner state supports at most 126 cells
+    p = copy.copy(p0); p.max_cells = 127
+    ctx2 = api.Context(ds, p)
+    with pytest.raises(_lib.TongaError) as e:
+        api.Chains(ctx2, 1)
+    assert e.value.code == -3 and "126" in str(e.value)
+    # interp_style 2 is broken in the reference (MCsub.jl:332) -> refused
+    p = copy.copy(p0); p.interp_style = 2
+    with pytest.raises(_lib.TongaError) as e:
+        api.Context(ds, p)
+    assert e.value.code == -1
+    ctx.close(); ctx2.close()
