@@ -112,15 +112,16 @@ def synthetic_rays(R: int, seed: int = 3, pts=(150, 250), box=(1000.0, 1000.0, 6
     m = int(npts.max())
     src = np.stack([rng.uniform(0, bx, R), rng.uniform(0, by, R), rng.uniform(50.0, bz, R)], 1)
     rcv = np.stack([rng.uniform(0, bx, R), rng.uniform(0, by, R), np.zeros(R)], 1)
-    x = np.full((m, R), np.nan, order="F")
-    y = np.full((m, R), np.nan, order="F")
-    z = np.full((m, R), np.nan, order="F")
-    for i in range(R):
-        n = npts[i]
-        t = np.linspace(0.0, 1.0, n)[:, None]
-        pt = src[i] + t * (rcv[i] - src[i]) + rng.normal(0.0, jitter, (n, 3))
-        pt[:, 2] = np.clip(pt[:, 2], 0.0, bz)
-        x[:n, i], y[:n, i], z[:n, i] = pt[:, 0], pt[:, 1], pt[:, 2]
+    # all rays at once: parameter t = k / (n-1) for k < n, NaN beyond (point x ray, Fortran order like the reference)
+    kk = np.arange(m)[:, None]
+    valid = kk < npts[None, :]
+    t = kk / np.maximum(npts[None, :] - 1, 1)
+    def axis(a, b):
+        v = a[None, :] + t * (b - a)[None, :] + rng.normal(0.0, jitter, (m, R))
+        return np.asfortranarray(np.where(valid, v, np.nan))
+    x, y = axis(src[:, 0], rcv[:, 0]), axis(src[:, 1], rcv[:, 1])
+    z = axis(src[:, 2], rcv[:, 2])
+    z = np.asfortranarray(np.where(valid, np.clip(z, 0.0, bz), np.nan))
     tab = ak135 if ak135 is not None else np.c_[_AK135_COARSE, np.zeros(len(_AK135_COARSE))]
     U = ak135_slowness(z, tab)
     sig = rng.uniform(0.04, 0.66, R)
@@ -131,10 +132,12 @@ def synthetic_rays(R: int, seed: int = 3, pts=(150, 250), box=(1000.0, 1000.0, 6
     tx, ty, tz = rng.uniform(0, bx, n_true), rng.uniform(0, by, n_true), rng.uniform(0, bz, n_true)
     tzeta = rng.uniform(0, zeta_scale, n_true)
     tS = np.zeros(R)
-    for i in range(R):
-        n = npts[i]
-        d = (tx[None] - x[:n, i, None]) ** 2 + (ty[None] - y[:n, i, None]) ** 2 + (tz[None] - z[:n, i, None]) ** 2
-        zt = tzeta[np.argmin(d, 1)]
-        tS[i] = np.sum(ds.rayL[:n - 1, i] * ds.rayU[:n - 1, i] * (0.5 * (zt[:-1] + zt[1:]) / 1000))
+    for i0 in range(0, R, 512):  # chunked nearest-nucleus forward model (host-side data synthesis only)
+        sl = slice(i0, min(i0 + 512, R))
+        xs, ys, zs = np.nan_to_num(x[:, sl]), np.nan_to_num(y[:, sl]), np.nan_to_num(z[:, sl])
+        d = (tx[None, None] - xs[..., None]) ** 2 + (ty[None, None] - ys[..., None]) ** 2 + (tz[None, None] - zs[..., None]) ** 2
+        zt = tzeta[np.argmin(d, 2)]
+        seg = np.nan_to_num(ds.rayL[:, sl] * ds.rayU[:, sl]) * (0.5 * (zt[:-1] + zt[1:]) / 1000)
+        tS[sl] = seg.sum(0)
     ds.tS = tS + rng.normal(0.0, sig)
     return ds
