@@ -114,6 +114,21 @@ int tonga_interpolate(tonga_ctx *ctx, int32_t K, const double *x, const double *
  * hist_cap = kept models per chain the history can hold (TD_inversion_function.jl:25 num_models_per_chain). */
 int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                         int32_t hist_cap);
+/* Two samplers implement the same loop and give bit-identical chains:
+ *   RESIDENT  one CTA per chain, the whole chain state (a nucleus index per ray point, t* per ray) in shared memory and
+ *             updated incrementally; needs max_cells <= 126 and a ray set of up to ~200k points (the 381-ray Tonga set
+ *             uses 32 KB).  The fast path (BASELINE.json configs 1, 2, 4, 5).
+ *   WIDE      no per-point chain state: every proposal runs the full batched forward model (as the reference does,
+ *             MCsub.jl:123-185) on the candidate models of all chains; any ray set and max_cells up to ~5000
+ *             (BASELINE.json config 3: 100k rays, 2000 nuclei).  At most 65535 chains per batch.
+ * AUTO = RESIDENT when it fits, else WIDE; tonga_chains_create is create_ex(AUTO). */
+#define TONGA_SAMPLER_AUTO 0
+#define TONGA_SAMPLER_RESIDENT 1
+#define TONGA_SAMPLER_WIDE 2
+int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
+                           int32_t hist_cap, int32_t sampler);
+/* TONGA_SAMPLER_RESIDENT or TONGA_SAMPLER_WIDE (0 for NULL) */
+int tonga_chains_sampler(const tonga_chains *ch);
 void tonga_chains_destroy(tonga_chains *ch);
 
 /* Start models.  build_starting (MCsub.jl:76-121) on the device ... */

@@ -56,6 +56,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     const int model = blockIdx.y;
     const Tile tile = tiles[blockIdx.x];
     const int K = Ks[model];
+    if (K < 0) return;  // wide sampler: this chain has no candidate to evaluate in this iteration
     // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier | fl32 x,y,z [3][Kcap] | owner16[tile_pts]
     double *s_nx = reinterpret_cast<double *>(smem_raw);
     double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
@@ -200,10 +201,10 @@ tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, co
 }
 
 int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
-                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev) {
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev, bool force_geometry) {
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
-    if (!ctx->prm.debug_prior && ctx->n_tiles > 0) {
+    if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
         const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + sizeof(float) * 3 * (size_t)Kcap + sizeof(uint16_t) * (size_t)ctx->tile_pts;
         if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

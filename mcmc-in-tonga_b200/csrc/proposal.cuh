@@ -1,0 +1,210 @@
+// proposal.cuh -- the proposal draw / a-priori checks and the acceptance rule of TD_inversion_function.jl:72-272, shared by the
+// shared-memory-resident sampler (sampler_kernel.cuh) and the wide sampler (wide_sampler.cu) so that both follow the
+// reference identically.
+#pragma once
+#include "tonga_internal.cuh"
+
+namespace tg {
+
+struct Prop {  // proposal of the current iteration
+    int action, idx, do_eval, accept;
+    double x, y, z, zeta, u;
+    double aux;            // birth: czeta (:81); death: zetanew (:146)
+    double ox, oy, oz;     // move: the old position (resident sampler: the nucleus array holds the proposed one during B..E)
+    double ztag;           // zeta of the implicit new owner of tagged bytes (birth: zetanew; move: zeta[idx])
+};
+
+// ---- warp-cooperative v_nearest (MCsub.jl:247-263) over K nuclei, skipping index `skip` --------------------------
+// SPACE (0 = shared-memory nuclei, 1 = global-memory nuclei) only separates the instantiations: each is called with
+// pointers of one address space, so the compiler specialises the loads (LDS vs LDG) instead of emitting generic ones.
+template <int SPACE>
+__device__ __noinline__ int warp_nearest(const double *nx, const double *ny, const double *nz, int K, int skip, double x,
+                                         double y, double z, int lane) {
+    double best = 1e9;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < K; i += 32) {
+        if (i == skip) continue;
+        const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);
+        if (d < best) { best = d; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    }
+    return bi == 0x7fffffff ? -1 : bi;
+}
+
+__device__ __forceinline__ double jl_min1(double a) {  // min([1 a]...) in Julia: NaN propagates
+    return (a != a) ? a : (a < 1.0 ? a : 1.0);
+}
+
+// Box-Muller pair from two uniforms in [0,1)
+__device__ __noinline__ void normal_pair(double u1, double u2, double &n0, double &n1) {
+    const double rr = sqrt(-2.0 * log(u1 + 0x1.0p-54));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    n0 = rr * cs;
+    n1 = rr * sn;
+}
+
+// Warp-collective (all 32 lanes of one warp call it with identical scalars): draws (mode 0, Philox4x32-10 keyed by `seed`, counter =
+// (iteration, global chain id, slot)) or takes over a recorded proposal, applies the a-priori checks of the reference and
+// evaluates v_nearest at the new / killed nucleus.  sig_zeta = zeta_scale * sig / 100 (TD_inversion_function.jl:22, hoisted by the
+// caller).  Returns `valid`
+// (1 = the candidate must be evaluated); pr.action / idx / x / y / z / zeta / u / aux are set on every lane.
+template <int SPACE>
+__device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_proposal *rec_in, unsigned long long seed, long long iter,
+                                             unsigned long long gid, const double *nx, const double *ny, const double *nz,
+                                             const double *nzeta, int K, double noise, const tonga_params &pm, double sig_zeta, int lane) {
+    pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
+    pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
+    double uu[8];
+    if (mode == 0) {
+        const Philox philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (lane < 4) philox((uint32_t)iter, (uint32_t)((unsigned long long)iter >> 32), (uint32_t)gid, (uint32_t)lane | ((uint32_t)(gid >> 32) << 8), w);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
+            const uint32_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
+            uu[2 * s] = u53(w0, w1);
+            uu[2 * s + 1] = u53(w2, w3);
+        }
+        const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
+        const int act0 = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
+        pr.action = act0 > nact ? nact : act0;
+    } else {
+        const tonga_proposal rec = *rec_in;
+        pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
+    }
+    const int act = pr.action;
+    int valid = 0;
+    if (act == 1) {  // ---- birth :76-125
+        if (K < pm.max_cells) {
+            if (mode == 0) {
+                pr.x = uu[2] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
+                pr.y = uu[3] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
+                pr.z = uu[4] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
+            }
+            const int ci = warp_nearest<SPACE>(nx, ny, nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
+            const double czeta = ci < 0 ? 0.0 : nzeta[ci];
+            pr.aux = czeta;
+            if (mode == 0) {
+                double n0, n1;
+                normal_pair(uu[5], uu[6], n0, n1);
+                pr.zeta = czeta + sig_zeta * n0;  // :82
+                pr.u = uu[7];                     // :121
+            }
+            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
+            else if (pm.prior == 2) valid = 1;
+            else valid = (pr.zeta > 0);  // :111
+        }
+    } else if (act == 2) {  // ---- death :126-181
+        if (K > pm.min_cells) {
+            if (mode == 0) {
+                const int k = (int)floor(uu[1] * K);  // :128
+                pr.idx = k >= K ? K - 1 : k;
+                pr.u = uu[7];  // :176
+            }
+            const int kill = pr.idx;
+            if (kill >= 0 && kill < K) {
+                const int zi = warp_nearest<SPACE>(nx, ny, nz, K, kill, nx[kill], ny[kill], nz[kill], lane);  // :146
+                pr.aux = zi < 0 ? 0.0 : nzeta[zi];
+                valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
+            }
+        }
+    } else if (act == 3) {  // ---- change :183-218
+        if (mode == 0) {
+            const int k = (int)floor(uu[1] * K);  // :184
+            pr.idx = k >= K ? K - 1 : k;
+            double n0, n1;
+            normal_pair(uu[2], uu[3], n0, n1);
+            pr.zeta = nzeta[pr.idx] + sig_zeta * n0;  // :188
+            pr.u = uu[7];                             // :214
+        }
+        if (pr.idx >= 0 && pr.idx < K) {
+            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
+            else if (pm.prior == 2) valid = 1;
+            else valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
+            // the reference evaluates first (:191) but discards the result when invalid
+        }
+    } else if (act == 4) {  // ---- move :220-251
+        if (K > 0) {
+            if (mode == 0) {
+                const int k = (int)floor(uu[1] * K);  // :222
+                pr.idx = k >= K ? K - 1 : k;
+                double n0, n1, n2, n3;
+                normal_pair(uu[2], uu[3], n0, n1);
+                normal_pair(uu[4], uu[5], n2, n3);
+                pr.x = nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
+                pr.y = ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
+                pr.z = nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
+                pr.u = uu[7];                                                      // :247
+            }
+            if (pr.idx >= 0 && pr.idx < K) {
+                valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
+                         pr.z <= pm.zmax);  // :230-232
+                if (valid) { pr.ox = nx[pr.idx]; pr.oy = ny[pr.idx]; pr.oz = nz[pr.idx]; }
+            }
+        }
+    } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
+        if (mode == 0) {
+            double n0, n1;
+            normal_pair(uu[2], uu[3], n0, n1);
+            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * n0;  // :23,:254
+            pr.u = uu[7];
+        }
+        valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
+    }
+    pr.do_eval = valid;
+    return valid;
+}
+
+// The acceptance rule, TD_inversion_function.jl:96-97,107-108,113-114 (birth), :151-152,160-162,166-168 (death), :196,202-203,207-208
+// (change), :241-242 (move), :264-267 (sigma, extension), with the reference's operation order.  K = nCells of the CURRENT
+// model, zeta_idx = current zeta[idx] (death / change), beta = inverse temperature (1 = reference), R = number of data.
+__device__ __forceinline__ int accept_decision(const Prop &pr, int K, double phi, double phin, double zeta_idx, double noise, double beta,
+                                               int R, const tonga_params &pm, double sig_zeta) {
+    const double PI = 3.141592653589793;
+    const int act = pr.action;
+    const double K0 = (double)K;
+    const double zn = pr.zeta, aux = pr.aux, u = pr.u;
+    const double dphi2 = beta * ((phin - phi) / 2);
+    double alpha = 0.0;
+    if (act == 1) {
+        const double g = ((aux - zn) * (aux - zn)) / (2 * (sig_zeta * sig_zeta));
+        if (pm.prior == 1)  // :96-97
+            alpha = ((K0) / (K0 + 1)) * ((sig_zeta * sqrt(2 * PI)) / (pm.zeta_scale)) * exp(g - dphi2);
+        else if (pm.prior == 2)  // :107-108
+            alpha = ((K0) / (K0 + 1)) * (sig_zeta / pm.zeta_scale) * exp(-(zn * zn) / (pm.zeta_scale * pm.zeta_scale) + g - dphi2);
+        else  // :113-114
+            alpha = ((K0) / (K0 + 1)) * (sqrt(2 * PI) * sig_zeta / pm.zeta_scale) * exp(-zn / pm.zeta_scale + g - dphi2);
+        return u < jl_min1(alpha);
+    } else if (act == 2) {
+        const double zk = zeta_idx;
+        const double g = ((zk - aux) * (zk - aux)) / (2 * (sig_zeta * sig_zeta));
+        if (pm.prior == 1)  // :151-152
+            alpha = ((K0) / (K0 - 1)) * ((pm.zeta_scale) / (sig_zeta * sqrt(2 * PI))) * exp(-g - dphi2);
+        else if (pm.prior == 2)  // :160-162
+            alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / sig_zeta) * exp((zk * zk) / (2 * (pm.zeta_scale * pm.zeta_scale)) - g - dphi2);
+        else  // :166-168
+            alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / (sqrt(2 * PI) * sig_zeta)) * exp(zk / pm.zeta_scale - g - dphi2);
+        return u < jl_min1(alpha);
+    } else if (act == 3) {
+        const double zo = zeta_idx;
+        if (pm.prior == 1) alpha = exp(-dphi2);  // :196
+        else if (pm.prior == 2) alpha = exp((zo * zo - zn * zn) / (2 * (pm.zeta_scale * pm.zeta_scale)) - dphi2);  // :202-203
+        else alpha = exp((zo - zn) / pm.zeta_scale - dphi2);  // :207-208
+        return u < jl_min1(alpha);
+    } else if (act == 4) {
+        return u < jl_min1(exp(-dphi2));  // :241-242
+    }
+    // sigma: log form :264-267
+    double la = beta * (log(noise / zn) * (double)R) - dphi2;  // beta = 1: TD_inversion_function.jl:264
+    la = (la != la) ? la : (la < 0.0 ? la : 0.0);
+    return log(u) <= la;
+}
+
+}  // namespace tg

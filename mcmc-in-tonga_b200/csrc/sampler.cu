@@ -32,6 +32,7 @@ static_assert(ST == TG_PHI_LANES, "the canonical phi reduction is defined over 1
 }  // namespace tg
 
 #include "sampler_kernel.cuh"
+#include "wide_kernels.cuh"
 
 namespace tg {
 
@@ -175,6 +176,7 @@ struct tonga_chains {
     unsigned long long seed = 0;
     long long iter_done = 0;
     bool have_models = false;
+    bool wide = false;  // wide sampler (wide_kernels.cuh): no per-point chain state, a full forward model per proposal
     int exact_only = 0;
     long long *d_prof = nullptr;  // optional per-phase cycle counters (tonga_chains_profile)
     size_t smem = 0;
@@ -191,8 +193,12 @@ struct tonga_chains {
     double *d_hist_cells = nullptr, *d_hist_phi = nullptr, *d_hist_ptS = nullptr;
     long long *d_hist_iter = nullptr;
     int32_t *d_hist_action = nullptr, *d_hist_accept = nullptr, *d_hist_next = nullptr;
+    // wide sampler: candidate models
+    int32_t *d_Kc = nullptr;
+    double *d_cells_c = nullptr;
+    tg::Prop *d_props = nullptr;
     // scratch
-    double *d_ptS_tmp = nullptr;  // [n][R]
+    double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
     uint8_t *d_owner_tmp = nullptr;
     unsigned long long *d_mism = nullptr;
@@ -208,12 +214,29 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch);
 
 extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                                    int32_t hist_cap) {
-    if (!ctx || !out || nChains < 1 || hist_cap < 0) return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: bad argument");
+    return tonga_chains_create_ex(ctx, out, nChains, chain_id0, seed, hist_cap, TONGA_SAMPLER_AUTO);
+}
+
+extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
+                                      int32_t hist_cap, int32_t sampler) {
+    if (!ctx || !out || nChains < 1 || hist_cap < 0 || sampler < TONGA_SAMPLER_AUTO || sampler > TONGA_SAMPLER_WIDE)
+        return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: bad argument");
     *out = nullptr;
     const tonga_params &pm = ctx->prm;
-    if (pm.max_cells > TG_MAX_K_U8 || pm.max_cells < 1 || pm.min_cells < 1 || pm.min_cells > pm.max_cells)
-        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: need 1 <= min_cells <= max_cells <= 126 (u8 owner state)");
+    if (pm.max_cells < 1 || pm.min_cells < 1 || pm.min_cells > pm.max_cells)
+        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: need 1 <= min_cells <= max_cells");
     if (ctx->R < 1 || ctx->P < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: empty ray set");
+    const int KC0 = ((pm.max_cells + 7) / 8) * 8;
+    const size_t smem_res = tg::smem_layout((int)ctx->Ppad, ctx->Rp, KC0).total;
+    const bool fits = pm.max_cells <= TG_MAX_K_U8 && smem_res <= ctx->smem_optin;
+    if (sampler == TONGA_SAMPLER_RESIDENT && !fits) {
+        if (pm.max_cells > TG_MAX_K_U8)
+            return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the resident sampler needs max_cells <= 126 (u8 owner state)");
+        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(smem_res) +
+                                                " B) exceeds shared memory; the smem-resident sampler handles ray sets up to ~200k points");
+    }
+    const bool wide = (sampler == TONGA_SAMPLER_WIDE) || !fits;
+    if (wide && nChains > 65535) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the wide sampler runs at most 65535 chains per batch");
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     tonga_chains *ch = new tonga_chains();
@@ -229,12 +252,8 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     ch->hist_cap = hist_cap;
     ch->chain_id0 = chain_id0;
     ch->seed = seed;
-    ch->smem = tg::smem_layout((int)ctx->Ppad, ch->Rp, ch->KC).total;
-    if (ch->smem > ctx->smem_optin) {
-        const size_t need = ch->smem;
-        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(need) +
-                                                " B) exceeds shared memory; the smem-resident sampler handles ray sets up to ~200k points");
-    }
+    ch->wide = wide;
+    ch->smem = wide ? 0 : smem_res;
     const size_t n = (size_t)nChains, KC = (size_t)ch->KC, R = (size_t)ctx->R, Rp = (size_t)ch->Rp, Pp = (size_t)ctx->Ppad, H = (size_t)hist_cap;
     TG_ALLOC(ch->d_K, 4 * n);
     TG_ALLOC(ch->d_cells, 8 * n * 4 * KC);
@@ -242,9 +261,17 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     TG_ALLOC(ch->d_noise, 8 * n);
     TG_ALLOC(ch->d_beta, 8 * n);
     TG_ALLOC(ch->d_tstar, 8 * n * Rp);
-    TG_ALLOC(ch->d_owner, n * Pp);
-    TG_ALLOC(ch->d_dcache, 4 * n * Pp);
-    TG_ALLOC(ch->d_dcache_tmp, 4 * n * Pp);
+    if (!wide) {
+        TG_ALLOC(ch->d_owner, n * Pp);
+        TG_ALLOC(ch->d_dcache, 4 * n * Pp);
+        TG_ALLOC(ch->d_dcache_tmp, 4 * n * Pp);
+        TG_ALLOC(ch->d_owner_tmp, n * Pp);
+    } else {
+        TG_ALLOC(ch->d_Kc, 4 * n);
+        TG_ALLOC(ch->d_cells_c, 8 * n * 4 * KC);
+        TG_ALLOC(ch->d_props, sizeof(tg::Prop) * n);
+        TG_CUDA(cudaMemsetAsync(ch->d_cells_c, 0, 8 * n * 4 * KC, ctx->stream));
+    }
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
     TG_ALLOC(ch->d_n_hist, 4 * n);
@@ -259,7 +286,6 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
     TG_ALLOC(ch->d_hist_next, 4 * n * H);
     TG_ALLOC(ch->d_ptS_tmp, 8 * n * R);
     TG_ALLOC(ch->d_phi_tmp, 8 * n);
-    TG_ALLOC(ch->d_owner_tmp, n * Pp);
     TG_ALLOC(ch->d_mism, 8);
     TG_ALLOC(ch->d_maxd, 16);
     cudaStream_t s = ctx->stream;
@@ -283,10 +309,16 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
         TG_CUDA(cudaMemcpyAsync(ch->d_noise, ones.data(), 8 * n, cudaMemcpyHostToDevice, s));
         TG_CUDA(cudaStreamSynchronize(s));
     }
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-    TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    if (!wide) {
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+    }
+    if (8 * 4 * KC > 48 * 1024) {
+        if (8 * 4 * KC > ctx->smem_optin) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: max_cells too large for shared memory");
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 4 * KC)));
+    }
     TG_CUDA(cudaEventCreate(&ch->ev0));
     TG_CUDA(cudaEventCreate(&ch->ev1));
     guard.armed = false;
@@ -309,7 +341,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd};
+                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props};
     for (void *p : ptrs) cudaFree(p);
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
@@ -320,7 +352,8 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
 // full evaluate of the current device-resident models -> owners, t*, phi of the chain state
 static int establish_state(tonga_chains *ch) {
     tonga_ctx *ctx = ch->ctx;
-    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner, ch->d_dcache);
+    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner, ch->d_dcache,
+                                 /*force_geometry=*/true);  // debug_prior: phi = 1 but the chain state (owners, t*) is still well defined
     if (rc != TONGA_OK) return rc;
     const size_t tot = (size_t)ch->n * ch->Rp;
     tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_ptS_tmp, ch->d_tstar);
@@ -375,6 +408,7 @@ extern "C" int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only)
 
 extern "C" int tonga_chains_profile(tonga_chains *ch, int32_t enable, int64_t *cycles /* [nChains][16] or NULL */) {
     if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_profile: NULL");
+    if (ch->wide) return tg::fail(TONGA_ERR_STATE, "tonga_chains_profile: per-phase counters exist only in the resident sampler");
     std::lock_guard<std::mutex> lk(ch->ctx->mu);
     TG_CUDA(cudaSetDevice(ch->ctx->device));
     TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
@@ -420,6 +454,37 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     char *d = (char *)ctx->d_scratch;
     if (mode == 1) TG_CUDA(cudaMemcpyAsync(d + o_rec, recs, sizeof(tonga_proposal) * N, cudaMemcpyHostToDevice, s));
 
+    const tonga_proposal *recs_in = (mode == 1) ? (const tonga_proposal *)(d + o_rec) : nullptr;
+    tonga_proposal *recs_out = (mode == 0 && recs) ? (tonga_proposal *)(d + o_rec) : nullptr;
+    int8_t *d_tr_accept = tr_accept ? (int8_t *)(d + o_acc) : nullptr;
+    double *d_tr_phi = tr_phi ? (double *)(d + o_phi) : nullptr;
+    int32_t *d_tr_K = tr_K ? (int32_t *)(d + o_K) : nullptr;
+    TG_CUDA(cudaEventRecord(ch->ev0, s));
+    if (ch->wide) {
+        tg::WideArgs w{};
+        w.prm = ctx->prm; w.R = ctx->R; w.Rp = ch->Rp; w.KC = ch->KC; w.mode = mode; w.hist_cap = ch->hist_cap; w.nIter = nIter;
+        w.seed = ch->seed; w.chain_id0 = ch->chain_id0; w.ray_orig = ctx->d_ray_orig; w.tS = ctx->d_tS; w.sig = ctx->d_sig;
+        w.K = ch->d_K; w.cells = ch->d_cells; w.phi = ch->d_phi; w.noise = ch->d_noise; w.beta = ch->d_beta; w.tstar = ch->d_tstar;
+        w.counts = ch->d_counts; w.pending_slot = ch->d_pending;
+        w.Kc = ch->d_Kc; w.cells_c = ch->d_cells_c; w.ptS_c = ch->d_ptS_tmp; w.props = ch->d_props;
+        w.recs_in = recs_in; w.recs_out = recs_out; w.tr_accept = d_tr_accept; w.tr_phi = d_tr_phi; w.tr_K = d_tr_K;
+        w.n_hist = ch->d_n_hist; w.model_num = ch->d_model_num; w.hist_K = ch->d_hist_K; w.hist_cells = ch->d_hist_cells;
+        w.hist_phi = ch->d_hist_phi; w.hist_ptS = ch->d_hist_ptS; w.hist_iter = ch->d_hist_iter; w.hist_action = ch->d_hist_action;
+        w.hist_accept = ch->d_hist_accept; w.hist_next = ch->d_hist_next;
+        const int saved_exact = ctx->exact_only;
+        ctx->exact_only = ch->exact_only || saved_exact;
+        for (int64_t it = 0; it < nIter; it++) {
+            w.it = it; w.iter = ch->iter_done + 1 + it;
+            tg::tg_wide_propose_kernel<<<ch->n, tg::WIDE_PROPOSE_THREADS, 0, s>>>(w);
+            if (!ctx->prm.debug_prior) {
+                rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_Kc, ch->d_cells_c, nullptr, ch->d_ptS_tmp, nullptr, nullptr, nullptr, nullptr);
+                if (rc != TONGA_OK) { ctx->exact_only = saved_exact; return rc; }
+            }
+            tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
+        }
+        ctx->exact_only = saved_exact;
+        TG_CUDA(cudaGetLastError());
+    } else {
     tg::SamplerArgs a{};
     a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
     a.pxf = ctx->d_pxf; a.pyf = ctx->d_pyf; a.pzf = ctx->d_pzf; a.tol_alpha = ctx->tol_alpha; a.tol_beta2 = ctx->tol_beta2;
@@ -431,17 +496,11 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
     a.owner = ch->d_owner; a.dcache = ch->d_dcache; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;
     a.iter0 = ch->iter_done + 1; a.nIter = nIter; a.mode = mode;
-    a.recs_in = (mode == 1) ? (const tonga_proposal *)(d + o_rec) : nullptr;
-    a.recs_out = (mode == 0 && recs) ? (tonga_proposal *)(d + o_rec) : nullptr;
-    a.tr_accept = tr_accept ? (int8_t *)(d + o_acc) : nullptr;
-    a.tr_phi = tr_phi ? (double *)(d + o_phi) : nullptr;
-    a.tr_K = tr_K ? (int32_t *)(d + o_K) : nullptr;
+    a.recs_in = recs_in; a.recs_out = recs_out; a.tr_accept = d_tr_accept; a.tr_phi = d_tr_phi; a.tr_K = d_tr_K;
     a.seed = ch->seed; a.chain_id0 = ch->chain_id0;
     a.hist_cap = ch->hist_cap; a.n_hist = ch->d_n_hist; a.model_num = ch->d_model_num;
     a.hist_K = ch->d_hist_K; a.hist_cells = ch->d_hist_cells; a.hist_phi = ch->d_hist_phi; a.hist_ptS = ch->d_hist_ptS;
     a.hist_iter = ch->d_hist_iter; a.hist_action = ch->d_hist_action; a.hist_accept = ch->d_hist_accept; a.hist_next = ch->d_hist_next;
-
-    TG_CUDA(cudaEventRecord(ch->ev0, s));
     if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
         if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
         else tg::tg_sampler_kernel<uint32_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
@@ -450,6 +509,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         else tg::tg_sampler_kernel<uint32_t, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
     }
     TG_CUDA(cudaGetLastError());
+    }
     TG_CUDA(cudaEventRecord(ch->ev1, s));
     ch->iter_done += nIter;
     if (mode == 0 && recs) TG_CUDA(cudaMemcpyAsync(recs, d + o_rec, sizeof(tonga_proposal) * N, cudaMemcpyDeviceToHost, s));
@@ -510,7 +570,14 @@ extern "C" int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K
         for (size_t i = 0; i < n; i++)
             for (size_t rs = 0; rs < R; rs++) ptS[i * R + (size_t)ctx->h_ray_orig[rs]] = ht[i * Rp + rs];
     }
-    if (owners) {
+    if (owners && ch->wide) {  // no resident owner state: one forward model of the current models (caller's point order)
+        int rc = tg::ensure_scratch(ctx, 4 * n * P);
+        if (rc != TONGA_OK) return rc;
+        rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, nullptr, (int32_t *)ctx->d_scratch, nullptr, nullptr, true);
+        if (rc != TONGA_OK) return rc;
+        TG_CUDA(cudaMemcpyAsync(owners, ctx->d_scratch, 4 * n * P, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else if (owners) {
         std::vector<uint8_t> ho(n * Pp);
         TG_CUDA(cudaMemcpy(ho.data(), ch->d_owner, n * Pp, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++)
@@ -571,12 +638,12 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp, ch->d_dcache_tmp);
+    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp, ch->d_dcache_tmp, true);
     if (rc != TONGA_OK) return rc;
     TG_CUDA(cudaMemsetAsync(ch->d_mism, 0, 8, s));
     TG_CUDA(cudaMemsetAsync(ch->d_maxd, 0, 16, s));
     dim3 grid(8, ch->n);
-    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
+    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ch->wide ? 0 : ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
                                               ch->d_phi, ch->d_phi_tmp, ch->d_dcache, ch->d_dcache_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
     unsigned long long mm = 0;
@@ -630,6 +697,8 @@ extern "C" int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const doub
 }
 
 extern "C" int tonga_chains_kcap(const tonga_chains *ch) { return ch ? ch->KC : 0; }
+
+extern "C" int tonga_chains_sampler(const tonga_chains *ch) { return !ch ? 0 : (ch->wide ? TONGA_SAMPLER_WIDE : TONGA_SAMPLER_RESIDENT); }
 
 extern "C" int tonga_chains_device_ptrs(tonga_chains *ch, void **n_hist, void **hist_K, void **hist_cells, void **hist_phi,
                                         void **hist_ptS, void **state_K, void **state_cells, void **state_phi) {

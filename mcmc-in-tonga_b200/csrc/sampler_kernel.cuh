@@ -11,6 +11,7 @@
 #pragma once
 #include <type_traits>
 
+#include "proposal.cuh"
 #include "tonga_internal.cuh"
 
 namespace tg {
@@ -56,14 +57,6 @@ struct SamplerArgs {
     int32_t *hist_action, *hist_accept, *hist_next;
 };
 
-struct Prop {  // proposal of the current iteration, broadcast through shared memory
-    int action, idx, do_eval, accept;
-    double x, y, z, zeta, u;
-    double aux;            // birth: czeta (:81); death: zetanew (:146)
-    double ox, oy, oz;     // move: the old position (the nucleus array holds the proposed one during B..E)
-    double ztag;           // zeta of the implicit new owner of tagged bytes (birth: zetanew; move: zeta[idx])
-};
-
 constexpr int SQ_CAP = 64;  // orphan queue entries per warp
 
 struct SmemLayout {
@@ -100,41 +93,9 @@ __device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s2u(src)), "r"(bytes) : "memory");
 }
 
-// ---- warp-cooperative v_nearest (MCsub.jl:247-263) over the nuclei in shared memory, skipping index `skip` ---------
-__device__ __noinline__ int warp_nearest(const double *nx, const double *ny, const double *nz, int K, int skip, double x,
-                                         double y, double z, int lane) {
-    double best = 1e9;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < K; i += 32) {
-        if (i == skip) continue;
-        const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);
-        if (d < best) { best = d; bi = i; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
-    }
-    return bi == 0x7fffffff ? -1 : bi;
-}
-
-__device__ __forceinline__ double jl_min1(double a) {  // min([1 a]...) in Julia: NaN propagates
-    return (a != a) ? a : (a < 1.0 ? a : 1.0);
-}
-
 __device__ __forceinline__ void mark_dirty(uint32_t *dirty, const int32_t *__restrict__ rayid, int p) {
     const int r = rayid[p];
     atomicOr(&dirty[r >> 5], 1u << (r & 31));
-}
-
-// Box-Muller pair from two uniforms in [0,1)
-__device__ __noinline__ void normal_pair(double u1, double u2, double &n0, double &n1) {
-    const double rr = sqrt(-2.0 * log(u1 + 0x1.0p-54));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    n0 = rr * cs;
-    n1 = rr * sn;
 }
 
 // FP32 screening of the orphan rescan: best and second-best squared distance over the fl32 nuclei (4 per step; unused
@@ -248,9 +209,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     int pending_slot = a.pending_slot[chain];
 
     const tonga_params &pm = a.prm;
-    // TD_inversion_function.jl:22-23,30-32
-    const double sig_zeta = pm.zeta_scale * pm.sig / 100;
-    const double PI = 3.141592653589793;
+    const double sig_zeta = pm.zeta_scale * pm.sig / 100;  // TD_inversion_function.jl:22
     const unsigned long long gid = (unsigned long long)(a.chain_id0 + chain);
 
     long long pt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -264,115 +223,17 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         // ================================================================ A: proposal (warp 0, warp-uniform values)
         if (vwarp == 0) {
             Prop pr;
-            pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
-            pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
-            double uu[8];
-            if (a.mode == 0) {
-                const Philox philox{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-                uint32_t w[4] = {0, 0, 0, 0};
-                if (lane < 4) philox((uint32_t)iter, (uint32_t)((unsigned long long)iter >> 32), (uint32_t)gid, (uint32_t)lane | ((uint32_t)(gid >> 32) << 8), w);
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
-                    const uint32_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
-                    uu[2 * s] = u53(w0, w1);
-                    uu[2 * s + 1] = u53(w2, w3);
-                }
-                const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
-                const int act0 = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
-                pr.action = act0 > nact ? nact : act0;
-            } else {
-                const tonga_proposal rec = a.recs_in[(size_t)chain * a.nIter + it];
-                pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
-            }
+            const int valid = draw_proposal<0>(pr, a.mode, a.mode == 1 ? a.recs_in + (size_t)chain * a.nIter + it : nullptr, a.seed, iter, gid, s_nx, s_ny,
+                                            s_nz, s_zeta, K, noise, pm, sig_zeta, lane);
             const int act = pr.action;
-            int valid = 0;
-            if (act == 1) {  // ---- birth :76-125
-                if (K < pm.max_cells) {
-                    if (a.mode == 0) {
-                        pr.x = uu[2] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
-                        pr.y = uu[3] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
-                        pr.z = uu[4] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
-                    }
-                    const int ci = warp_nearest(s_nx, s_ny, s_nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
-                    const double czeta = ci < 0 ? 0.0 : s_zeta[ci];
-                    pr.aux = czeta;
-                    if (a.mode == 0) {
-                        double n0, n1;
-                        normal_pair(uu[5], uu[6], n0, n1);
-                        pr.zeta = czeta + sig_zeta * n0;  // :82
-                        pr.u = uu[7];                     // :121
-                    }
-                    if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
-                    else if (pm.prior == 2) valid = 1;
-                    else valid = (pr.zeta > 0);  // :111
+            if (valid && act == 2 && lane == 0) s_fx[pr.idx] = __int_as_float(0x7f800000);  // fl32 screening must not see the killed nucleus
+            if (valid && act == 4) {  // from here to the accept decision the nucleus array holds the PROPOSED position
+                __syncwarp();
+                if (lane == 0) {
+                    s_nx[pr.idx] = pr.x; s_ny[pr.idx] = pr.y; s_nz[pr.idx] = pr.z;
+                    s_fx[pr.idx] = (float)pr.x; s_fy[pr.idx] = (float)pr.y; s_fz[pr.idx] = (float)pr.z;
                 }
-            } else if (act == 2) {  // ---- death :126-181
-                if (K > pm.min_cells) {
-                    if (a.mode == 0) {
-                        const int k = (int)floor(uu[1] * K);  // :128
-                        pr.idx = k >= K ? K - 1 : k;
-                        pr.u = uu[7];  // :176
-                    }
-                    const int kill = pr.idx;
-                    if (kill >= 0 && kill < K) {
-                        const int zi = warp_nearest(s_nx, s_ny, s_nz, K, kill, s_nx[kill], s_ny[kill], s_nz[kill], lane);  // :146
-                        pr.aux = zi < 0 ? 0.0 : s_zeta[zi];
-                        valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
-                        if (valid && lane == 0) s_fx[kill] = __int_as_float(0x7f800000);  // fl32 screening must not see the killed nucleus
-                    }
-                }
-            } else if (act == 3) {  // ---- change :183-218
-                if (a.mode == 0) {
-                    const int k = (int)floor(uu[1] * K);  // :184
-                    pr.idx = k >= K ? K - 1 : k;
-                    double n0, n1;
-                    normal_pair(uu[2], uu[3], n0, n1);
-                    pr.zeta = s_zeta[pr.idx] + sig_zeta * n0;  // :188
-                    pr.u = uu[7];                              // :214
-                }
-                if (pr.idx >= 0 && pr.idx < K) {
-                    if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
-                    else if (pm.prior == 2) valid = 1;
-                    else valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
-                    // the reference evaluates first (:191) but discards the result when invalid
-                }
-            } else if (act == 4) {  // ---- move :220-251
-                if (K > 0) {
-                    if (a.mode == 0) {
-                        const int k = (int)floor(uu[1] * K);  // :222
-                        pr.idx = k >= K ? K - 1 : k;
-                        double n0, n1, n2, n3;
-                        normal_pair(uu[2], uu[3], n0, n1);
-                        normal_pair(uu[4], uu[5], n2, n3);
-                        pr.x = s_nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
-                        pr.y = s_ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
-                        pr.z = s_nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
-                        pr.u = uu[7];                                                        // :247
-                    }
-                    if (pr.idx >= 0 && pr.idx < K) {
-                        valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
-                                 pr.z <= pm.zmax);  // :230-232
-                        if (valid) {  // from here to the accept decision the nucleus array holds the PROPOSED position
-                            pr.ox = s_nx[pr.idx]; pr.oy = s_ny[pr.idx]; pr.oz = s_nz[pr.idx];
-                            __syncwarp();
-                            if (lane == 0) {
-                                s_nx[pr.idx] = pr.x; s_ny[pr.idx] = pr.y; s_nz[pr.idx] = pr.z;
-                                s_fx[pr.idx] = (float)pr.x; s_fy[pr.idx] = (float)pr.y; s_fz[pr.idx] = (float)pr.z;
-                            }
-                        }
-                    }
-                }
-            } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
-                if (a.mode == 0) {
-                    double n0, n1;
-                    normal_pair(uu[2], uu[3], n0, n1);
-                    pr.zeta = noise + (pm.max_sig * pm.sig / 100) * n0;  // :23,:254
-                    pr.u = uu[7];
-                }
-                valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
             }
-            pr.do_eval = valid;
             // zlut: owner byte -> zeta under the proposed model (bit 7 set = switches to the implicit new owner)
             if (valid && act != 5) {
                 pr.ztag = (act == 1) ? pr.zeta : (act == 4 ? s_zeta[pr.idx] : 0.0);
@@ -592,47 +453,10 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 const double t = ((s_dirty[r >> 5] >> (r & 31)) & 1u) ? s_tnew[r] : s_tstar[r];
                 return misfit_term(t, a.tS[r], a.sig[r], nz);
             });
+            if (pm.debug_prior) phin = 1.0;  // MCsub.jl:128-136: the chain samples the prior
             // ============================================================ E: acceptance (one thread of the leader warp)
-            if (vtid == 0) {
-                const double K0 = (double)K;
-                const double zn = s_prop->zeta, aux = s_prop->aux, u = s_prop->u;
-                const double dphi2 = beta * ((phin - phi) / 2);
-                double alpha = 0.0;
-                int acc = 0;
-                if (act == 1) {
-                    const double g = ((aux - zn) * (aux - zn)) / (2 * (sig_zeta * sig_zeta));
-                    if (pm.prior == 1)  // :96-97
-                        alpha = ((K0) / (K0 + 1)) * ((sig_zeta * sqrt(2 * PI)) / (pm.zeta_scale)) * exp(g - dphi2);
-                    else if (pm.prior == 2)  // :107-108
-                        alpha = ((K0) / (K0 + 1)) * (sig_zeta / pm.zeta_scale) * exp(-(zn * zn) / (pm.zeta_scale * pm.zeta_scale) + g - dphi2);
-                    else  // :113-114
-                        alpha = ((K0) / (K0 + 1)) * (sqrt(2 * PI) * sig_zeta / pm.zeta_scale) * exp(-zn / pm.zeta_scale + g - dphi2);
-                    acc = (u < jl_min1(alpha));
-                } else if (act == 2) {
-                    const double zk = s_zeta[pidx];
-                    const double g = ((zk - aux) * (zk - aux)) / (2 * (sig_zeta * sig_zeta));
-                    if (pm.prior == 1)  // :151-152
-                        alpha = ((K0) / (K0 - 1)) * ((pm.zeta_scale) / (sig_zeta * sqrt(2 * PI))) * exp(-g - dphi2);
-                    else if (pm.prior == 2)  // :160-162
-                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / sig_zeta) * exp((zk * zk) / (2 * (pm.zeta_scale * pm.zeta_scale)) - g - dphi2);
-                    else  // :166-168
-                        alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / (sqrt(2 * PI) * sig_zeta)) * exp(zk / pm.zeta_scale - g - dphi2);
-                    acc = (u < jl_min1(alpha));
-                } else if (act == 3) {
-                    const double zo = s_zeta[pidx];
-                    if (pm.prior == 1) alpha = exp(-dphi2);  // :196
-                    else if (pm.prior == 2) alpha = exp((zo * zo - zn * zn) / (2 * (pm.zeta_scale * pm.zeta_scale)) - dphi2);  // :202-203
-                    else alpha = exp((zo - zn) / pm.zeta_scale - dphi2);  // :207-208
-                    acc = (u < jl_min1(alpha));
-                } else if (act == 4) {
-                    acc = (u < jl_min1(exp(-dphi2)));  // :241-242
-                } else {  // sigma: log form :264-267
-                    double la = beta * (log(noise / zn) * (double)R) - dphi2;  // beta = 1: TD_inversion_function.jl:264
-                    la = (la != la) ? la : (la < 0.0 ? la : 0.0);
-                    acc = (log(u) <= la);
-                }
-                s_prop->accept = acc;
-            }
+            if (vtid == 0)
+                s_prop->accept = accept_decision(*s_prop, K, phi, phin, (act == 2 || act == 3) ? s_zeta[pidx] : 0.0, noise, beta, R, pm, sig_zeta);
             __syncthreads();
             tick(3);
             accepted = s_prop->accept;

@@ -602,11 +602,207 @@ def test_abi_error_paths_and_helpers(tonga):
     p = copy.copy(p0); p.max_cells = 127
     ctx2 = api.Context(ds, p)
     with pytest.raises(_lib.TongaError) as e:
-        api.Chains(ctx2, 1)
+        api.Chains(ctx2, 1, sampler="resident")
     assert e.value.code == -3 and "126" in str(e.value)
+    chw = api.Chains(ctx2, 1)  # auto -> the wide sampler
+    assert chw.sampler == "wide"
+    with pytest.raises(_lib.TongaError) as e:
+        chw.profile(True)
+    assert e.value.code == -4
+    chw.close()
     # interp_style 2 is broken in the reference (MCsub.jl:332) -> refused
     p = copy.copy(p0); p.interp_style = 2
     with pytest.raises(_lib.TongaError) as e:
         api.Context(ds, p)
     assert e.value.code == -1
     ctx.close(); ctx2.close()
+
+
+# ------------------------------------------------------------------------------------------------ wide sampler
+def _check_replay(ch, out, runs, od, hist_n=None):
+    st = ch.state(want_owners=False)
+    hist = ch.history()
+    for c, (r, mb) in enumerate(runs):
+        assert np.array_equal(out["accept"][c], r.accept), f"accept/reject sequence differs (chain {c})"
+        assert np.array_equal(out["K"][c], r.K)
+        assert _close(out["phi"][c], r.phi)
+        k = mb.K
+        assert st["K"][c] == k
+        for a, ref in enumerate(mb.cells()):
+            assert np.array_equal(st["cells"][c, a, :k], ref), "final nuclei must be bit-identical"
+        assert _close(st["ptS"][c], mb.ptS[:od.R])
+        if hist_n is not None:
+            assert hist["n_hist"][c] == r.n_hist == hist_n
+            assert np.array_equal(hist["K"][c, :r.n_hist], r.hist_K[:r.n_hist])
+            assert np.array_equal(hist["action"][c, :r.n_hist], r.hist_action[:r.n_hist])
+            assert np.array_equal(hist["accept"][c, :r.n_hist], r.hist_accept[:r.n_hist])
+            assert _close(hist["phi"][c, :r.n_hist], r.hist_phi[:r.n_hist])
+            for j in range(r.n_hist):
+                kj = r.hist_K[j]
+                assert np.array_equal(hist["cells"][c, j, :, :kj], r.hist_cells[j, :, :kj])
+            assert _close(hist["ptS"][c, :r.n_hist], r.hist_ptS[:r.n_hist])
+
+
+@pytest.mark.parametrize("prior", [1, 2, 3])
+def test_wide_sampler_replays_oracle_stream(tonga, prior):
+    """The wide sampler (full forward model per proposal, no shared-memory chain state) against the oracle's chain."""
+    import copy
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.prior = prior
+    p.n_iter, p.burn_in, p.keep_each = 300.0, 100.0, 10.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(51 + prior)
+    n, n_iter = 5, 300
+    models = _start_models(rng, n, ds)
+    runs = [_oracle_generate(op, od, models[c], n_iter, 2000 + c, hist_cap=64) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n, hist_cap=64, sampler="wide")
+    assert ch.sampler == "wide"
+    K, cells = pack_models(models, Kcap=ch.KC)
+    ch.set_models(K, cells)
+    out = ch.run(n_iter, recs=recs, trace=True)
+    _check_replay(ch, out, runs, od, hist_n=20)
+    assert ch.verify() == (0, 0.0, 0.0)
+    own = ch.state(want_owners=True)["owners"]
+    assert own.shape == (n, ctx.P) and own.min() >= 0 and (own.max(1) < ch.state()["K"]).all()
+    ch.close(); ctx.close()
+
+
+def test_wide_sampler_equals_resident_sampler(tonga):
+    """Same seed, same global chain ids: the two samplers give bit-identical chains (proposals, decisions, phi, history)."""
+    import copy
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 500.0, 200.0, 10.0
+    ctx = Context(ds, p)
+    res = {}
+    for kind in ("resident", "wide"):
+        ch = Chains(ctx, 12, chain_id0=5, seed=99, sampler=kind)
+        ch.build_starting()
+        out = ch.run(250, record=True, trace=True)
+        out2 = ch.run(250, record=True, trace=True)  # a second call continues the same streams
+        res[kind] = (out, out2, ch.state(), ch.history(), ch.stats())
+        ch.close()
+    (a1, a2, sa, ha, ta), (b1, b2, sb, hb, tb) = res["resident"], res["wide"]
+    for x, y in ((a1, b1), (a2, b2)):
+        assert x["recs"].tobytes() == y["recs"].tobytes()
+        assert np.array_equal(x["accept"], y["accept"]) and np.array_equal(x["K"], y["K"])
+        assert x["phi"].tobytes() == y["phi"].tobytes(), "phi must be bit-identical (same canonical summation orders)"
+    assert np.array_equal(sa["K"], sb["K"]) and sa["phi"].tobytes() == sb["phi"].tobytes() and sa["ptS"].tobytes() == sb["ptS"].tobytes()
+    for c in range(12):
+        k = sa["K"][c]
+        assert np.array_equal(sa["cells"][c, :, :k], sb["cells"][c, :, :k])
+    assert np.array_equal(ha["n_hist"], hb["n_hist"]) and (ha["n_hist"] == 30).all()
+    for key in ("K", "iter", "action", "accept", "next_action"):
+        assert np.array_equal(ha[key], hb[key]), key
+    assert ha["phi"].tobytes() == hb["phi"].tobytes() and ha["ptS"].tobytes() == hb["ptS"].tobytes()
+    assert ta[0] == tb[0] and np.array_equal(ta[1], tb[1])
+    ctx.close()
+
+
+def test_wide_sampler_beyond_126_cells(tonga):
+    """max_cells = 400 (the resident sampler stops at 126): auto selects the wide sampler; replay of the oracle's chain."""
+    import copy
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.max_cells, p.min_cells = 400, 150
+    p.n_iter, p.burn_in, p.keep_each = 200.0, 100.0, 20.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(77)
+    n, n_iter = 3, 200
+    models = _start_models(rng, n, ds, kmin=150, kmax=400)  # includes births refused at max_cells / deaths at min_cells
+    models[0] = random_model(rng, 400, box_of(ds))
+    models[1] = random_model(rng, 150, box_of(ds))
+    runs = [_oracle_generate(op, od, models[c], n_iter, 3000 + c, hist_cap=16) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n, hist_cap=16)
+    assert ch.sampler == "wide" and ch.KC == 400
+    K, cells = pack_models(models, Kcap=ch.KC)
+    ch.set_models(K, cells)
+    out = ch.run(n_iter, recs=recs, trace=True)
+    _check_replay(ch, out, runs, od, hist_n=5)
+    assert ch.verify() == (0, 0.0, 0.0)
+    ch.close(); ctx.close()
+
+
+def test_wide_sampler_large_ray_set():
+    """A ray set too large for shared memory (config-3 shape scaled down: 2000 rays, ~4e5 points, up to 300 nuclei)."""
+    import oracle as O
+    from tonga_b200.api import Chains, Context, pack_models
+    from tonga_b200.data import synthetic_rays
+    from tonga_b200.structs import parameters
+    p = parameters()
+    p.max_cells, p.min_cells = 300, 5
+    p.n_iter, p.burn_in, p.keep_each = 40.0, 20.0, 10.0
+    ds = synthetic_rays(2000, seed=5, p=p)
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(8)
+    n, n_iter = 2, 40
+    models = [random_model(rng, k, box_of(ds)) for k in (40, 250)]
+    runs = [_oracle_generate(op, od, models[c], n_iter, 4000 + c, hist_cap=8) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n, hist_cap=8)
+    assert ch.sampler == "wide"
+    K, cells = pack_models(models, Kcap=ch.KC)
+    ch.set_models(K, cells)
+    out = ch.run(n_iter, recs=recs, trace=True)
+    _check_replay(ch, out, runs, od, hist_n=2)
+    assert ch.verify() == (0, 0.0, 0.0)
+    ch.close(); ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["resident", "wide"])
+def test_debug_prior_chains(tonga, kind):
+    """debug_prior = 1 (MCsub.jl:128-136, phi == 1): both samplers follow the oracle's prior-sampling chain; hierarchical
+    noise (action 5, extension) rides along."""
+    import copy
+    from tonga_b200.api import Chains, Context, pack_models
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.debug_prior = 1
+    p.n_iter, p.burn_in, p.keep_each = 400.0, 100.0, 10.0
+    ctx = Context(ds, p)
+    op, od = _orc(ds, p)
+    rng = np.random.default_rng(91)
+    n, n_iter = 4, 400
+    models = _start_models(rng, n, ds)
+    runs = [_oracle_generate(op, od, models[c], n_iter, 5000 + c) for c in range(n)]
+    recs = np.stack([r.recs for r, _ in runs])
+    ch = Chains(ctx, n, hist_cap=0, sampler=kind)
+    K, cells = pack_models(models, Kcap=ch.KC)
+    ch.set_models(K, cells)
+    out = ch.run(n_iter, recs=recs, trace=True)
+    for c, (r, mb) in enumerate(runs):
+        assert np.array_equal(out["accept"][c], r.accept) and np.array_equal(out["K"][c], r.K)
+        assert (out["phi"][c] == 1.0).all() and (r.phi == 1.0).all()
+        k = mb.K
+        for a, ref in enumerate(mb.cells()):
+            assert np.array_equal(ch.state()["cells"][c, a, :k], ref)
+    ch.close(); ctx.close()
+
+
+def test_wide_sampler_sigma_move(tonga):
+    """n_actions = 5 (hierarchical noise, extension): wide == resident bit for bit in generate mode."""
+    import copy
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    ctx = Context(ds, p, n_actions=5)
+    res = {}
+    for kind in ("resident", "wide"):
+        ch = Chains(ctx, 6, seed=3, hist_cap=0, sampler=kind)
+        ch.build_starting()
+        res[kind] = (ch.run(300, record=True, trace=True), ch.state())
+        ch.close()
+    (a, sa), (b, sb) = res["resident"], res["wide"]
+    assert (a["recs"]["action"] == 5).any()
+    assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"])
+    assert a["phi"].tobytes() == b["phi"].tobytes() and sa["noise"].tobytes() == sb["noise"].tobytes()
+    ctx.close()
