@@ -121,13 +121,18 @@ int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int
  *   WIDE      no per-point chain state: every proposal runs the full batched forward model (as the reference does,
  *             MCsub.jl:123-185) on the candidate models of all chains; any ray set and max_cells up to ~5000
  *             (BASELINE.json config 3: 100k rays, 2000 nuclei).  At most 65535 chains per batch.
- * AUTO = RESIDENT when it fits, else WIDE; tonga_chains_create is create_ex(AUTO). */
+ *   STREAMED  per-point chain state (u16 nucleus index + fl32 squared distance per ray point, 6 B) in HBM, updated
+ *             incrementally: every proposal is one streaming pass over the points (18 B per point) plus a second one when it
+ *             is accepted, instead of the O(points x cells) forward model.  max_cells <= 65534; memory 6 B x points x chains.
+ * AUTO = RESIDENT when it fits, else STREAMED when its state fits in device memory, else WIDE; tonga_chains_create is
+ * create_ex(AUTO). */
 #define TONGA_SAMPLER_AUTO 0
 #define TONGA_SAMPLER_RESIDENT 1
 #define TONGA_SAMPLER_WIDE 2
+#define TONGA_SAMPLER_STREAMED 3
 int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                            int32_t hist_cap, int32_t sampler);
-/* TONGA_SAMPLER_RESIDENT or TONGA_SAMPLER_WIDE (0 for NULL) */
+/* TONGA_SAMPLER_RESIDENT, _WIDE or _STREAMED (0 for NULL) */
 int tonga_chains_sampler(const tonga_chains *ch);
 void tonga_chains_destroy(tonga_chains *ch);
 

@@ -51,7 +51,8 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, float tol_alpha,
                float tol_beta2, int exact_only, const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
                const int32_t *__restrict__ point_orig, int R, int ldT, int64_t P, int64_t Ppad, int tile_pts,
-               double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32) {
+               double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32,
+               uint16_t *__restrict__ owners16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int model = blockIdx.y;
     const Tile tile = tiles[blockIdx.x];
@@ -159,6 +160,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                 const int64_t p = tile.p0 + j;
                 if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi[q];  // caller's flat order
                 if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
+                if (owners16) owners16[(size_t)model * Ppad + p] = s_owner[j];  // streamed sampler's chain state
                 if (dmin32) dmin32[(size_t)model * Ppad + p] = bi[q] < 0 ? 1e9f : dbest[q];  // owner distance cache of the sampler
             }
         }
@@ -201,7 +203,7 @@ tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, co
 }
 
 int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
-                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev, bool force_geometry) {
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev, bool force_geometry, uint16_t *owners16_dev) {
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
@@ -213,7 +215,7 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
                                                                   ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->tol_alpha, ctx->tol_beta2,
                                                                   ctx->exact_only, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
-                                                                  owners32_dev, owners8_dev, dmin32_dev);
+                                                                  owners32_dev, owners8_dev, dmin32_dev, owners16_dev);
         TG_CUDA(cudaGetLastError());
     }
     if (owners8_dev && ctx->Ppad > ctx->P) {

@@ -80,7 +80,7 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
 }
 
 __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
-                                 const uint8_t *own_b, const double *ts_a /* [n][Rp] sorted rays */,
+                                 const uint8_t *own_b, const uint16_t *own16_a, const uint16_t *own16_b, const double *ts_a /* [n][Rp] sorted rays */,
                                  const double *ts_b /* [n][R] caller's ray order */, const double *phi_a, const double *phi_b,
                                  const float *dc_a, const float *dc_b, float tol_alpha, float tol_beta2,
                                  unsigned long long *mism, double *maxd /* [2] as ordered uint64 bits */) {
@@ -88,7 +88,8 @@ __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, 
     unsigned long long local = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
     {
-        local += own_a[(size_t)chain * Ppad + p] != own_b[(size_t)chain * Ppad + p];
+        if (own16_a) local += own16_a[(size_t)chain * Ppad + p] != own16_b[(size_t)chain * Ppad + p];  // streamed sampler
+        else local += own_a[(size_t)chain * Ppad + p] != own_b[(size_t)chain * Ppad + p];
         // the sampler's fl32 owner-distance cache must stay within a few ulp of the freshly computed distance
         const float ca = dc_a[(size_t)chain * Ppad + p], cb = dc_b[(size_t)chain * Ppad + p];
         local += !(ca < 0.0f || fabsf(ca - cb) <= tol_alpha * (ca + cb) + tol_beta2);  // stale marker, or inside the screening's error band
@@ -176,7 +177,8 @@ struct tonga_chains {
     unsigned long long seed = 0;
     long long iter_done = 0;
     bool have_models = false;
-    bool wide = false;  // wide sampler (wide_kernels.cuh): no per-point chain state, a full forward model per proposal
+    bool wide = false;      // wide or streamed sampler (wide_kernels.cuh): lock-step launches per iteration, candidate models in global memory
+    bool streamed = false;  // streamed sampler: per-point chain state (u16 owner, fl32 owner distance) in HBM, updated incrementally
     int exact_only = 0;
     long long *d_prof = nullptr;  // optional per-phase cycle counters (tonga_chains_profile)
     size_t smem = 0;
@@ -197,6 +199,11 @@ struct tonga_chains {
     int32_t *d_Kc = nullptr;
     double *d_cells_c = nullptr;
     tg::Prop *d_props = nullptr;
+    // streamed sampler
+    uint16_t *d_owner16 = nullptr;  // [n][Ppad]
+    double *d_tstar_c = nullptr;    // [n][Rp]
+    int32_t *d_accept = nullptr;    // [n]
+    size_t stream_smem = 0;
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
@@ -219,7 +226,7 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
 
 extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                                       int32_t hist_cap, int32_t sampler) {
-    if (!ctx || !out || nChains < 1 || hist_cap < 0 || sampler < TONGA_SAMPLER_AUTO || sampler > TONGA_SAMPLER_WIDE)
+    if (!ctx || !out || nChains < 1 || hist_cap < 0 || sampler < TONGA_SAMPLER_AUTO || sampler > TONGA_SAMPLER_STREAMED)
         return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: bad argument");
     *out = nullptr;
     const tonga_params &pm = ctx->prm;
@@ -235,10 +242,21 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(smem_res) +
                                                 " B) exceeds shared memory; the smem-resident sampler handles ray sets up to ~200k points");
     }
-    const bool wide = (sampler == TONGA_SAMPLER_WIDE) || !fits;
-    if (wide && nChains > 65535) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the wide sampler runs at most 65535 chains per batch");
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
+    // streamed sampler: 6 B per ray point and chain of state; AUTO uses it when that fits in 60 % of the free memory
+    const size_t stream_smem = (size_t)ctx->tile_pts * 4 + (size_t)ctx->tile_pts / 8 + 16 + 12 * (size_t)KC0;
+    const bool stream_ok = pm.max_cells <= 65534 && stream_smem <= ctx->smem_optin;
+    if (sampler == TONGA_SAMPLER_STREAMED && !stream_ok)
+        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the streamed sampler needs max_cells <= 65534 and its tile state in shared memory");
+    bool streamed = sampler == TONGA_SAMPLER_STREAMED;
+    if (sampler == TONGA_SAMPLER_AUTO && !fits && stream_ok) {
+        size_t fr = 0, tot = 0;
+        TG_CUDA(cudaMemGetInfo(&fr, &tot));
+        streamed = (double)nChains * 6.0 * (double)ctx->Ppad < 0.6 * (double)fr;
+    }
+    const bool wide = streamed || (sampler == TONGA_SAMPLER_WIDE) || !fits;
+    if (wide && nChains > 65535) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the wide / streamed samplers run at most 65535 chains per batch");
     tonga_chains *ch = new tonga_chains();
     struct Guard {  // frees a half-built batch when an allocation below fails (TG_ALLOC / TG_CUDA return early)
         tonga_chains *&c;
@@ -253,6 +271,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->chain_id0 = chain_id0;
     ch->seed = seed;
     ch->wide = wide;
+    ch->streamed = streamed;
+    ch->stream_smem = stream_smem;
     ch->smem = wide ? 0 : smem_res;
     const size_t n = (size_t)nChains, KC = (size_t)ch->KC, R = (size_t)ctx->R, Rp = (size_t)ch->Rp, Pp = (size_t)ctx->Ppad, H = (size_t)hist_cap;
     TG_ALLOC(ch->d_K, 4 * n);
@@ -271,6 +291,18 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_ALLOC(ch->d_cells_c, 8 * n * 4 * KC);
         TG_ALLOC(ch->d_props, sizeof(tg::Prop) * n);
         TG_CUDA(cudaMemsetAsync(ch->d_cells_c, 0, 8 * n * 4 * KC, ctx->stream));
+    }
+    if (streamed) {
+        TG_ALLOC(ch->d_owner16, 2 * n * Pp);
+        TG_ALLOC(ch->d_dcache, 4 * n * Pp);
+        TG_ALLOC(ch->d_tstar_c, 8 * n * Rp);
+        TG_ALLOC(ch->d_accept, 4 * n);
+        TG_CUDA(cudaMemsetAsync(ch->d_owner16, 0xFF, 2 * n * Pp, ctx->stream));  // the padded tail stays "none"
+        TG_CUDA(cudaMemsetAsync(ch->d_accept, 0, 4 * n, ctx->stream));
+        if (stream_smem > 48 * 1024) {
+            TG_CUDA(cudaFuncSetAttribute(tg::tg_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+            TG_CUDA(cudaFuncSetAttribute(tg::tg_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+        }
     }
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
@@ -341,7 +373,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props};
+                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept};
     for (void *p : ptrs) cudaFree(p);
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
@@ -353,7 +385,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
 static int establish_state(tonga_chains *ch) {
     tonga_ctx *ctx = ch->ctx;
     int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi, nullptr, ch->d_owner, ch->d_dcache,
-                                 /*force_geometry=*/true);  // debug_prior: phi = 1 but the chain state (owners, t*) is still well defined
+                                 /*force_geometry=*/true, ch->d_owner16);  // debug_prior: phi = 1 but the chain state (owners, t*) is still well defined
     if (rc != TONGA_OK) return rc;
     const size_t tot = (size_t)ch->n * ch->Rp;
     tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_ptS_tmp, ch->d_tstar);
@@ -471,16 +503,27 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         w.n_hist = ch->d_n_hist; w.model_num = ch->d_model_num; w.hist_K = ch->d_hist_K; w.hist_cells = ch->d_hist_cells;
         w.hist_phi = ch->d_hist_phi; w.hist_ptS = ch->d_hist_ptS; w.hist_iter = ch->d_hist_iter; w.hist_action = ch->d_hist_action;
         w.hist_accept = ch->d_hist_accept; w.hist_next = ch->d_hist_next;
+        w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept;
+        tg::StreamArgs sa{};
+        sa.tiles = ctx->d_tiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
+        sa.dtT = ctx->d_dtT; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
+        sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ctx->tile_pts;
+        sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
+        sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
+        const dim3 sgrid((unsigned)ctx->n_tiles, (unsigned)ch->n);
         const int saved_exact = ctx->exact_only;
         ctx->exact_only = ch->exact_only || saved_exact;
         for (int64_t it = 0; it < nIter; it++) {
             w.it = it; w.iter = ch->iter_done + 1 + it;
             tg::tg_wide_propose_kernel<<<ch->n, tg::WIDE_PROPOSE_THREADS, 0, s>>>(w);
-            if (!ctx->prm.debug_prior) {
+            if (ch->streamed) {
+                tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
+            } else if (!ctx->prm.debug_prior) {
                 rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_Kc, ch->d_cells_c, nullptr, ch->d_ptS_tmp, nullptr, nullptr, nullptr, nullptr);
                 if (rc != TONGA_OK) { ctx->exact_only = saved_exact; return rc; }
             }
             tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
+            if (ch->streamed) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
         }
         ctx->exact_only = saved_exact;
         TG_CUDA(cudaGetLastError());
@@ -570,7 +613,15 @@ extern "C" int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K
         for (size_t i = 0; i < n; i++)
             for (size_t rs = 0; rs < R; rs++) ptS[i * R + (size_t)ctx->h_ray_orig[rs]] = ht[i * Rp + rs];
     }
-    if (owners && ch->wide) {  // no resident owner state: one forward model of the current models (caller's point order)
+    if (owners && ch->streamed) {
+        std::vector<uint16_t> ho(n * Pp);
+        TG_CUDA(cudaMemcpy(ho.data(), ch->d_owner16, 2 * n * Pp, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++)
+            for (size_t p = 0; p < P; p++) {
+                const uint16_t o = ho[i * Pp + p];
+                owners[i * P + (size_t)ctx->h_point_orig[p]] = (o == 0xFFFFu) ? -1 : (int32_t)o;
+            }
+    } else if (owners && ch->wide) {  // no resident owner state: one forward model of the current models (caller's point order)
         int rc = tg::ensure_scratch(ctx, 4 * n * P);
         if (rc != TONGA_OK) return rc;
         rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, nullptr, (int32_t *)ctx->d_scratch, nullptr, nullptr, true);
@@ -638,13 +689,24 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp, ch->d_dcache_tmp, true);
+    const size_t nPp = (size_t)ch->n * (size_t)ctx->Ppad;
+    uint16_t *own16_tmp = nullptr;
+    float *dc_tmp = ch->d_dcache_tmp;
+    struct Tmp { void *a = nullptr, *b = nullptr; ~Tmp() { cudaFree(a); cudaFree(b); } } tmp;  // streamed: the reference copy lives only during verify
+    if (ch->streamed) {
+        TG_CUDA(cudaMalloc(&tmp.a, 2 * nPp));
+        TG_CUDA(cudaMalloc(&tmp.b, 4 * nPp));
+        own16_tmp = (uint16_t *)tmp.a;
+        dc_tmp = (float *)tmp.b;
+    }
+    int rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_K, ch->d_cells, ch->d_noise, ch->d_ptS_tmp, ch->d_phi_tmp, nullptr, ch->d_owner_tmp, dc_tmp, true, own16_tmp);
     if (rc != TONGA_OK) return rc;
     TG_CUDA(cudaMemsetAsync(ch->d_mism, 0, 8, s));
     TG_CUDA(cudaMemsetAsync(ch->d_maxd, 0, 16, s));
-    dim3 grid(8, ch->n);
-    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, ch->wide ? 0 : ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp, ch->d_tstar, ch->d_ptS_tmp,
-                                              ch->d_phi, ch->d_phi_tmp, ch->d_dcache, ch->d_dcache_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
+    dim3 grid(ch->streamed ? 64 : 8, ch->n);
+    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, (ch->wide && !ch->streamed) ? 0 : ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp,
+                                              ch->d_owner16, own16_tmp, ch->d_tstar, ch->d_ptS_tmp,
+                                              ch->d_phi, ch->d_phi_tmp, ch->d_dcache, dc_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
     unsigned long long mm = 0;
     double md[2] = {0, 0};
@@ -698,7 +760,7 @@ extern "C" int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const doub
 
 extern "C" int tonga_chains_kcap(const tonga_chains *ch) { return ch ? ch->KC : 0; }
 
-extern "C" int tonga_chains_sampler(const tonga_chains *ch) { return !ch ? 0 : (ch->wide ? TONGA_SAMPLER_WIDE : TONGA_SAMPLER_RESIDENT); }
+extern "C" int tonga_chains_sampler(const tonga_chains *ch) { return !ch ? 0 : (ch->streamed ? TONGA_SAMPLER_STREAMED : (ch->wide ? TONGA_SAMPLER_WIDE : TONGA_SAMPLER_RESIDENT)); }
 
 extern "C" int tonga_chains_device_ptrs(tonga_chains *ch, void **n_hist, void **hist_K, void **hist_cells, void **hist_phi,
                                         void **hist_ptS, void **state_K, void **state_cells, void **state_phi) {

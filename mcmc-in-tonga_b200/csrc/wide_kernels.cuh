@@ -33,6 +33,10 @@ struct WideArgs {
     double *cells_c;  // [n][4][KC]
     double *ptS_c;    // [n][R] caller's ray order (written by tg_eval_kernel)
     Prop *props;      // [n]
+    // streamed sampler: t* of the candidates in sorted ray order, accept flags for the commit pass
+    int streamed;
+    double *tstar_c;        // [n][Rp]
+    int32_t *accept_flag;   // [n]
     // streams / traces
     const tonga_proposal *recs_in;
     tonga_proposal *recs_out;
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
     const int act = s_prop.action, idx = s_prop.idx;
     const int Kn = (act == 1) ? K + 1 : (act == 2 ? K - 1 : K);
     // sigma move / prior sampling (debug_prior): t* does not change or is not needed -> no forward model
-    const bool geometry = s_prop.do_eval && act != 5 && !a.prm.debug_prior;
+    const bool geometry = s_prop.do_eval && act != 5 && (a.streamed || !a.prm.debug_prior);
     if (tid == 0) a.Kc[chain] = geometry ? Kn : -1;
     if (!s_prop.do_eval || act == 5) return;
     double *cand = a.cells_c + (size_t)chain * 4 * KC;
@@ -107,7 +111,8 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
     double phi = a.phi[chain], noise = a.noise[chain];
     const double beta = a.beta[chain];
     double *ts = a.tstar + (size_t)chain * a.Rp;
-    const double *tc = a.ptS_c + (size_t)chain * R;
+    const double *tc = a.ptS_c + (size_t)chain * R;        // wide: candidate t*, caller's ray order
+    const double *tsc = a.tstar_c + (size_t)chain * a.Rp;  // streamed: candidate t*, sorted ray order
     int accepted = 0;
     if (do_eval) {
         double phin;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
         } else {
             const double nz = (act == 5) ? pr.zeta : noise;
             phin = phi_canonical_128(R, tid, scratch, [&](int r) {
-                const double t = (act == 5) ? ts[r] : tc[a.ray_orig[r]];
+                const double t = (act == 5) ? ts[r] : (a.streamed ? tsc[r] : tc[a.ray_orig[r]]);
                 return misfit_term(t, a.tS[r], a.sig[r], nz);
             });
         }
@@ -129,7 +134,9 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 double *cur = a.cells + (size_t)chain * 4 * KC;
                 const double *cand = a.cells_c + (size_t)chain * 4 * KC;
                 for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) cur[i] = cand[i];
-                if (!pm.debug_prior)
+                if (a.streamed)
+                    for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tsc[r];
+                else if (!pm.debug_prior)
                     for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tc[a.ray_orig[r]];
             }
             phi = phin;
@@ -175,6 +182,184 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
         if (a.tr_K) a.tr_K[(size_t)chain * a.nIter + a.it] = K;
         a.K[chain] = K; a.phi[chain] = phi; a.noise[chain] = noise;
         a.n_hist[chain] = n_hist; a.model_num[chain] = model_num;
+        if (a.accept_flag) a.accept_flag[chain] = accepted;
+    }
+}
+
+// ================================================================================================ streamed sampler
+// Per-point chain state in HBM (u16 owner + fl32 squared distance to the owner per ray point), updated incrementally:
+// one pass over the points per proposal instead of the O(P K) forward model.  CTA = (tile of whole rays, chain).
+//   COMMIT = false  candidate pass: classify every point of the tile against the proposal (birth / move: fl32 distance
+//                   to the new position vs the cached owner distance, exact FP64 inside the error band; death / move:
+//                   points of the killed / moved nucleus are rescanned over the candidate model), re-integrate the rays that
+//                   hold a changed point (left to right, canonical order) and write t* of every ray of the tile to tstar_c.
+//                   Nothing of the chain state is modified.
+//   COMMIT = true   accepted chains only: the same classification again (deterministic), now written to owner / dcache;
+//                   a death also renumbers the owners above the killed index (deleteat!, TD_inversion_function.jl:132-135).
+// Algorithmic traffic of a pass: 18 B per point (3 x fl32 coordinates, fl32 owner distance, u16 owner).
+struct StreamArgs {
+    const Tile *tiles;
+    const float *pxf, *pyf, *pzf;
+    const double *px, *py, *pz, *dtT;
+    const int32_t *ray_off;
+    float tol_alpha, tol_beta2;
+    int exact_only, KC, Rp, ldT, tile_pts;
+    long long Ppad;
+    const Prop *props;
+    const int32_t *Kc;        // candidate nCells (-1: nothing to evaluate)
+    const double *cells_c;    // candidate models [n][4][KC]
+    uint16_t *owner;          // [n][Ppad]
+    float *dcache;            // [n][Ppad]
+    const double *tstar;      // [n][Rp]
+    double *tstar_c;          // [n][Rp]
+    const int32_t *accept_flag;
+};
+
+constexpr int STREAM_THREADS = 256;
+#define TG_NONE16S 0xFFFFu
+
+template <bool COMMIT>
+__global__ void __launch_bounds__(STREAM_THREADS) tg_stream_kernel(const StreamArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int chain = blockIdx.y, tid = threadIdx.x;
+    const Prop pr = a.props[chain];
+    const int act = pr.action;
+    if (!pr.do_eval || act == 5) return;
+    if (COMMIT && (!a.accept_flag[chain] || act == 3)) return;
+    const int Kn = a.Kc[chain];  // nuclei of the candidate model
+    const Tile tile = a.tiles[blockIdx.x];
+    const int npts = tile.p1 - tile.p0;
+    // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | orphan queue u16[tile_pts] | counter | fl32 nuclei [3][KC] (staged on demand)
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(smem_raw);
+    uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_owner + a.tile_pts);
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_chg + a.tile_pts / 32);
+    int *s_cnt = reinterpret_cast<int *>(s_queue + a.tile_pts);
+    float *s_fx = reinterpret_cast<float *>(s_cnt + 4);
+    float *s_fy = s_fx + a.KC, *s_fz = s_fy + a.KC;
+
+    const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
+    uint16_t *own = a.owner + (size_t)chain * a.Ppad;
+    float *dc = a.dcache + (size_t)chain * a.Ppad;
+    const int idx = pr.idx;
+    const double cx = pr.x, cy = pr.y, cz = pr.z;
+    const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
+    const int newo = (act == 1) ? Kn - 1 : idx;  // index a switched point takes: the appended nucleus / the moved one
+    const float ta = a.tol_alpha, tb = a.tol_beta2;
+
+    if (!COMMIT) for (int i = tid; i < a.tile_pts / 32; i += STREAM_THREADS) s_chg[i] = 0u;
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+
+    // ---- phase 1: one flat pass over the tile's points
+    for (int j = tid; j < npts; j += STREAM_THREADS) {
+        const long long p = tile.p0 + j;
+        const uint32_t o = own[p];
+        uint32_t no = o;  // owner under the candidate model (candidate numbering)
+        bool changed = false;
+        if (act == 1 || act == 4) {
+            if (act == 4 && (int)o == idx) {  // owned by the moved nucleus: full rescan below
+                s_queue[atomicAdd(s_cnt, 1)] = (uint16_t)j;
+            } else {
+                const float d_o = dc[p];
+                const float d_c = dist2_f32(cxf, cyf, czf, a.pxf[p], a.pyf[p], a.pzf[p]);
+                const float diff = d_c - d_o, tol = fmaf(ta, d_c + d_o, tb);
+                bool sw = diff < -tol;
+                if (a.exact_only || fabsf(diff) <= tol || diff != diff) {  // inside the error band: exact FP64, MCsub.jl:254-255
+                    const double x = a.px[p], y = a.py[p], z = a.pz[p];
+                    const double de_o = (o == TG_NONE16S) ? 1e9 : dist2_exact(cc[o], cc[a.KC + o], cc[2 * a.KC + o], x, y, z);
+                    const double de_c = dist2_exact(cx, cy, cz, x, y, z);
+                    // birth: the new nucleus has the highest index -> strict <.  move: index idx also wins exact ties against o > idx.
+                    sw = (de_c < de_o) || (act == 4 && de_c == de_o && idx < (int)o && o != TG_NONE16S);
+                }
+                if (sw) {
+                    no = (uint32_t)newo;
+                    changed = true;
+                    if (COMMIT) { own[p] = (uint16_t)no; dc[p] = d_c; }
+                }
+            }
+        } else if (act == 2) {
+            if ((int)o == idx) s_queue[atomicAdd(s_cnt, 1)] = (uint16_t)j;
+            else if (o != TG_NONE16S && (int)o > idx) {
+                no = o - 1;  // deleteat! renumbering
+                if (COMMIT) own[p] = (uint16_t)no;
+            }
+        } else {  // change: owners stay, the rays through the cell are re-integrated
+            changed = ((int)o == idx);
+        }
+        if (!COMMIT) {
+            s_owner[j] = (uint16_t)no;
+            if (changed) atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+        }
+    }
+    __syncthreads();
+    // ---- orphans (death / move): nearest nucleus of the candidate model, fl32 screening + exact recheck
+    const int nq = *s_cnt;
+    if (nq > 0) {
+        for (int i = tid; i < 3 * a.KC; i += STREAM_THREADS) {
+            const int ax = i / a.KC, k = i - ax * a.KC;
+            s_fx[i] = (k < Kn) ? (float)cc[(size_t)ax * a.KC + k] : __int_as_float(0x7f800000);
+        }
+        __syncthreads();
+        for (int e = tid; e < nq; e += STREAM_THREADS) {
+            const int j = s_queue[e];
+            const long long p = tile.p0 + j;
+            int bi = -1;
+            float dbest = 1e9f;
+            if (!a.exact_only) {
+                const float x = a.pxf[p], y = a.pyf[p], z = a.pzf[p];
+                float d1 = 1e9f, d2 = 1e9f;
+#pragma unroll 4
+                for (int i = 0; i < Kn; i++) {
+                    const float d = dist2_f32(s_fx[i], s_fy[i], s_fz[i], x, y, z);
+                    const bool lt = d < d1;
+                    d2 = lt ? d1 : fminf(d2, d);
+                    bi = lt ? i : bi;
+                    d1 = lt ? d : d1;
+                }
+                dbest = d1;
+                const float tol = fmaf(ta, d1 + d2, tb);
+                if (!(d2 - d1 > tol)) bi = -2;  // ambiguous
+            } else {
+                bi = -2;
+            }
+            if (bi == -2) {
+                const double x = a.px[p], y = a.py[p], z = a.pz[p];
+                double best = 1e9;
+                bi = -1;
+                for (int i = 0; i < Kn; i++) {
+                    const double d = dist2_exact(cc[i], cc[a.KC + i], cc[2 * a.KC + i], x, y, z);
+                    if (d < best) { best = d; bi = i; }
+                }
+                dbest = (float)best;
+            }
+            const uint16_t no = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bi;
+            if (COMMIT) {
+                own[p] = no;
+                dc[p] = bi < 0 ? 1e9f : dbest;
+            } else {
+                s_owner[j] = no;
+                if (act == 2 || bi != idx) atomicOr(&s_chg[j >> 5], 1u << (j & 31));  // a point that stays with the moved nucleus keeps its zeta
+            }
+        }
+    }
+    if (COMMIT) return;
+    __syncthreads();
+    // ---- phase 2: t* of the tile's rays (thread per ray); only rays holding a changed point are re-integrated
+    const double *zc = cc + 3 * (size_t)a.KC;
+    auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16S ? 0.0 : zc[o]; };
+    const double *ts = a.tstar + (size_t)chain * a.Rp;
+    double *tsc = a.tstar_c + (size_t)chain * a.Rp;
+    for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) {
+        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
+        const int j0 = q0 - tile.p0, j1 = j0 + n;  // bit range [j0, j1) of the changed bitmap
+        bool dirty = false;
+        for (int w = j0 >> 5; w <= (j1 - 1) >> 5 && n > 0; w++) {
+            uint32_t bits = s_chg[w];
+            if (w == (j0 >> 5)) bits &= 0xFFFFFFFFu << (j0 & 31);
+            if (w == ((j1 - 1) >> 5) && (j1 & 31)) bits &= 0xFFFFFFFFu >> (32 - (j1 & 31));
+            dirty |= bits != 0u;
+        }
+        tsc[r] = dirty ? ray_tstar_seq<uint16_t>(s_owner - tile.p0, a.dtT, a.ldT, r, q0, n, zeta_of) : ts[r];
     }
 }
 

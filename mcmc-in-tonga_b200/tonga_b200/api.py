@@ -160,12 +160,13 @@ class Context:
 class Chains:
     """A batch of independent RJ-MCMC chains resident on one GPU (replaces the pmap chain farm, main_inversion.jl:15)."""
 
-    SAMPLERS = {"auto": 0, "resident": 1, "wide": 2}
+    SAMPLERS = {"auto": 0, "resident": 1, "wide": 2, "streamed": 3}
 
     def __init__(self, ctx: Context, n_chains: int, chain_id0: int = 0, seed: int = 20260000, hist_cap: int | None = None,
                  sampler: str = "auto"):
         """sampler: "resident" (chain state in shared memory, max_cells <= 126, up to ~200k ray points), "wide" (a full
-        batched forward model per proposal; any size) or "auto" (resident when it fits).  Same chains either way."""
+        batched forward model per proposal; any size), "streamed" (per-point state in HBM, one streaming pass per proposal; any
+        ray set, 6 B per point and chain) or "auto" (resident when it fits, else streamed).  Same chains either way."""
         self.ctx, self.lib, self.n = ctx, ctx.lib, n_chains
         p = ctx.params
         if hist_cap is None:  # num_models_per_chain, TD_inversion_function.jl:25
@@ -177,7 +178,7 @@ class Chains:
         else:
             check(self.lib.tonga_chains_create_ex(ctx._h, C.byref(self._h), n_chains, chain_id0, seed, hist_cap, self.SAMPLERS[sampler]))
         self.KC = self.lib.tonga_chains_kcap(self._h)
-        self.sampler = {1: "resident", 2: "wide"}[self.lib.tonga_chains_sampler(self._h)] if hasattr(self.lib, "tonga_chains_sampler") else "resident"
+        self.sampler = {1: "resident", 2: "wide", 3: "streamed"}[self.lib.tonga_chains_sampler(self._h)] if hasattr(self.lib, "tonga_chains_sampler") else "resident"
         self._fin = weakref.finalize(self, self.lib.tonga_chains_destroy, self._h)
         self._ctx_keepalive = ctx
 

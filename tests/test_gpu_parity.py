@@ -604,8 +604,8 @@ def test_abi_error_paths_and_helpers(tonga):
     with pytest.raises(_lib.TongaError) as e:
         api.Chains(ctx2, 1, sampler="resident")
     assert e.value.code == -3 and "126" in str(e.value)
-    chw = api.Chains(ctx2, 1)  # auto -> the wide sampler
-    assert chw.sampler == "wide"
+    chw = api.Chains(ctx2, 1)  # auto -> the streamed sampler (per-point state in HBM)
+    assert chw.sampler == "streamed"
     with pytest.raises(_lib.TongaError) as e:
         chw.profile(True)
     assert e.value.code == -4
@@ -643,9 +643,11 @@ def _check_replay(ch, out, runs, od, hist_n=None):
             assert _close(hist["ptS"][c, :r.n_hist], r.hist_ptS[:r.n_hist])
 
 
+@pytest.mark.parametrize("kind", ["wide", "streamed"])
 @pytest.mark.parametrize("prior", [1, 2, 3])
-def test_wide_sampler_replays_oracle_stream(tonga, prior):
-    """The wide sampler (full forward model per proposal, no shared-memory chain state) against the oracle's chain."""
+def test_wide_sampler_replays_oracle_stream(tonga, prior, kind):
+    """The wide sampler (full forward model per proposal) and the streamed sampler (per-point state in HBM, incremental
+    passes) against the oracle's chain."""
     import copy
     from tonga_b200.api import Chains, Context, pack_models
     ds, p0 = tonga
@@ -659,20 +661,25 @@ def test_wide_sampler_replays_oracle_stream(tonga, prior):
     models = _start_models(rng, n, ds)
     runs = [_oracle_generate(op, od, models[c], n_iter, 2000 + c, hist_cap=64) for c in range(n)]
     recs = np.stack([r.recs for r, _ in runs])
-    ch = Chains(ctx, n, hist_cap=64, sampler="wide")
-    assert ch.sampler == "wide"
+    ch = Chains(ctx, n, hist_cap=64, sampler=kind)
+    assert ch.sampler == kind
     K, cells = pack_models(models, Kcap=ch.KC)
     ch.set_models(K, cells)
     out = ch.run(n_iter, recs=recs, trace=True)
     _check_replay(ch, out, runs, od, hist_n=20)
     assert ch.verify() == (0, 0.0, 0.0)
-    own = ch.state(want_owners=True)["owners"]
-    assert own.shape == (n, ctx.P) and own.min() >= 0 and (own.max(1) < ch.state()["K"]).all()
+    st = ch.state(want_owners=True)
+    own = st["owners"]
+    assert own.shape == (n, ctx.P) and own.min() >= 0 and (own.max(1) < st["K"]).all()
+    for c in range(n):  # the maintained owners are those of a fresh forward model
+        k = st["K"][c]
+        ref = ctx.evaluate_batch(np.array([k], np.int32), st["cells"][c:c + 1, :, :k].copy(), want_owners=True)["owners"][0]
+        assert np.array_equal(own[c], ref)
     ch.close(); ctx.close()
 
 
 def test_wide_sampler_equals_resident_sampler(tonga):
-    """Same seed, same global chain ids: the two samplers give bit-identical chains (proposals, decisions, phi, history)."""
+    """Same seed, same global chain ids: the three samplers give bit-identical chains (proposals, decisions, phi, history)."""
     import copy
     from tonga_b200.api import Chains, Context
     ds, p0 = tonga
@@ -680,14 +687,22 @@ def test_wide_sampler_equals_resident_sampler(tonga):
     p.n_iter, p.burn_in, p.keep_each = 500.0, 200.0, 10.0
     ctx = Context(ds, p)
     res = {}
-    for kind in ("resident", "wide"):
+    for kind in ("resident", "wide", "streamed"):
         ch = Chains(ctx, 12, chain_id0=5, seed=99, sampler=kind)
         ch.build_starting()
         out = ch.run(250, record=True, trace=True)
         out2 = ch.run(250, record=True, trace=True)  # a second call continues the same streams
-        res[kind] = (out, out2, ch.state(), ch.history(), ch.stats())
+        res[kind] = (out, out2, ch.state(want_owners=True), ch.history(), ch.stats())
+        assert ch.verify() == (0, 0.0, 0.0)
         ch.close()
-    (a1, a2, sa, ha, ta), (b1, b2, sb, hb, tb) = res["resident"], res["wide"]
+    assert np.array_equal(res["resident"][2]["owners"], res["streamed"][2]["owners"])
+    _same_chains(res["resident"], res["wide"])
+    _same_chains(res["resident"], res["streamed"])
+    ctx.close()
+
+
+def _same_chains(ra, rb):
+    (a1, a2, sa, ha, ta), (b1, b2, sb, hb, tb) = ra, rb
     for x, y in ((a1, b1), (a2, b2)):
         assert x["recs"].tobytes() == y["recs"].tobytes()
         assert np.array_equal(x["accept"], y["accept"]) and np.array_equal(x["K"], y["K"])
@@ -701,11 +716,11 @@ def test_wide_sampler_equals_resident_sampler(tonga):
         assert np.array_equal(ha[key], hb[key]), key
     assert ha["phi"].tobytes() == hb["phi"].tobytes() and ha["ptS"].tobytes() == hb["ptS"].tobytes()
     assert ta[0] == tb[0] and np.array_equal(ta[1], tb[1])
-    ctx.close()
 
 
-def test_wide_sampler_beyond_126_cells(tonga):
-    """max_cells = 400 (the resident sampler stops at 126): auto selects the wide sampler; replay of the oracle's chain."""
+@pytest.mark.parametrize("kind", ["auto", "wide"])
+def test_wide_sampler_beyond_126_cells(tonga, kind):
+    """max_cells = 400 (the resident sampler stops at 126): auto selects the streamed sampler; replay of the oracle's chain."""
     import copy
     from tonga_b200.api import Chains, Context, pack_models
     ds, p0 = tonga
@@ -721,8 +736,8 @@ def test_wide_sampler_beyond_126_cells(tonga):
     models[1] = random_model(rng, 150, box_of(ds))
     runs = [_oracle_generate(op, od, models[c], n_iter, 3000 + c, hist_cap=16) for c in range(n)]
     recs = np.stack([r.recs for r, _ in runs])
-    ch = Chains(ctx, n, hist_cap=16)
-    assert ch.sampler == "wide" and ch.KC == 400
+    ch = Chains(ctx, n, hist_cap=16, sampler=kind)
+    assert ch.sampler == ("streamed" if kind == "auto" else kind) and ch.KC == 400
     K, cells = pack_models(models, Kcap=ch.KC)
     ch.set_models(K, cells)
     out = ch.run(n_iter, recs=recs, trace=True)
@@ -731,7 +746,8 @@ def test_wide_sampler_beyond_126_cells(tonga):
     ch.close(); ctx.close()
 
 
-def test_wide_sampler_large_ray_set():
+@pytest.mark.parametrize("kind", ["auto", "wide"])
+def test_wide_sampler_large_ray_set(kind):
     """A ray set too large for shared memory (config-3 shape scaled down: 2000 rays, ~4e5 points, up to 300 nuclei)."""
     import oracle as O
     from tonga_b200.api import Chains, Context, pack_models
@@ -748,8 +764,8 @@ def test_wide_sampler_large_ray_set():
     models = [random_model(rng, k, box_of(ds)) for k in (40, 250)]
     runs = [_oracle_generate(op, od, models[c], n_iter, 4000 + c, hist_cap=8) for c in range(n)]
     recs = np.stack([r.recs for r, _ in runs])
-    ch = Chains(ctx, n, hist_cap=8)
-    assert ch.sampler == "wide"
+    ch = Chains(ctx, n, hist_cap=8, sampler=kind)
+    assert ch.sampler == ("streamed" if kind == "auto" else kind)
     K, cells = pack_models(models, Kcap=ch.KC)
     ch.set_models(K, cells)
     out = ch.run(n_iter, recs=recs, trace=True)
@@ -758,7 +774,7 @@ def test_wide_sampler_large_ray_set():
     ch.close(); ctx.close()
 
 
-@pytest.mark.parametrize("kind", ["resident", "wide"])
+@pytest.mark.parametrize("kind", ["resident", "wide", "streamed"])
 def test_debug_prior_chains(tonga, kind):
     """debug_prior = 1 (MCsub.jl:128-136, phi == 1): both samplers follow the oracle's prior-sampling chain; hierarchical
     noise (action 5, extension) rides along."""
@@ -789,20 +805,22 @@ def test_debug_prior_chains(tonga, kind):
 
 
 def test_wide_sampler_sigma_move(tonga):
-    """n_actions = 5 (hierarchical noise, extension): wide == resident bit for bit in generate mode."""
+    """n_actions = 5 (hierarchical noise, extension): wide == streamed == resident bit for bit in generate mode."""
     import copy
     from tonga_b200.api import Chains, Context
     ds, p0 = tonga
     p = copy.copy(p0)
     ctx = Context(ds, p, n_actions=5)
     res = {}
-    for kind in ("resident", "wide"):
+    for kind in ("resident", "wide", "streamed"):
         ch = Chains(ctx, 6, seed=3, hist_cap=0, sampler=kind)
         ch.build_starting()
         res[kind] = (ch.run(300, record=True, trace=True), ch.state())
         ch.close()
-    (a, sa), (b, sb) = res["resident"], res["wide"]
+    a, sa = res["resident"]
     assert (a["recs"]["action"] == 5).any()
-    assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"])
-    assert a["phi"].tobytes() == b["phi"].tobytes() and sa["noise"].tobytes() == sb["noise"].tobytes()
+    for kind in ("wide", "streamed"):
+        b, sb = res[kind]
+        assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"])
+        assert a["phi"].tobytes() == b["phi"].tobytes() and sa["noise"].tobytes() == sb["noise"].tobytes()
     ctx.close()
