@@ -199,6 +199,7 @@ struct tonga_chains {
     int32_t *d_Kc = nullptr;
     double *d_cells_c = nullptr;
     tg::Prop *d_props = nullptr;
+    float *d_cells_cf = nullptr;
     // streamed sampler
     uint16_t *d_owner16 = nullptr;  // [n][Ppad]
     double *d_tstar_c = nullptr;    // [n][Rp]
@@ -245,7 +246,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     // streamed sampler: 6 B per ray point and chain of state; AUTO uses it when that fits in 60 % of the free memory
-    const size_t stream_smem = (size_t)ctx->tile_pts * 4 + (size_t)ctx->tile_pts / 8 + 16 + 12 * (size_t)KC0;
+    const size_t stream_smem = (size_t)ctx->tile_pts * 4 + (size_t)ctx->tile_pts / 8 + 16;
     const bool stream_ok = pm.max_cells <= 65534 && stream_smem <= ctx->smem_optin;
     if (sampler == TONGA_SAMPLER_STREAMED && !stream_ok)
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the streamed sampler needs max_cells <= 65534 and its tile state in shared memory");
@@ -297,6 +298,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_ALLOC(ch->d_dcache, 4 * n * Pp);
         TG_ALLOC(ch->d_tstar_c, 8 * n * Rp);
         TG_ALLOC(ch->d_accept, 4 * n);
+        TG_ALLOC(ch->d_cells_cf, 4 * n * 3 * KC);
         TG_CUDA(cudaMemsetAsync(ch->d_owner16, 0xFF, 2 * n * Pp, ctx->stream));  // the padded tail stays "none"
         TG_CUDA(cudaMemsetAsync(ch->d_accept, 0, 4 * n, ctx->stream));
         if (stream_smem > 48 * 1024) {
@@ -373,7 +375,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept};
+                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf};
     for (void *p : ptrs) cudaFree(p);
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
@@ -503,14 +505,14 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         w.n_hist = ch->d_n_hist; w.model_num = ch->d_model_num; w.hist_K = ch->d_hist_K; w.hist_cells = ch->d_hist_cells;
         w.hist_phi = ch->d_hist_phi; w.hist_ptS = ch->d_hist_ptS; w.hist_iter = ch->d_hist_iter; w.hist_action = ch->d_hist_action;
         w.hist_accept = ch->d_hist_accept; w.hist_next = ch->d_hist_next;
-        w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept;
+        w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept; w.cells_cf = ch->d_cells_cf;
         tg::StreamArgs sa{};
         sa.tiles = ctx->d_tiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
         sa.dtT = ctx->d_dtT; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
         sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ctx->tile_pts;
-        sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
+        sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.cells_cf = ch->d_cells_cf; sa.n_chains = ch->n; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
-        const dim3 sgrid((unsigned)ctx->n_tiles, (unsigned)ch->n);
+        const dim3 sgrid((unsigned)((size_t)ctx->n_tiles * (size_t)ch->n));
         const int saved_exact = ctx->exact_only;
         ctx->exact_only = ch->exact_only || saved_exact;
         for (int64_t it = 0; it < nIter; it++) {

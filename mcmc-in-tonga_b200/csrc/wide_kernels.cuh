@@ -31,6 +31,7 @@ struct WideArgs {
     // candidate
     int32_t *Kc;      // [n]; -1 = nothing to evaluate
     double *cells_c;  // [n][4][KC]
+    float *cells_cf;  // [n][3][KC] fl32 copy of the candidate nuclei, +inf beyond Kc (streamed sampler; NULL otherwise)
     double *ptS_c;    // [n][R] caller's ray order (written by tg_eval_kernel)
     Prop *props;      // [n]
     // streamed sampler: t* of the candidates in sorted ray order, accept flags for the commit pass
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
             else if (act == 3 && i == idx && c == 3) v = nv[3];  // :189
             else if (act == 4 && i == idx && c < 3) v = nv[c];   // :233-235
             cand[c * KC + i] = v;
+            if (a.cells_cf && c < 3) a.cells_cf[((size_t)chain * 3 + c) * KC + i] = (i < Kn) ? (float)v : __int_as_float(0x7f800000);
         }
     }
 }
@@ -208,6 +210,8 @@ struct StreamArgs {
     const Prop *props;
     const int32_t *Kc;        // candidate nCells (-1: nothing to evaluate)
     const double *cells_c;    // candidate models [n][4][KC]
+    const float *cells_cf;    // their fl32 copies [n][3][KC], +inf beyond Kc
+    int n_chains;
     uint16_t *owner;          // [n][Ppad]
     float *dcache;            // [n][Ppad]
     const double *tstar;      // [n][Rp]
@@ -216,28 +220,48 @@ struct StreamArgs {
 };
 
 constexpr int STREAM_THREADS = 256;
+constexpr int STREAM_PPT = 4;  // points per thread and batch of phase 1 (all loads of a batch are issued before the first use)
 #define TG_NONE16S 0xFFFFu
 
+// Warp-cooperative t* of one ray in the canonical left-to-right order: the lanes compute the 32 segment terms of a batch in
+// parallel (dt load, zeta gather, seg_term); the ordered sum is then formed by adding the lanes' terms one by one, which is
+// the same sequence of additions as ray_tstar_seq.  Result valid in all lanes.
+template <typename ZetaOf>
+__device__ __forceinline__ double ray_tstar_warp(const uint16_t *owner /* of the ray's first point */, const double *__restrict__ dtT, int ldT,
+                                                 int r, int n, int lane, ZetaOf zeta_of) {
+    double acc = 0.0;
+    const double *__restrict__ col = dtT + dt_col(r);
+    for (int j0 = 0; j0 < n - 1; j0 += 32) {
+        const int j = j0 + lane;
+        double term = 0.0;
+        if (j < n - 1) term = seg_term(col[(size_t)j * ldT], zeta_of(owner[j]), zeta_of(owner[j + 1]));
+        const int cnt = min(32, n - 1 - j0);
+        for (int i = 0; i < cnt; i++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, term, i));
+    }
+    return acc;
+}
+
 template <bool COMMIT>
-__global__ void __launch_bounds__(STREAM_THREADS) tg_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int chain = blockIdx.y, tid = threadIdx.x;
+    // chain is the fastest-varying CTA index: the CTAs working on one tile (one per chain) run together, so the tile's
+    // coordinates come from HBM once and from L2 for the other chains
+    const int chain = blockIdx.x % a.n_chains, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Prop pr = a.props[chain];
     const int act = pr.action;
     if (!pr.do_eval || act == 5) return;
     if (COMMIT && (!a.accept_flag[chain] || act == 3)) return;
     const int Kn = a.Kc[chain];  // nuclei of the candidate model
-    const Tile tile = a.tiles[blockIdx.x];
+    const Tile tile = a.tiles[blockIdx.x / a.n_chains];
     const int npts = tile.p1 - tile.p0;
-    // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | orphan queue u16[tile_pts] | counter | fl32 nuclei [3][KC] (staged on demand)
+    // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | queue u16[tile_pts] (orphans, then dirty rays) | counters
     uint16_t *s_owner = reinterpret_cast<uint16_t *>(smem_raw);
     uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_owner + a.tile_pts);
     uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_chg + a.tile_pts / 32);
     int *s_cnt = reinterpret_cast<int *>(s_queue + a.tile_pts);
-    float *s_fx = reinterpret_cast<float *>(s_cnt + 4);
-    float *s_fy = s_fx + a.KC, *s_fz = s_fy + a.KC;
 
     const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
+    const float *cf = a.cells_cf + (size_t)chain * 3 * a.KC;  // fl32 copy of the candidate nuclei, +inf beyond Kn
     uint16_t *own = a.owner + (size_t)chain * a.Ppad;
     float *dc = a.dcache + (size_t)chain * a.Ppad;
     const int idx = pr.idx;
@@ -247,91 +271,133 @@ __global__ void __launch_bounds__(STREAM_THREADS) tg_stream_kernel(const StreamA
     const float ta = a.tol_alpha, tb = a.tol_beta2;
 
     if (!COMMIT) for (int i = tid; i < a.tile_pts / 32; i += STREAM_THREADS) s_chg[i] = 0u;
-    if (tid == 0) *s_cnt = 0;
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
     __syncthreads();
 
     // ---- phase 1: one flat pass over the tile's points
-    for (int j = tid; j < npts; j += STREAM_THREADS) {
-        const long long p = tile.p0 + j;
-        const uint32_t o = own[p];
-        uint32_t no = o;  // owner under the candidate model (candidate numbering)
-        bool changed = false;
-        if (act == 1 || act == 4) {
-            if (act == 4 && (int)o == idx) {  // owned by the moved nucleus: full rescan below
-                s_queue[atomicAdd(s_cnt, 1)] = (uint16_t)j;
-            } else {
-                const float d_o = dc[p];
-                const float d_c = dist2_f32(cxf, cyf, czf, a.pxf[p], a.pyf[p], a.pzf[p]);
-                const float diff = d_c - d_o, tol = fmaf(ta, d_c + d_o, tb);
-                bool sw = diff < -tol;
-                if (a.exact_only || fabsf(diff) <= tol || diff != diff) {  // inside the error band: exact FP64, MCsub.jl:254-255
-                    const double x = a.px[p], y = a.py[p], z = a.pz[p];
-                    const double de_o = (o == TG_NONE16S) ? 1e9 : dist2_exact(cc[o], cc[a.KC + o], cc[2 * a.KC + o], x, y, z);
-                    const double de_c = dist2_exact(cx, cy, cz, x, y, z);
-                    // birth: the new nucleus has the highest index -> strict <.  move: index idx also wins exact ties against o > idx.
-                    sw = (de_c < de_o) || (act == 4 && de_c == de_o && idx < (int)o && o != TG_NONE16S);
-                }
-                if (sw) {
-                    no = (uint32_t)newo;
-                    changed = true;
-                    if (COMMIT) { own[p] = (uint16_t)no; dc[p] = d_c; }
-                }
+    if (act == 1 || act == 4) {
+        for (int base = 0; base < npts; base += STREAM_THREADS * STREAM_PPT) {
+            uint32_t o[STREAM_PPT];
+            float d_o[STREAM_PPT], x[STREAM_PPT], y[STREAM_PPT], z[STREAM_PPT];
+#pragma unroll
+            for (int q = 0; q < STREAM_PPT; q++) {  // 20 independent loads in flight per thread
+                const int j = base + q * STREAM_THREADS + tid;
+                const long long p = tile.p0 + (j < npts ? j : 0);
+                o[q] = own[p]; d_o[q] = dc[p];
+                x[q] = a.pxf[p]; y[q] = a.pyf[p]; z[q] = a.pzf[p];
             }
-        } else if (act == 2) {
-            if ((int)o == idx) s_queue[atomicAdd(s_cnt, 1)] = (uint16_t)j;
-            else if (o != TG_NONE16S && (int)o > idx) {
-                no = o - 1;  // deleteat! renumbering
-                if (COMMIT) own[p] = (uint16_t)no;
+#pragma unroll
+            for (int q = 0; q < STREAM_PPT; q++) {
+                const int j = base + q * STREAM_THREADS + tid;
+                if (j >= npts) continue;
+                const long long p = tile.p0 + j;
+                uint32_t no = o[q];
+                if (act == 4 && (int)o[q] == idx) {  // owned by the moved nucleus: full rescan below
+                    s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)j;
+                } else {
+                    const float d_c = dist2_f32(cxf, cyf, czf, x[q], y[q], z[q]);
+                    const float diff = d_c - d_o[q], tol = fmaf(ta, d_c + d_o[q], tb);
+                    bool sw = diff < -tol;
+                    if (a.exact_only || !(fabsf(diff) > tol)) {  // inside the error band (or NaN): exact FP64, MCsub.jl:254-255
+                        const double xe = a.px[p], ye = a.py[p], ze = a.pz[p];
+                        const uint32_t oo = o[q];
+                        const double de_o = (oo == TG_NONE16S) ? 1e9 : dist2_exact(cc[oo], cc[a.KC + oo], cc[2 * a.KC + oo], xe, ye, ze);
+                        const double de_c = dist2_exact(cx, cy, cz, xe, ye, ze);
+                        // birth: the new nucleus has the highest index -> strict <.  move: index idx also wins exact ties against o > idx.
+                        sw = (de_c < de_o) || (act == 4 && de_c == de_o && idx < (int)oo && oo != TG_NONE16S);
+                    }
+                    if (sw) {
+                        no = (uint32_t)newo;
+                        if (COMMIT) { own[p] = (uint16_t)no; dc[p] = d_c; }
+                        else atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+                    }
+                }
+                if (!COMMIT) s_owner[j] = (uint16_t)no;
             }
-        } else {  // change: owners stay, the rays through the cell are re-integrated
-            changed = ((int)o == idx);
         }
-        if (!COMMIT) {
-            s_owner[j] = (uint16_t)no;
-            if (changed) atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+    } else {  // death / change: only the owners are read (2 B per point)
+        for (int base = 0; base < npts; base += STREAM_THREADS * STREAM_PPT) {
+            uint32_t o[STREAM_PPT];
+#pragma unroll
+            for (int q = 0; q < STREAM_PPT; q++) {
+                const int j = base + q * STREAM_THREADS + tid;
+                o[q] = own[tile.p0 + (j < npts ? j : 0)];
+            }
+#pragma unroll
+            for (int q = 0; q < STREAM_PPT; q++) {
+                const int j = base + q * STREAM_THREADS + tid;
+                if (j >= npts) continue;
+                uint32_t no = o[q];
+                if (act == 2) {
+                    if ((int)o[q] == idx) s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)j;
+                    else if (o[q] != TG_NONE16S && (int)o[q] > idx) {
+                        no = o[q] - 1;  // deleteat! renumbering
+                        if (COMMIT) own[tile.p0 + j] = (uint16_t)no;
+                    }
+                } else if ((int)o[q] == idx) {  // change: owners stay, the rays through the cell are re-integrated
+                    atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+                }
+                if (!COMMIT) s_owner[j] = (uint16_t)no;
+            }
         }
     }
     __syncthreads();
-    // ---- orphans (death / move): nearest nucleus of the candidate model, fl32 screening + exact recheck
-    const int nq = *s_cnt;
-    if (nq > 0) {
-        for (int i = tid; i < 3 * a.KC; i += STREAM_THREADS) {
-            const int ax = i / a.KC, k = i - ax * a.KC;
-            s_fx[i] = (k < Kn) ? (float)cc[(size_t)ax * a.KC + k] : __int_as_float(0x7f800000);
+    // ---- orphans (death / move): nearest nucleus of the candidate model, fl32 screening over the chain's fl32 nucleus table
+    // (L1/L2-resident) + exact recheck
+    const int nq = s_cnt[0];
+    for (int e = warp; e < nq; e += STREAM_THREADS / 32) {  // one warp per orphan: the lanes split the nuclei
+        const int j = s_queue[e];
+        const long long p = tile.p0 + j;
+        int bi = -2;
+        float dbest = 1e9f;
+        if (!a.exact_only) {
+            const float x = a.pxf[p], y = a.pyf[p], z = a.pzf[p];
+            float d1 = 1e9f, d2 = 1e9f;
+            int i1 = -1;
+            for (int i = 4 * lane; i < Kn; i += 128) {
+                const float4 fx = __ldg(reinterpret_cast<const float4 *>(cf + i)), fy = __ldg(reinterpret_cast<const float4 *>(cf + a.KC + i)),
+                             fz = __ldg(reinterpret_cast<const float4 *>(cf + 2 * a.KC + i));
+                const float d[4] = {dist2_f32(fx.x, fy.x, fz.x, x, y, z), dist2_f32(fx.y, fy.y, fz.y, x, y, z), dist2_f32(fx.z, fy.z, fz.z, x, y, z),
+                                    dist2_f32(fx.w, fy.w, fz.w, x, y, z)};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool lt = d[u] < d1;
+                    d2 = lt ? d1 : fminf(d2, d[u]);
+                    i1 = lt ? i + u : i1;
+                    d1 = lt ? d[u] : d1;
+                }
+            }
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {  // merge (best, second best) across the lanes
+                const float e1 = __shfl_xor_sync(0xffffffffu, d1, m), e2 = __shfl_xor_sync(0xffffffffu, d2, m);
+                const int ei = __shfl_xor_sync(0xffffffffu, i1, m);
+                const bool lt = e1 < d1;
+                d2 = fminf(fminf(d2, e2), lt ? d1 : e1);
+                i1 = lt ? ei : i1;
+                d1 = lt ? e1 : d1;
+            }
+            dbest = d1;
+            const float tol = fmaf(ta, d1 + d2, tb);
+            if (d2 - d1 > tol) bi = i1;  // unambiguous (an exact fl32 tie between two lanes has d2 == d1 -> exact path)
         }
-        __syncthreads();
-        for (int e = tid; e < nq; e += STREAM_THREADS) {
-            const int j = s_queue[e];
-            const long long p = tile.p0 + j;
-            int bi = -1;
-            float dbest = 1e9f;
-            if (!a.exact_only) {
-                const float x = a.pxf[p], y = a.pyf[p], z = a.pzf[p];
-                float d1 = 1e9f, d2 = 1e9f;
-#pragma unroll 4
-                for (int i = 0; i < Kn; i++) {
-                    const float d = dist2_f32(s_fx[i], s_fy[i], s_fz[i], x, y, z);
-                    const bool lt = d < d1;
-                    d2 = lt ? d1 : fminf(d2, d);
-                    bi = lt ? i : bi;
-                    d1 = lt ? d : d1;
-                }
-                dbest = d1;
-                const float tol = fmaf(ta, d1 + d2, tb);
-                if (!(d2 - d1 > tol)) bi = -2;  // ambiguous
-            } else {
-                bi = -2;
+        if (bi == -2) {  // exact FP64: each lane keeps its first minimum, the merge prefers the lower index on ties (MCsub.jl:255)
+            const double x = a.px[p], y = a.py[p], z = a.pz[p];
+            double best = 1e9;
+            int b = 0x7fffffff;
+            for (int i = lane; i < Kn; i += 32) {
+                const double d = dist2_exact(cc[i], cc[a.KC + i], cc[2 * a.KC + i], x, y, z);
+                if (d < best) { best = d; b = i; }
             }
-            if (bi == -2) {
-                const double x = a.px[p], y = a.py[p], z = a.pz[p];
-                double best = 1e9;
-                bi = -1;
-                for (int i = 0; i < Kn; i++) {
-                    const double d = dist2_exact(cc[i], cc[a.KC + i], cc[2 * a.KC + i], x, y, z);
-                    if (d < best) { best = d; bi = i; }
-                }
-                dbest = (float)best;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+                const int oi = __shfl_xor_sync(0xffffffffu, b, m);
+                if (ob < best || (ob == best && oi < b)) { best = ob; b = oi; }
             }
+            bi = (b == 0x7fffffff) ? -1 : b;
+            dbest = (float)best;
+        }
+        if (lane == 0) {
             const uint16_t no = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bi;
             if (COMMIT) {
                 own[p] = no;
@@ -344,7 +410,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) tg_stream_kernel(const StreamA
     }
     if (COMMIT) return;
     __syncthreads();
-    // ---- phase 2: t* of the tile's rays (thread per ray); only rays holding a changed point are re-integrated
+    // ---- phase 2: t* of the tile's rays.  Rays without a changed point keep their t*; the others are listed and re-integrated
+    // by the warps, one ray at a time (ray_tstar_warp: canonical left-to-right sum).
     const double *zc = cc + 3 * (size_t)a.KC;
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16S ? 0.0 : zc[o]; };
     const double *ts = a.tstar + (size_t)chain * a.Rp;
@@ -359,7 +426,16 @@ __global__ void __launch_bounds__(STREAM_THREADS) tg_stream_kernel(const StreamA
             if (w == ((j1 - 1) >> 5) && (j1 & 31)) bits &= 0xFFFFFFFFu >> (32 - (j1 & 31));
             dirty |= bits != 0u;
         }
-        tsc[r] = dirty ? ray_tstar_seq<uint16_t>(s_owner - tile.p0, a.dtT, a.ldT, r, q0, n, zeta_of) : ts[r];
+        if (dirty) s_queue[atomicAdd(&s_cnt[1], 1)] = (uint16_t)(r - tile.r0);
+        else tsc[r] = ts[r];
+    }
+    __syncthreads();
+    const int nd = s_cnt[1];
+    for (int e = warp; e < nd; e += STREAM_THREADS / 32) {
+        const int r = tile.r0 + s_queue[e];
+        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
+        const double t = ray_tstar_warp(s_owner + (q0 - tile.p0), a.dtT, a.ldT, r, n, lane, zeta_of);
+        if (lane == 0) tsc[r] = t;
     }
 }
 

@@ -104,7 +104,7 @@ def synthetic_rays(R: int, seed: int = 3, pts=(150, 250), box=(1000.0, 1000.0, 6
                    zeta_scale: float = 50.0, jitter: float = 0.5, p: parameters | None = None,
                    ak135: np.ndarray | None = None) -> DataStruct:
     """straight rays source->receiver(z=0), equally spaced points + N(0, jitter) km,
-    tS from a random `n_true`-nucleus model + N(0, sigma^2), sigma ~ U(0.04, 0.66)."""
+    tS from a random `n_true`-nucleus model + N(0, sigma^2), sigma ~ U(0.04, 0.66)  (n_true = 0: noise only; fast)."""
     p = p or parameters()
     rng = np.random.default_rng(seed)
     bx, by, bz = box
@@ -132,7 +132,7 @@ def synthetic_rays(R: int, seed: int = 3, pts=(150, 250), box=(1000.0, 1000.0, 6
     tx, ty, tz = rng.uniform(0, bx, n_true), rng.uniform(0, by, n_true), rng.uniform(0, bz, n_true)
     tzeta = rng.uniform(0, zeta_scale, n_true)
     tS = np.zeros(R)
-    for i0 in range(0, R, 512):  # chunked nearest-nucleus forward model (host-side data synthesis only)
+    for i0 in range(0, R if n_true > 0 else 0, 512):  # chunked nearest-nucleus forward model (host-side data synthesis only)
         sl = slice(i0, min(i0 + 512, R))
         xs, ys, zs = np.nan_to_num(x[:, sl]), np.nan_to_num(y[:, sl]), np.nan_to_num(z[:, sl])
         d = (tx[None, None] - xs[..., None]) ** 2 + (ty[None, None] - ys[..., None]) ** 2 + (tz[None, None] - zs[..., None]) ** 2
