@@ -246,7 +246,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     // streamed sampler: 6 B per ray point and chain of state; AUTO uses it when that fits in 60 % of the free memory
-    const size_t stream_smem = (size_t)ctx->tile_pts * 4 + (size_t)ctx->tile_pts / 8 + 16;
+    const size_t stream_smem = ((size_t)ctx->tile_pts + 8) * 4 + ((size_t)ctx->tile_pts + 8) / 8 + 4 + 16;
     const bool stream_ok = pm.max_cells <= 65534 && stream_smem <= ctx->smem_optin;
     if (sampler == TONGA_SAMPLER_STREAMED && !stream_ok)
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the streamed sampler needs max_cells <= 65534 and its tile state in shared memory");

@@ -10,6 +10,8 @@
 // proposal and acceptance code is shared with the resident sampler and t* / phi use the same canonical summation orders, so
 // the two samplers produce bit-identical chains (tests/test_gpu_parity.py::test_wide_matches_resident).
 #pragma once
+#include <type_traits>
+
 #include "proposal.cuh"
 #include "tonga_internal.cuh"
 
@@ -253,12 +255,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     if (COMMIT && (!a.accept_flag[chain] || act == 3)) return;
     const int Kn = a.Kc[chain];  // nuclei of the candidate model
     const Tile tile = a.tiles[blockIdx.x / a.n_chains];
-    const int npts = tile.p1 - tile.p0;
     // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | queue u16[tile_pts] (orphans, then dirty rays) | counters
+    const int cap = a.tile_pts + 8;  // the aligned groups may start up to 3 points before / end up to 3 points after the tile
     uint16_t *s_owner = reinterpret_cast<uint16_t *>(smem_raw);
-    uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_owner + a.tile_pts);
-    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_chg + a.tile_pts / 32);
-    int *s_cnt = reinterpret_cast<int *>(s_queue + a.tile_pts);
+    uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_owner + cap);
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_chg + cap / 32 + 1);
+    int *s_cnt = reinterpret_cast<int *>(s_queue + cap);
 
     const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
     const float *cf = a.cells_cf + (size_t)chain * 3 * a.KC;  // fl32 copy of the candidate nuclei, +inf beyond Kn
@@ -270,84 +272,118 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     const int newo = (act == 1) ? Kn - 1 : idx;  // index a switched point takes: the appended nucleus / the moved one
     const float ta = a.tol_alpha, tb = a.tol_beta2;
 
-    if (!COMMIT) for (int i = tid; i < a.tile_pts / 32; i += STREAM_THREADS) s_chg[i] = 0u;
+    if (!COMMIT) for (int i = tid; i < cap / 32 + 1; i += STREAM_THREADS) s_chg[i] = 0u;
     if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
     __syncthreads();
 
-    // ---- phase 1: one flat pass over the tile's points
-    if (act == 1 || act == 4) {
-        for (int base = 0; base < npts; base += STREAM_THREADS * STREAM_PPT) {
-            uint32_t o[STREAM_PPT];
-            float d_o[STREAM_PPT], x[STREAM_PPT], y[STREAM_PPT], z[STREAM_PPT];
+    // ---- phase 1: one flat pass over the tile's points, 4 consecutive points (one aligned 8 / 16 B vector per array) per thread
+    // and step.  The first / last group may reach into the neighbouring tiles: those points are masked out (never written).
+    // ACT is a compile-time constant so that every action carries only its own logic.
+    const long long p0a = tile.p0 & ~3ll;                     // aligned start; s_owner / s_chg are indexed relative to it
+    const int lo = (int)(tile.p0 - p0a), hi = (int)(tile.p1 - p0a);  // valid relative range [lo, hi)
+    const int ngroups = (hi + 3) >> 2;
+    auto phase1 = [&](auto actc) {
+        constexpr int ACT = decltype(actc)::value;
+#pragma unroll 2
+        for (int g = tid; g < ngroups; g += STREAM_THREADS) {
+            const long long p = p0a + 4 * g;
+            const ushort4 ov = *reinterpret_cast<const ushort4 *>(own + p);
+            const uint32_t o[4] = {ov.x, ov.y, ov.z, ov.w};
+            uint32_t no[4] = {ov.x, ov.y, ov.z, ov.w};
+            uint32_t valid = 0xFu;  // bit q: point 4g+q belongs to this tile
+            if (4 * g < lo) valid &= 0xFu << (lo - 4 * g);
+            if (4 * g + 4 > hi) valid &= 0xFu >> (4 * g + 4 - hi);
+            uint32_t chg = 0;       // bit q: the owner or the zeta of the point changes under the candidate model
+            uint32_t wr = 0;        // bit q: COMMIT must write the owner
+            float dnew[4];
+            if (ACT == 1 || ACT == 4) {
+                const float4 dv = *reinterpret_cast<const float4 *>(dc + p);
+                const float4 xv = *reinterpret_cast<const float4 *>(a.pxf + p), yv = *reinterpret_cast<const float4 *>(a.pyf + p),
+                             zv = *reinterpret_cast<const float4 *>(a.pzf + p);
+                const float d_o[4] = {dv.x, dv.y, dv.z, dv.w}, x[4] = {xv.x, xv.y, xv.z, xv.w}, y[4] = {yv.x, yv.y, yv.z, yv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w};
+                uint32_t amb = 0, orph = 0;
 #pragma unroll
-            for (int q = 0; q < STREAM_PPT; q++) {  // 20 independent loads in flight per thread
-                const int j = base + q * STREAM_THREADS + tid;
-                const long long p = tile.p0 + (j < npts ? j : 0);
-                o[q] = own[p]; d_o[q] = dc[p];
-                x[q] = a.pxf[p]; y[q] = a.pyf[p]; z[q] = a.pzf[p];
-            }
-#pragma unroll
-            for (int q = 0; q < STREAM_PPT; q++) {
-                const int j = base + q * STREAM_THREADS + tid;
-                if (j >= npts) continue;
-                const long long p = tile.p0 + j;
-                uint32_t no = o[q];
-                if (act == 4 && (int)o[q] == idx) {  // owned by the moved nucleus: full rescan below
-                    s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)j;
-                } else {
+                for (int q = 0; q < 4; q++) {
                     const float d_c = dist2_f32(cxf, cyf, czf, x[q], y[q], z[q]);
+                    dnew[q] = d_c;
                     const float diff = d_c - d_o[q], tol = fmaf(ta, d_c + d_o[q], tb);
-                    bool sw = diff < -tol;
-                    if (a.exact_only || !(fabsf(diff) > tol)) {  // inside the error band (or NaN): exact FP64, MCsub.jl:254-255
-                        const double xe = a.px[p], ye = a.py[p], ze = a.pz[p];
+                    const bool mine = (ACT == 4) && ((int)o[q] == idx);  // owned by the moved nucleus: full rescan below
+                    orph |= mine ? (1u << q) : 0u;
+                    chg |= (!mine && diff < -tol) ? (1u << q) : 0u;
+                    amb |= (!mine && (a.exact_only || !(fabsf(diff) > tol))) ? (1u << q) : 0u;  // inside the error band (or NaN)
+                }
+                amb &= valid; orph &= valid; chg &= valid;
+                if (amb) {  // exact FP64 comparison, MCsub.jl:254-255
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) {
+                        if (!((amb >> q) & 1u)) continue;
+                        const double xe = a.px[p + q], ye = a.py[p + q], ze = a.pz[p + q];
                         const uint32_t oo = o[q];
                         const double de_o = (oo == TG_NONE16S) ? 1e9 : dist2_exact(cc[oo], cc[a.KC + oo], cc[2 * a.KC + oo], xe, ye, ze);
                         const double de_c = dist2_exact(cx, cy, cz, xe, ye, ze);
                         // birth: the new nucleus has the highest index -> strict <.  move: index idx also wins exact ties against o > idx.
-                        sw = (de_c < de_o) || (act == 4 && de_c == de_o && idx < (int)oo && oo != TG_NONE16S);
-                    }
-                    if (sw) {
-                        no = (uint32_t)newo;
-                        if (COMMIT) { own[p] = (uint16_t)no; dc[p] = d_c; }
-                        else atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+                        const bool sw = (de_c < de_o) || (ACT == 4 && de_c == de_o && idx < (int)oo && oo != TG_NONE16S);
+                        chg = sw ? (chg | (1u << q)) : (chg & ~(1u << q));
                     }
                 }
-                if (!COMMIT) s_owner[j] = (uint16_t)no;
-            }
-        }
-    } else {  // death / change: only the owners are read (2 B per point)
-        for (int base = 0; base < npts; base += STREAM_THREADS * STREAM_PPT) {
-            uint32_t o[STREAM_PPT];
 #pragma unroll
-            for (int q = 0; q < STREAM_PPT; q++) {
-                const int j = base + q * STREAM_THREADS + tid;
-                o[q] = own[tile.p0 + (j < npts ? j : 0)];
-            }
-#pragma unroll
-            for (int q = 0; q < STREAM_PPT; q++) {
-                const int j = base + q * STREAM_THREADS + tid;
-                if (j >= npts) continue;
-                uint32_t no = o[q];
-                if (act == 2) {
-                    if ((int)o[q] == idx) s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)j;
-                    else if (o[q] != TG_NONE16S && (int)o[q] > idx) {
-                        no = o[q] - 1;  // deleteat! renumbering
-                        if (COMMIT) own[tile.p0 + j] = (uint16_t)no;
-                    }
-                } else if ((int)o[q] == idx) {  // change: owners stay, the rays through the cell are re-integrated
-                    atomicOr(&s_chg[j >> 5], 1u << (j & 31));
+                for (int q = 0; q < 4; q++) no[q] = ((chg >> q) & 1u) ? (uint32_t)newo : o[q];
+                wr = chg;
+                if (ACT == 4 && orph) {
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++)
+                        if ((orph >> q) & 1u) s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)(4 * g + q);
                 }
-                if (!COMMIT) s_owner[j] = (uint16_t)no;
+            } else if (ACT == 2) {
+                uint32_t orph = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    orph |= ((int)o[q] == idx) ? (1u << q) : 0u;
+                    const bool dec = o[q] != TG_NONE16S && (int)o[q] > idx;  // deleteat! renumbering
+                    no[q] = dec ? o[q] - 1 : o[q];
+                    wr |= dec ? (1u << q) : 0u;
+                }
+                orph &= valid; wr &= valid;
+                if (orph) {
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++)
+                        if ((orph >> q) & 1u) s_queue[atomicAdd(&s_cnt[0], 1)] = (uint16_t)(4 * g + q);
+                }
+            } else {  // change: owners stay, the rays through the cell are re-integrated
+#pragma unroll
+                for (int q = 0; q < 4; q++) chg |= ((int)o[q] == idx) ? (1u << q) : 0u;
+                chg &= valid;
+            }
+            if (!COMMIT) {
+                *reinterpret_cast<ushort4 *>(s_owner + 4 * g) = make_ushort4((uint16_t)no[0], (uint16_t)no[1], (uint16_t)no[2], (uint16_t)no[3]);
+                if (chg) atomicOr(&s_chg[g >> 3], chg << ((4 * g) & 31));
+            } else if (wr) {
+                if (valid == 0xFu) {
+                    *reinterpret_cast<ushort4 *>(own + p) = make_ushort4((uint16_t)no[0], (uint16_t)no[1], (uint16_t)no[2], (uint16_t)no[3]);
+                } else {  // tile boundary: the neighbouring tile's CTA owns the other points of this vector
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if ((wr >> q) & 1u) own[p + q] = (uint16_t)no[q];
+                }
+                if (ACT == 1 || ACT == 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if ((wr >> q) & 1u) dc[p + q] = dnew[q];
+                }
             }
         }
-    }
+    };
+    if (act == 1) phase1(std::integral_constant<int, 1>{});
+    else if (act == 4) phase1(std::integral_constant<int, 4>{});
+    else if (act == 2) phase1(std::integral_constant<int, 2>{});
+    else phase1(std::integral_constant<int, 3>{});
     __syncthreads();
     // ---- orphans (death / move): nearest nucleus of the candidate model, fl32 screening over the chain's fl32 nucleus table
     // (L1/L2-resident) + exact recheck
     const int nq = s_cnt[0];
     for (int e = warp; e < nq; e += STREAM_THREADS / 32) {  // one warp per orphan: the lanes split the nuclei
-        const int j = s_queue[e];
-        const long long p = tile.p0 + j;
+        const int j = s_queue[e];  // relative to p0a
+        const long long p = p0a + j;
         int bi = -2;
         float dbest = 1e9f;
         if (!a.exact_only) {
@@ -418,7 +454,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     double *tsc = a.tstar_c + (size_t)chain * a.Rp;
     for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) {
         const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-        const int j0 = q0 - tile.p0, j1 = j0 + n;  // bit range [j0, j1) of the changed bitmap
+        const int j0 = (int)(q0 - p0a), j1 = j0 + n;  // bit range [j0, j1) of the changed bitmap
         bool dirty = false;
         for (int w = j0 >> 5; w <= (j1 - 1) >> 5 && n > 0; w++) {
             uint32_t bits = s_chg[w];
@@ -434,7 +470,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     for (int e = warp; e < nd; e += STREAM_THREADS / 32) {
         const int r = tile.r0 + s_queue[e];
         const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-        const double t = ray_tstar_warp(s_owner + (q0 - tile.p0), a.dtT, a.ldT, r, n, lane, zeta_of);
+        const double t = ray_tstar_warp(s_owner + (q0 - p0a), a.dtT, a.ldT, r, n, lane, zeta_of);
         if (lane == 0) tsc[r] = t;
     }
 }
