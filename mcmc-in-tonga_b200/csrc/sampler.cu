@@ -203,7 +203,9 @@ struct tonga_chains {
     // streamed sampler
     uint16_t *d_owner16 = nullptr;  // [n][Ppad]
     double *d_tstar_c = nullptr;    // [n][Rp]
+    double *d_term_c = nullptr;     // [n][Rp]
     int32_t *d_accept = nullptr;    // [n]
+    int32_t *d_active = nullptr;    // [n + 1]: active chain list, then its length
     size_t stream_smem = 0;
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
@@ -258,6 +260,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     }
     const bool wide = streamed || (sampler == TONGA_SAMPLER_WIDE) || !fits;
     if (wide && nChains > 65535) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the wide / streamed samplers run at most 65535 chains per batch");
+    if (streamed && (double)ctx->n_tiles * (double)nChains > 2147483647.0)
+        return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: tiles x chains exceeds the launch grid of the streamed sampler");
     tonga_chains *ch = new tonga_chains();
     struct Guard {  // frees a half-built batch when an allocation below fails (TG_ALLOC / TG_CUDA return early)
         tonga_chains *&c;
@@ -297,7 +301,9 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_ALLOC(ch->d_owner16, 2 * n * Pp);
         TG_ALLOC(ch->d_dcache, 4 * n * Pp);
         TG_ALLOC(ch->d_tstar_c, 8 * n * Rp);
+        TG_ALLOC(ch->d_term_c, 8 * n * Rp);
         TG_ALLOC(ch->d_accept, 4 * n);
+        TG_ALLOC(ch->d_active, 4 * (n + 1));
         TG_ALLOC(ch->d_cells_cf, 4 * n * 3 * KC);
         TG_CUDA(cudaMemsetAsync(ch->d_owner16, 0xFF, 2 * n * Pp, ctx->stream));  // the padded tail stays "none"
         TG_CUDA(cudaMemsetAsync(ch->d_accept, 0, 4 * n, ctx->stream));
@@ -375,7 +381,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf};
+                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active};
     for (void *p : ptrs) cudaFree(p);
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
@@ -505,18 +511,22 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         w.n_hist = ch->d_n_hist; w.model_num = ch->d_model_num; w.hist_K = ch->d_hist_K; w.hist_cells = ch->d_hist_cells;
         w.hist_phi = ch->d_hist_phi; w.hist_ptS = ch->d_hist_ptS; w.hist_iter = ch->d_hist_iter; w.hist_action = ch->d_hist_action;
         w.hist_accept = ch->d_hist_accept; w.hist_next = ch->d_hist_next;
-        w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept; w.cells_cf = ch->d_cells_cf;
+        w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept; w.cells_cf = ch->d_cells_cf; w.term_c = ch->d_term_c;
+        w.active = ch->streamed ? ch->d_active : nullptr; w.n_active = ch->streamed ? ch->d_active + ch->n : nullptr;
         tg::StreamArgs sa{};
         sa.tiles = ctx->d_tiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
         sa.dtT = ctx->d_dtT; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
         sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ctx->tile_pts;
         sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.cells_cf = ch->d_cells_cf; sa.n_chains = ch->n; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
-        const dim3 sgrid((unsigned)((size_t)ctx->n_tiles * (size_t)ch->n));
+        sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ctx->n_tiles;
+        sa.term_c = ch->d_term_c; sa.tS = ctx->d_tS; sa.sig = ctx->d_sig; sa.noise = ch->d_noise;
+        const dim3 sgrid((unsigned)((size_t)ctx->n_tiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int saved_exact = ctx->exact_only;
         ctx->exact_only = ch->exact_only || saved_exact;
         for (int64_t it = 0; it < nIter; it++) {
             w.it = it; w.iter = ch->iter_done + 1 + it;
+            if (ch->streamed) TG_CUDA(cudaMemsetAsync(ch->d_active + ch->n, 0, 4, s));
             tg::tg_wide_propose_kernel<<<ch->n, tg::WIDE_PROPOSE_THREADS, 0, s>>>(w);
             if (ch->streamed) {
                 tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);

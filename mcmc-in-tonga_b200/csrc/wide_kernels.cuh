@@ -39,6 +39,9 @@ struct WideArgs {
     // streamed sampler: t* of the candidates in sorted ray order, accept flags for the commit pass
     int streamed;
     double *tstar_c;        // [n][Rp]
+    const double *term_c;   // [n][Rp] misfit terms of the candidate (written by tg_stream_kernel<false>)
+    int32_t *active;        // [n] chains whose candidate needs the point pass this iteration (any order)
+    int32_t *n_active;      // [1], zeroed by the host before the propose kernel
     int32_t *accept_flag;   // [n]
     // streams / traces
     const tonga_proposal *recs_in;
@@ -85,7 +88,10 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
     const int Kn = (act == 1) ? K + 1 : (act == 2 ? K - 1 : K);
     // sigma move / prior sampling (debug_prior): t* does not change or is not needed -> no forward model
     const bool geometry = s_prop.do_eval && act != 5 && (a.streamed || !a.prm.debug_prior);
-    if (tid == 0) a.Kc[chain] = geometry ? Kn : -1;
+    if (tid == 0) {
+        a.Kc[chain] = geometry ? Kn : -1;
+        if (geometry && a.active) a.active[atomicAdd(a.n_active, 1)] = chain;
+    }
     if (!s_prop.do_eval || act == 5) return;
     double *cand = a.cells_c + (size_t)chain * 4 * KC;
     const double nv[4] = {s_prop.x, s_prop.y, s_prop.z, s_prop.zeta};
@@ -124,10 +130,29 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             phin = 1.0;  // MCsub.jl:128-136
         } else {
             const double nz = (act == 5) ? pr.zeta : noise;
-            phin = phi_canonical_128(R, tid, scratch, [&](int r) {
-                const double t = (act == 5) ? ts[r] : (a.streamed ? tsc[r] : tc[a.ray_orig[r]]);
-                return misfit_term(t, a.tS[r], a.sig[r], nz);
-            });
+            if (a.streamed && act != 5) {  // the candidate pass left the per-ray misfit terms: canonical sum only
+                const double *trm = a.term_c + (size_t)chain * a.Rp;
+                double acc = 0.0;
+                int r = tid;
+                for (; r + 7 * TG_PHI_LANES < R; r += 8 * TG_PHI_LANES) {  // 8 loads in flight, then the ordered adds
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = trm[r + u * TG_PHI_LANES];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+                }
+                for (; r < R; r += TG_PHI_LANES) acc = __dadd_rn(acc, trm[r]);
+                acc = warp_sum_canonical(acc);
+                if ((tid & 31) == 0) scratch[tid >> 5] = acc;
+                __syncthreads();
+                phin = __dadd_rn(__dadd_rn(__dadd_rn(scratch[0], scratch[1]), scratch[2]), scratch[3]);
+                __syncthreads();
+            } else {
+                phin = phi_canonical_128(R, tid, scratch, [&](int r) {
+                    const double t = (act == 5) ? ts[r] : (a.streamed ? tsc[r] : tc[a.ray_orig[r]]);
+                    return misfit_term(t, a.tS[r], a.sig[r], nz);
+                });
+            }
         }
         if (tid == 0) s_accept = accept_decision(pr, K, phi, phin, (act == 2 || act == 3) ? a.cells[(size_t)chain * 4 * KC + 3 * KC + pr.idx] : 0.0, noise, beta, R, pm,
                                                      pm.zeta_scale * pm.sig / 100);
@@ -138,9 +163,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 double *cur = a.cells + (size_t)chain * 4 * KC;
                 const double *cand = a.cells_c + (size_t)chain * 4 * KC;
                 for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) cur[i] = cand[i];
-                if (a.streamed)
-                    for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tsc[r];
-                else if (!pm.debug_prior)
+                if (!a.streamed && !pm.debug_prior)  // streamed: the commit pass copies t* tile by tile
                     for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tc[a.ray_orig[r]];
             }
             phi = phin;
@@ -165,7 +188,8 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             const double *cur = a.cells + (size_t)chain * 4 * KC;
             for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) hc[i] = cur[i];
             double *hp = a.hist_ptS + h * R;
-            for (int r = tid; r < R; r += TG_PHI_LANES) hp[a.ray_orig[r]] = ts[r];
+            const double *tcur = (a.streamed && accepted && act != 5) ? tsc : ts;  // streamed: the commit pass has not copied t* yet
+            for (int r = tid; r < R; r += TG_PHI_LANES) hp[a.ray_orig[r]] = tcur[r];
             if (tid == 0) {
                 a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = a.iter;
                 a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;
@@ -216,12 +240,17 @@ struct StreamArgs {
     int n_chains;
     uint16_t *owner;          // [n][Ppad]
     float *dcache;            // [n][Ppad]
-    const double *tstar;      // [n][Rp]
-    double *tstar_c;          // [n][Rp]
+    double *tstar;            // [n][Rp]
+    double *tstar_c;          // [n][Rp] t* under the candidate model
+    double *term_c;           // [n][Rp] misfit term of every ray under the candidate model (summed by the accept kernel)
+    const double *tS, *sig, *noise;
     const int32_t *accept_flag;
+    const int32_t *active, *n_active;  // chains with a candidate to process (tg_wide_propose_kernel)
+    int n_tiles;
 };
 
 constexpr int STREAM_THREADS = 256;
+constexpr int STREAM_GROUP = 1;  // active chains a CTA processes one after the other on its tile (coordinates re-read from L1)
 constexpr int STREAM_PPT = 4;  // points per thread and batch of phase 1 (all loads of a batch are issued before the first use)
 #define TG_NONE16S 0xFFFFu
 
@@ -246,15 +275,29 @@ __device__ __forceinline__ double ray_tstar_warp(const uint16_t *owner /* of the
 template <bool COMMIT>
 __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // chain is the fastest-varying CTA index: the CTAs working on one tile (one per chain) run together, so the tile's
-    // coordinates come from HBM once and from L2 for the other chains
-    const int chain = blockIdx.x % a.n_chains, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // CTA = (tile, group of STREAM_GROUP active chains), processed one after the other: the tile's coordinates come from HBM once,
+    // from L2 for the other groups and from L1 for the other chains of the group.  The launch covers n_tiles x ceil(n_chains /
+    // GROUP) CTAs; those beyond the active list exit at once.  (A persistent-CTA variant with a static item loop was measured
+    // 40 % slower.)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_active = *a.n_active;
+    const int n_groups = (a.n_chains + STREAM_GROUP - 1) / STREAM_GROUP;
+    const int grp = blockIdx.x % n_groups;
+    if (grp * STREAM_GROUP >= n_active) return;
+    const Tile tile = a.tiles[blockIdx.x / n_groups];
+    for (int ci = grp * STREAM_GROUP; ci < min(n_active, (grp + 1) * STREAM_GROUP); ci++) {
+    __syncthreads();  // the previous chain's shared-memory state is free
+    const int chain = a.active[ci];
     const Prop pr = a.props[chain];
     const int act = pr.action;
-    if (!pr.do_eval || act == 5) return;
-    if (COMMIT && (!a.accept_flag[chain] || act == 3)) return;
+    if (COMMIT && !a.accept_flag[chain]) continue;
     const int Kn = a.Kc[chain];  // nuclei of the candidate model
-    const Tile tile = a.tiles[blockIdx.x / a.n_chains];
+    if (COMMIT) {  // the accepted candidate's t* becomes the chain's
+        const double *tsc = a.tstar_c + (size_t)chain * a.Rp;
+        double *ts = a.tstar + (size_t)chain * a.Rp;
+        for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) ts[r] = tsc[r];
+        if (act == 3) continue;  // change: no owner moves
+    }
     // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | queue u16[tile_pts] (orphans, then dirty rays) | counters
     const int cap = a.tile_pts + 8;  // the aligned groups may start up to 3 points before / end up to 3 points after the tile
     uint16_t *s_owner = reinterpret_cast<uint16_t *>(smem_raw);
@@ -444,7 +487,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
             }
         }
     }
-    if (COMMIT) return;
+    if (COMMIT) continue;
     __syncthreads();
     // ---- phase 2: t* of the tile's rays.  Rays without a changed point keep their t*; the others are listed and re-integrated
     // by the warps, one ray at a time (ray_tstar_warp: canonical left-to-right sum).
@@ -452,6 +495,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16S ? 0.0 : zc[o]; };
     const double *ts = a.tstar + (size_t)chain * a.Rp;
     double *tsc = a.tstar_c + (size_t)chain * a.Rp;
+    double *trm = a.term_c + (size_t)chain * a.Rp;
+    const double nz = a.noise[chain];
     for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) {
         const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
         const int j0 = (int)(q0 - p0a), j1 = j0 + n;  // bit range [j0, j1) of the changed bitmap
@@ -463,7 +508,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
             dirty |= bits != 0u;
         }
         if (dirty) s_queue[atomicAdd(&s_cnt[1], 1)] = (uint16_t)(r - tile.r0);
-        else tsc[r] = ts[r];
+        else { const double t = ts[r]; tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
     }
     __syncthreads();
     const int nd = s_cnt[1];
@@ -471,7 +516,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
         const int r = tile.r0 + s_queue[e];
         const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
         const double t = ray_tstar_warp(s_owner + (q0 - p0a), a.dtT, a.ldT, r, n, lane, zeta_of);
-        if (lane == 0) tsc[r] = t;
+        if (lane == 0) { tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
+    }
     }
 }
 

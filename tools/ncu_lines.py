@@ -60,5 +60,5 @@ def srcline(f, l):
             src[f] = []
     return src[f][l - 1].strip()[:80] if 0 < l <= len(src[f]) else ""
 print("file:line            samp%  inst%  nSASS | no_inst barrier long_sb short_sb wait math branch | source")
-for fl, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for fl, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get("SORT") == "inst" else 0])[:top]:
     print(f"{fl[0][:14]}:{fl[1]:<5} {100*a[0]/ts:5.1f}% {100*a[1]/ti:5.1f}% {a[-1]:5d} | " + " ".join(f"{100*v/ts:4.1f}" for v in a[2:9]) + " | " + srcline(*fl))

@@ -28,3 +28,17 @@ ms = ch.last_kernel_ms()
 it, counts = ch.stats()
 print(f"{ch.sampler}: P={ctx.P} chains={n} K0={K0}: {ms / iters:.3f} ms/iteration, {n * iters / ms * 1e3:.0f} proposals/s, "
       f"{ms / iters / n * 1e3:.1f} us per chain-proposal; proposed/accepted/evaluated by action: {counts.sum(0).tolist()}")
+
+if os.environ.get("PER_ACTION"):
+    out = ch.run(iters, record=True)
+    base = out["recs"]
+    for A in (1, 2, 3, 4):
+        recs = base.copy()
+        off = recs["action"] != A
+        recs["action"][off] = 1; recs["zeta"][off] = -1.0  # a-priori rejected birth: no evaluation
+        it0, c0 = ch.stats()
+        ch.run(iters, recs=recs)
+        ms = ch.last_kernel_ms()
+        it1, c1 = ch.stats()
+        ev = int((c1 - c0)[:, 2, A - 1].sum()); acc = int((c1 - c0)[:, 1, A - 1].sum())
+        print(f"  action {A}: {ev} evaluated, {acc} accepted, {ms:.2f} ms -> {ms / max(ev, 1) * 1e3:.1f} us per evaluated chain-proposal")
