@@ -189,7 +189,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     chk(upload(&ctx->d_px, px, ctx->stream));
     chk(upload(&ctx->d_py, py, ctx->stream));
     chk(upload(&ctx->d_pz, pz, ctx->stream));
-    {   // fl32 copies + the rigorous screening band (DESIGN.md 4.3): with u = 2^-24 and M = max |coordinate| (points and box),
+    {   // fl32 copies + the rigorous screening band (DESIGN.md 4.2): with u = 2^-24 and M = max |coordinate| (points and box),
         // |D32 - D| <= 11u*D32 + 7.5u*M^2 for any evaluation order; alpha = 16u and beta = 12u*M^2 leave a 1.4x margin.
         std::vector<float> xf(Ppad), yf(Ppad), zf(Ppad);
         double M = 0.0;

@@ -47,7 +47,7 @@ __device__ __forceinline__ double dist2_exact(double mx, double my, double mz, d
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// FP32 screening distance (any rounding / FMA order is fine: the error band of DESIGN.md 4.3 covers it)
+// FP32 screening distance (any rounding / FMA order is fine: the error band of DESIGN.md 4.2 covers it)
 __device__ __forceinline__ float dist2_f32(float mx, float my, float mz, float x, float y, float z) {
     const float dx = mx - x, dy = my - y, dz = mz - z;
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
