@@ -72,6 +72,12 @@ int tonga_device_count(int *n_out);
 int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double *rayX, const double *rayY, const double *rayZ,
                  const double *rayL, const double *rayU, const double *tS, const double *allSig,
                  const tonga_params *params, int32_t device);
+/* The same context built from the raw point matrices: rayL = sqrt.(dx.^2 + dy.^2 + dz.^2) and rayU = 0.5 .* (U[k] + U[k+1])
+ * (load_data_Tonga.jl:66-69) are computed on the device together with the flatten, for ray sets where the host-side
+ * preprocessing and flatten of tonga_create take seconds (BASELINE config 3: 2e7 points).  U[m x R] = slowness at the ray
+ * points (column-major like rayX; NaN padding).  Bit-identical to tonga_create fed with those rayL / rayU. */
+int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, const double *rayX, const double *rayY, const double *rayZ,
+                             const double *U, const double *tS, const double *allSig, const tonga_params *params, int32_t device);
 void tonga_destroy(tonga_ctx *ctx);
 /* R, number of valid points P, number of segments S, padded point count used on the device */
 int tonga_info(const tonga_ctx *ctx, int32_t *R, int64_t *P, int64_t *S, int64_t *Ppad);

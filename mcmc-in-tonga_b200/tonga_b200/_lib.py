@@ -45,6 +45,7 @@ SYMBOLS = {
     "tonga_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "tonga_create": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                C.POINTER(TongaParams), C.c_int32]),
+    "tonga_create_from_points": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TongaParams), C.c_int32]),
     "tonga_destroy": (None, [_P]),
     "tonga_info": (C.c_int, [_P, c_ip, c_lp, c_lp, c_lp]),
     "tonga_ray_offsets": (C.c_int, [_P, c_ip]),

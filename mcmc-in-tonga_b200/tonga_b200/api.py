@@ -74,9 +74,12 @@ class Context:
     """Device-resident ray geometry + observations: what `dataStruct` is to evaluate()."""
 
     def __init__(self, dataStruct: DataStruct | None, TD_parameters: parameters | None = None, device: int = 0,
-                 n_actions: int = 4, params: TongaParams | None = None):
+                 n_actions: int = 4, params: TongaParams | None = None, device_ingest: bool = False):
+        """device_ingest=True: rayL / rayU (load_data_Tonga.jl:66-69) and the flatten are computed on the GPU from
+        dataStruct.rayX/Y/Z and dataStruct.U (tonga_create_from_points); same context bit for bit, much faster for large sets."""
         self.lib = _lib.load()
         self._h = C.c_void_p()
+        f = lambda a: np.asfortranarray(a, dtype=np.float64)
         if dataStruct is None:  # geometry-less context (v_nearest / Interpolation on arbitrary points only)
             z = np.zeros((1, 0), order="F")
             p = params or TongaParams()
@@ -86,15 +89,22 @@ class Context:
             self.params = p
         else:
             ds = dataStruct
-            f = lambda a: np.asfortranarray(a, dtype=np.float64)
-            rx, ry, rz, rl, ru = f(ds.rayX), f(ds.rayY), f(ds.rayZ), f(ds.rayL), f(ds.rayU)
+            rx, ry, rz = f(ds.rayX), f(ds.rayY), f(ds.rayZ)
             self.m, self.R = rx.shape
-            if rl.shape != (self.m - 1, self.R) or ru.shape != rl.shape:
-                raise TongaError(-1, "rayL / rayU must be (m-1) x R")
             tS, sg = np.ascontiguousarray(ds.tS, dtype=np.float64), np.ascontiguousarray(ds.allSig, dtype=np.float64)
             self.params = params or make_params(TD_parameters, ds, n_actions)
-            check(self.lib.tonga_create(C.byref(self._h), self.m, self.R, dp(rx), dp(ry), dp(rz), dp(rl), dp(ru), dp(tS), dp(sg),
-                                        C.byref(self.params), device))
+            if device_ingest:
+                U = f(ds.U)
+                if U.shape != rx.shape:
+                    raise TongaError(-1, "U must be m x R like rayX")
+                check(self.lib.tonga_create_from_points(C.byref(self._h), self.m, self.R, dp(rx), dp(ry), dp(rz), dp(U), dp(tS), dp(sg),
+                                                        C.byref(self.params), device))
+            else:
+                rl, ru = f(ds.rayL), f(ds.rayU)
+                if rl.shape != (self.m - 1, self.R) or ru.shape != rl.shape:
+                    raise TongaError(-1, "rayL / rayU must be (m-1) x R")
+                check(self.lib.tonga_create(C.byref(self._h), self.m, self.R, dp(rx), dp(ry), dp(rz), dp(rl), dp(ru), dp(tS), dp(sg),
+                                            C.byref(self.params), device))
         R, P, S, Pp = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
         check(self.lib.tonga_info(self._h, C.byref(R), C.byref(P), C.byref(S), C.byref(Pp)))
         self.P, self.S, self.Ppad = P.value, S.value, Pp.value

@@ -824,3 +824,37 @@ def test_wide_sampler_sigma_move(tonga):
         assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"])
         assert a["phi"].tobytes() == b["phi"].tobytes() and sa["noise"].tobytes() == sb["noise"].tobytes()
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ device-side ingest (N4)
+@pytest.mark.parametrize("which", ["tonga", "synthetic"])
+def test_device_ingest_matches_host_flatten(tonga, which):
+    """tonga_create_from_points (rayl, rayu, dt, flatten on the GPU; load_data_Tonga.jl:66-69) == tonga_create fed with the host
+    arithmetic of data.ray_lengths: same sizes, same offsets, bit-identical owners / t* / phi, bit-identical chains."""
+    from tonga_b200.api import Chains, Context
+    from tonga_b200.data import synthetic_rays
+    from tonga_b200.structs import parameters
+    if which == "tonga":
+        ds, p = tonga
+    else:
+        p = parameters()
+        ds = synthetic_rays(700, seed=12, pts=(2, 90), p=p)  # ragged, including 2-point rays
+    a, b = Context(ds, p), Context(ds, p, device_ingest=True)
+    assert (a.R, a.P, a.S, a.Ppad) == (b.R, b.P, b.S, b.Ppad)
+    assert np.array_equal(a.ray_offsets(), b.ray_offsets())
+    rng = np.random.default_rng(4)
+    for K in (1, 7, 60):
+        mdl = random_model(rng, K, box_of(ds))
+        Kb, cells = np.array([K], np.int32), np.stack(mdl)[None]
+        ra, rb = a.evaluate_batch(Kb, cells, want_owners=True), b.evaluate_batch(Kb, cells, want_owners=True)
+        assert np.array_equal(ra["owners"], rb["owners"])
+        assert ra["ptS"].tobytes() == rb["ptS"].tobytes() and ra["phi"].tobytes() == rb["phi"].tobytes()
+    outs = []
+    for ctx in (a, b):
+        ch = Chains(ctx, 4, seed=2, hist_cap=0)
+        ch.build_starting()
+        outs.append(ch.run(200, record=True, trace=True))
+        assert ch.verify() == (0, 0.0, 0.0)
+        ch.close()
+    assert outs[0]["recs"].tobytes() == outs[1]["recs"].tobytes() and outs[0]["phi"].tobytes() == outs[1]["phi"].tobytes()
+    a.close(); b.close()

@@ -17,10 +17,13 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 p = parameters()
 t0 = time.time(); ds = synthetic_rays(R, seed=3, p=p); t_gen = time.time() - t0
 t0 = time.time(); ctx = Context(ds, p); t_flat = time.time() - t0
+t0 = time.time(); ctx_dev = Context(ds, p, device_ingest=True); t_ingest = time.time() - t0
+assert (ctx_dev.P, ctx_dev.S) == (ctx.P, ctx.S)
+ctx_dev.close()
 box = (ds.xVec.min(), ds.xVec.max(), ds.yVec.min(), ds.yVec.max(), ds.zVec.min(), ds.zVec.max())
 fp64_peak, fp32_peak = ctx.peak_flops()
 rng = np.random.default_rng(0)
-out = dict(R=R, P=int(ctx.P), S=int(ctx.S), gen_s=t_gen, flatten_upload_s=t_flat, fp64_peak_tflops=fp64_peak, fp32_peak_tflops=fp32_peak, results=[])
+out = dict(R=R, P=int(ctx.P), S=int(ctx.S), gen_s=t_gen, flatten_upload_s=t_flat, device_ingest_s=t_ingest, fp64_peak_tflops=fp64_peak, fp32_peak_tflops=fp32_peak, results=[])
 for K, n in ((100, 4), (500, 2), (2000, 1)):
     cells = np.stack([rng.uniform(box[0], box[1], (n, K)), rng.uniform(box[2], box[3], (n, K)), rng.uniform(box[4], box[5], (n, K)),
                       rng.uniform(0, 50, (n, K))], 1)
