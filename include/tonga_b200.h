@@ -189,6 +189,18 @@ int tonga_chains_get_history(tonga_chains *ch, int32_t Kcap, int32_t *n_hist, in
  * three outputs across ranks (they are plain sums). */
 int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const double *X, const double *Y, const double *Z, double *sum_out,
                         double *sumsq_out, int64_t *count_out);
+/* ---- checkpoint / resume (TD_inversion_function.jl:40-67 load, :282-294 save).  The model part of a checkpoint is
+ * tonga_chains_get_state / tonga_chains_set_models; these carry the rest: the iteration count (= the Philox counter), the
+ * thinning phase model_num[nChains] (:276), the history slot awaiting its next action (-1 = none), the counters
+ * ([nChains][3][5], may be NULL) and the kept models (arrays exactly as tonga_chains_get_history returns them, Kcap =
+ * tonga_chains_kcap()).  A batch restored with set_models + set_progress + set_history continues bit-identically. */
+int tonga_chains_get_progress(tonga_chains *ch, int64_t *iter_done, int64_t *model_num, int32_t *pending_slot);
+int tonga_chains_set_progress(tonga_chains *ch, int64_t iter_done, const int64_t *model_num, const int32_t *pending_slot,
+                              const int64_t *counts);
+int tonga_chains_set_history(tonga_chains *ch, int32_t Kcap, const int32_t *n_hist, const int32_t *hist_K, const double *hist_cells,
+                             const double *hist_phi, const double *hist_ptS, const int64_t *hist_iter, const int32_t *hist_action,
+                             const int32_t *hist_accept, const int32_t *hist_next_action);
+
 /* Consistency check on the device: re-run the full evaluate for every chain's current model and compare it with the
  * incrementally maintained state.  owner_mismatch = number of points whose owner differs; max_dphi / max_dts =
  * largest |difference| in phi / t* (the two paths share their reduction order, so both should be exactly 0). */

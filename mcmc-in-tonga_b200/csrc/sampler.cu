@@ -694,6 +694,64 @@ extern "C" int tonga_chains_get_history(tonga_chains *ch, int32_t Kcap, int32_t 
     return TONGA_OK;
 }
 
+
+// ---- checkpoint / resume (TD_inversion_function.jl:40-67, 282-294): the model part is tonga_chains_get_state / set_models; these
+// entry points carry the rest of a chain's progress so that a resumed batch continues bit-identically.
+extern "C" int tonga_chains_get_progress(tonga_chains *ch, int64_t *iter_done, int64_t *model_num, int32_t *pending_slot) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_get_progress: NULL");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
+    const size_t n = (size_t)ch->n;
+    if (iter_done) *iter_done = ch->iter_done;
+    if (model_num) TG_CUDA(cudaMemcpy(model_num, ch->d_model_num, 8 * n, cudaMemcpyDeviceToHost));
+    if (pending_slot) TG_CUDA(cudaMemcpy(pending_slot, ch->d_pending, 4 * n, cudaMemcpyDeviceToHost));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_set_progress(tonga_chains *ch, int64_t iter_done, const int64_t *model_num, const int32_t *pending_slot,
+                                         const int64_t *counts) {
+    if (!ch || iter_done < 0) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_progress: bad argument");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
+    const size_t n = (size_t)ch->n;
+    if (pending_slot)
+        for (size_t i = 0; i < n; i++)
+            if (pending_slot[i] < -1 || pending_slot[i] >= ch->hist_cap)
+                return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_progress: pending_slot outside [-1, hist_cap)");
+    ch->iter_done = iter_done;
+    if (model_num) TG_CUDA(cudaMemcpy(ch->d_model_num, model_num, 8 * n, cudaMemcpyHostToDevice));
+    if (pending_slot) TG_CUDA(cudaMemcpy(ch->d_pending, pending_slot, 4 * n, cudaMemcpyHostToDevice));
+    if (counts) TG_CUDA(cudaMemcpy(ch->d_counts, counts, 8 * n * 15, cudaMemcpyHostToDevice));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_set_history(tonga_chains *ch, int32_t Kcap, const int32_t *n_hist, const int32_t *hist_K, const double *hist_cells,
+                                        const double *hist_phi, const double *hist_ptS, const int64_t *hist_iter, const int32_t *hist_action,
+                                        const int32_t *hist_accept, const int32_t *hist_next_action) {
+    if (!ch || !n_hist) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_history: bad argument");
+    tonga_ctx *ctx = ch->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    TG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t n = (size_t)ch->n, KC = (size_t)ch->KC, R = (size_t)ctx->R, H = (size_t)ch->hist_cap, nh = n * H;
+    for (size_t i = 0; i < n; i++)
+        if (n_hist[i] < 0) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_history: negative n_hist");
+    if (nh > 0 && hist_cells && Kcap != (int)KC) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_history: Kcap must equal tonga_chains_kcap()");
+    TG_CUDA(cudaMemcpy(ch->d_n_hist, n_hist, 4 * n, cudaMemcpyHostToDevice));
+    if (nh == 0) return TONGA_OK;
+    if (hist_K) TG_CUDA(cudaMemcpy(ch->d_hist_K, hist_K, 4 * nh, cudaMemcpyHostToDevice));
+    if (hist_cells) TG_CUDA(cudaMemcpy(ch->d_hist_cells, hist_cells, 8 * nh * 4 * KC, cudaMemcpyHostToDevice));
+    if (hist_phi) TG_CUDA(cudaMemcpy(ch->d_hist_phi, hist_phi, 8 * nh, cudaMemcpyHostToDevice));
+    if (hist_ptS) TG_CUDA(cudaMemcpy(ch->d_hist_ptS, hist_ptS, 8 * nh * R, cudaMemcpyHostToDevice));
+    if (hist_iter) TG_CUDA(cudaMemcpy(ch->d_hist_iter, hist_iter, 8 * nh, cudaMemcpyHostToDevice));
+    if (hist_action) TG_CUDA(cudaMemcpy(ch->d_hist_action, hist_action, 4 * nh, cudaMemcpyHostToDevice));
+    if (hist_accept) TG_CUDA(cudaMemcpy(ch->d_hist_accept, hist_accept, 4 * nh, cudaMemcpyHostToDevice));
+    if (hist_next_action) TG_CUDA(cudaMemcpy(ch->d_hist_next, hist_next_action, 4 * nh, cudaMemcpyHostToDevice));
+    return TONGA_OK;
+}
+
 extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, double *max_dphi, double *max_dts) {
     if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_verify: NULL");
     if (!ch->have_models) return tg::fail(TONGA_ERR_STATE, "tonga_chains_verify: no models yet");

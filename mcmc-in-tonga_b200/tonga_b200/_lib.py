@@ -70,6 +70,9 @@ SYMBOLS = {
     "tonga_chains_reset": (C.c_int, [_P]),
     "tonga_chains_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "tonga_chains_get_history": (C.c_int, [_P, C.c_int32, c_ip, c_ip, c_dp, c_dp, c_dp, c_lp, c_ip, c_ip, c_ip]),
+    "tonga_chains_get_progress": (C.c_int, [_P, c_lp, c_lp, c_ip]),
+    "tonga_chains_set_progress": (C.c_int, [_P, C.c_int64, c_lp, c_ip, c_lp]),
+    "tonga_chains_set_history": (C.c_int, [_P, C.c_int32, c_ip, c_ip, c_dp, c_dp, c_dp, c_lp, c_ip, c_ip, c_ip]),
     "tonga_chains_raster": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_lp]),
     "tonga_chains_verify": (C.c_int, [_P, c_lp, c_dp, c_dp]),
     "tonga_chains_kcap": (C.c_int, [_P]),

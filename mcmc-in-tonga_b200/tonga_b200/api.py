@@ -178,6 +178,7 @@ class Chains:
         batched forward model per proposal; any size), "streamed" (per-point state in HBM, one streaming pass per proposal; any
         ray set, 6 B per point and chain) or "auto" (resident when it fits, else streamed).  Same chains either way."""
         self.ctx, self.lib, self.n = ctx, ctx.lib, n_chains
+        self.chain_id0, self.seed = int(chain_id0), int(seed)
         p = ctx.params
         if hist_cap is None:  # num_models_per_chain, TD_inversion_function.jl:25
             hist_cap = int((p.n_iter - p.burn_in) / p.keep_each) + 1 if p.keep_each > 0 else 0
@@ -277,6 +278,34 @@ class Chains:
                                                 dp(out["ptS"]), lp(out["iter"]), ip(out["action"]), ip(out["accept"]),
                                                 ip(out["next_action"])))
         return out
+
+    def checkpoint(self) -> dict:
+        """Everything a resumed batch needs to continue bit-identically (TD_inversion_function.jl:282-294 saves model, iter,
+        saved_#, model_num, model_hist): the current models, the iteration count (= Philox counter), the thinning phase, the
+        counters and the kept models."""
+        st = self.state(want_ptS=False)
+        it = C.c_int64()
+        model_num = np.zeros(self.n, np.int64)
+        pending = np.zeros(self.n, np.int32)
+        check(self.lib.tonga_chains_get_progress(self._h, C.byref(it), lp(model_num), ip(pending)))
+        _, counts = self.stats()
+        hist = self.history()
+        return dict(K=st["K"], cells=st["cells"], noise=st["noise"], iter=np.int64(it.value), model_num=model_num, pending_slot=pending,
+                    counts=counts, seed=np.uint64(self.seed), chain_id0=np.int64(self.chain_id0), hist_cap=np.int64(self.hist_cap),
+                    **{"hist_" + k: v for k, v in hist.items()})
+
+    def restore(self, ck: dict):
+        """Inverse of checkpoint() on a batch created with the same context, chain count, chain_id0, seed and hist_cap."""
+        if int(ck["hist_cap"]) != self.hist_cap or len(ck["K"]) != self.n or int(ck["chain_id0"]) != self.chain_id0 or int(ck["seed"]) != self.seed:
+            raise TongaError(-1, "checkpoint does not belong to this batch (chain count, chain_id0, seed or hist_cap differ)")
+        self.set_models(ck["K"], ck["cells"][:, :, :self.KC], ck["noise"])
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        check(self.lib.tonga_chains_set_progress(self._h, int(ck["iter"]), lp(c(ck["model_num"], np.int64)), ip(c(ck["pending_slot"], np.int32)),
+                                                 lp(c(ck["counts"], np.int64))))
+        check(self.lib.tonga_chains_set_history(self._h, self.KC, ip(c(ck["hist_n_hist"], np.int32)), ip(c(ck["hist_K"], np.int32)),
+                                                dp(c(ck["hist_cells"], np.float64)), dp(c(ck["hist_phi"], np.float64)), dp(c(ck["hist_ptS"], np.float64)),
+                                                lp(c(ck["hist_iter"], np.int64)), ip(c(ck["hist_action"], np.int32)), ip(c(ck["hist_accept"], np.int32)),
+                                                ip(c(ck["hist_next_action"], np.int32))))
 
     def raster(self, X, Y, Z):
         """plot_model_hist's accumulation (MCsub.jl:753-825) at arbitrary nodes -> (sum, sumsq, count) over all kept models."""

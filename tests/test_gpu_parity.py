@@ -858,3 +858,53 @@ def test_device_ingest_matches_host_flatten(tonga, which):
         ch.close()
     assert outs[0]["recs"].tobytes() == outs[1]["recs"].tobytes() and outs[0]["phi"].tobytes() == outs[1]["phi"].tobytes()
     a.close(); b.close()
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint / resume (N3)
+@pytest.mark.parametrize("kind", ["resident", "streamed"])
+def test_checkpoint_resume_is_bit_identical(tonga, tmp_path, kind):
+    """TD_inversion_function.jl:40-67 / :282-294: a batch saved mid-run and resumed in a new object continues exactly like the
+    uninterrupted run (same Philox streams, thinning phase, counters, history incl. the pending next_action)."""
+    import copy
+    from tonga_b200 import checkpoint as ckpt
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 300.0, 100.0, 7.0
+    ctx = Context(ds, p)
+    a = Chains(ctx, 6, chain_id0=2, seed=77, sampler=kind)
+    a.build_starting()
+    ta = a.run(300, trace=True)
+    b = Chains(ctx, 6, chain_id0=2, seed=77, sampler=kind)
+    b.build_starting()
+    tb1 = b.run(143, trace=True)  # stops right after a kept model (iter 100 + 6*7 = 142 is kept at model_num 43? any phase must work)
+    ckpt.save_checkpoint(str(tmp_path / "batch.npz"), b)
+    b.close()
+    ck = ckpt.load_checkpoint(str(tmp_path / "batch.npz"))
+    assert int(ck["iter"]) == 143 and bool(ck["burnin"])
+    c = ckpt.resume(ctx, ck)
+    assert c.sampler == kind
+    tb2 = c.run(157, trace=True)
+    for key in ("accept", "phi", "K"):
+        assert np.concatenate([tb1[key], tb2[key]], 1).tobytes() == ta[key].tobytes(), key
+    sa, sc = a.state(), c.state()
+    assert sa["phi"].tobytes() == sc["phi"].tobytes() and sa["ptS"].tobytes() == sc["ptS"].tobytes() and np.array_equal(sa["K"], sc["K"])
+    ha, hc = a.history(), c.history()
+    for key in ha:
+        if key == "cells":
+            for i in range(6):
+                for j in range(ha["n_hist"][i]):
+                    k = ha["K"][i, j]
+                    assert np.array_equal(ha["cells"][i, j, :, :k], hc["cells"][i, j, :, :k])
+        else:
+            assert ha[key].tobytes() == hc[key].tobytes(), key
+    assert a.stats()[0] == c.stats()[0] == 300 and np.array_equal(a.stats()[1], c.stats()[1])
+    assert c.verify() == (0, 0.0, 0.0)
+    # model.jld-equivalent export
+    n = ckpt.export_model_hist(str(tmp_path / "model_hist.bin"), hc, likelihood=1.5)
+    back = ckpt.import_model_hist(str(tmp_path / "model_hist.bin"))
+    assert n == int(hc["n_hist"].sum()) and len(back) == 6
+    m0 = back[3][5]
+    assert m0["K"] == hc["K"][3, 5] and m0["phi"] == hc["phi"][3, 5] and np.array_equal(m0["ptS"], hc["ptS"][3, 5])
+    assert np.array_equal(m0["cells"], hc["cells"][3, 5, :, :m0["K"]])
+    a.close(); c.close(); ctx.close()

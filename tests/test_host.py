@@ -86,3 +86,30 @@ def test_product_never_imports_the_oracle():
         for f in fs:
             if f.endswith((".py", ".cu", ".cuh", ".jl", ".h", "Makefile")):
                 assert not pat.search(open(os.path.join(dp_, f)).read()), f"{f} references the oracle"
+
+
+def test_model_hist_export_round_trip(tmp_path):
+    """checkpoint.export_model_hist / import_model_hist (the layout julia/model_hist_to_jld.jl reads), incl. the reference's
+    action/accept aliasing."""
+    from tonga_b200 import checkpoint as ckpt
+    rng = np.random.default_rng(0)
+    n, H, KC, R = 3, 4, 8, 5
+    hist = dict(n_hist=np.array([4, 2, 6], np.int32), K=rng.integers(1, KC + 1, (n, H)).astype(np.int32), cells=rng.normal(size=(n, H, 4, KC)),
+                phi=rng.normal(size=(n, H)), ptS=rng.normal(size=(n, H, R)), iter=np.zeros((n, H), np.int64),
+                action=rng.integers(1, 5, (n, H)).astype(np.int32), accept=rng.integers(0, 2, (n, H)).astype(np.int32),
+                next_action=rng.integers(0, 5, (n, H)).astype(np.int32))
+    path = str(tmp_path / "mh.bin")
+    assert ckpt.export_model_hist(path, hist, likelihood=-2.0) == 4 + 2 + 4  # n_hist beyond the capacity is clipped
+    back = ckpt.import_model_hist(path)
+    assert [len(b) for b in back] == [4, 2, 4]
+    for c in range(n):
+        for j, m in enumerate(back[c]):
+            k = hist["K"][c, j]
+            assert m["K"] == k and m["action"] == hist["action"][c, j] and m["accept"] == hist["accept"][c, j] and m["likelihood"] == -2.0
+            assert np.array_equal(m["cells"], hist["cells"][c, j, :, :k]) and np.array_equal(m["ptS"], hist["ptS"][c, j])
+    ckpt.export_model_hist(path, hist, likelihood=0.0, reference_aliasing=True)
+    back = ckpt.import_model_hist(path)
+    for c in range(n):
+        for j, m in enumerate(back[c]):
+            nxt = hist["next_action"][c, j]
+            assert m["accept"] == 0 and m["action"] == (nxt if nxt > 0 else hist["action"][c, j])
