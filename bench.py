@@ -276,7 +276,7 @@ def main():
                        "l2": "256 MB buffer written between timed steps (L2 flush)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_t / args.steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,  # per step: tg_order_kernel (launch order by nCells) + tg_sampler_kernel
             "clocks": clocks,
             "roofline": roof,
             "acceptance": {"birth_death_change_move": acc_rate, "evaluated_fraction": float(c[2].sum() / max(c[0].sum(), 1)),

@@ -20,6 +20,7 @@
 // (tonga_chains_verify checks that on the device).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tonga_internal.cuh"
@@ -76,6 +77,22 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
             zt = 0.0 + pm.zeta_scale * (sqrt(-2.0 * log(b0)) * cs);
         } else zt = -log(b0) * pm.zeta_scale;  // :108
         c[3 * KC + i] = zt;
+    }
+}
+
+// CTA -> chain order of the resident sampler.  A chain's cost per iteration falls with its nCells (fewer, larger cells: more
+// points change owner, more rays are re-integrated), and the launch lasts as long as its slowest SM.  CTAs are dealt to the
+// SMs round-robin in launch order, so launching the chains sorted by K gives every SM one chain of every cost tier.
+// perm[rank] = chain, rank = number of chains with smaller (K, index).
+__global__ void tg_order_kernel(int n, const int32_t *__restrict__ K, int32_t *__restrict__ perm) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const int kc = K[c];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const int kj = K[j];
+            rank += (kj < kc) || (kj == kc && j < c);
+        }
+        perm[rank] = c;
     }
 }
 
@@ -180,6 +197,7 @@ struct tonga_chains {
     bool wide = false;      // wide or streamed sampler (wide_kernels.cuh): lock-step launches per iteration, candidate models in global memory
     bool streamed = false;  // streamed sampler: per-point chain state (u16 owner, fl32 owner distance) in HBM, updated incrementally
     int exact_only = 0;
+    bool no_order = false;  // TONGA_NO_ORDER=1 in the environment: identity launch order (A/B measurements)
     long long *d_prof = nullptr;  // optional per-phase cycle counters (tonga_chains_profile)
     size_t smem = 0;
     // device state
@@ -189,6 +207,7 @@ struct tonga_chains {
     float *d_dcache = nullptr, *d_dcache_tmp = nullptr;  // [n][Ppad] fl32 squared distance of every point to its owner
     long long *d_counts = nullptr;
     int32_t *d_pending = nullptr;
+    int32_t *d_perm = nullptr;  // resident sampler: launch order
     int32_t *d_n_hist = nullptr;
     long long *d_model_num = nullptr;
     int32_t *d_hist_K = nullptr;
@@ -276,6 +295,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->chain_id0 = chain_id0;
     ch->seed = seed;
     ch->wide = wide;
+    ch->no_order = std::getenv("TONGA_NO_ORDER") != nullptr;
     ch->streamed = streamed;
     ch->stream_smem = stream_smem;
     ch->smem = wide ? 0 : smem_res;
@@ -314,6 +334,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     }
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
+    TG_ALLOC(ch->d_perm, 4 * n);
     TG_ALLOC(ch->d_n_hist, 4 * n);
     TG_ALLOC(ch->d_model_num, 8 * n);
     TG_ALLOC(ch->d_hist_K, 4 * n * H);
@@ -381,7 +402,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
                     ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active};
+                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active};
     for (void *p : ptrs) cudaFree(p);
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
@@ -556,6 +577,10 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.hist_cap = ch->hist_cap; a.n_hist = ch->d_n_hist; a.model_num = ch->d_model_num;
     a.hist_K = ch->d_hist_K; a.hist_cells = ch->d_hist_cells; a.hist_phi = ch->d_hist_phi; a.hist_ptS = ch->d_hist_ptS;
     a.hist_iter = ch->d_hist_iter; a.hist_action = ch->d_hist_action; a.hist_accept = ch->d_hist_accept; a.hist_next = ch->d_hist_next;
+    if (ch->n <= 16384 && !ch->no_order) {
+        tg::tg_order_kernel<<<(ch->n + 255) / 256, 256, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
+        a.perm = ch->d_perm;
+    }
     if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
         if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
         else tg::tg_sampler_kernel<uint32_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);

@@ -27,6 +27,7 @@ struct SamplerArgs {
     int R, Rp, KC, ldT;
     int P, Ppad;
     int n_sm;  // SM count (leader-warp rotation)
+    const int32_t *perm;  // CTA -> chain: chains sorted by expected cost so that every SM hosts the same mix (NULL = identity)
     tonga_params prm;
     // chain state (global)
     int32_t *K;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     const int lead = 0;  // (rotating the leader with blockIdx.x / n_sm was measured: phase A shrinks, phase B grows by as much)
     const int vtid = (tid - lead * 32) & (ST - 1), vwarp = vtid >> 5;  // virtual ids: the leader is virtual warp 0
     QT *s_queue = reinterpret_cast<QT *>(smem + L.o_queue) + warp * SQ_CAP;
-    const int chain = blockIdx.x;
+    const int chain = a.perm ? a.perm[blockIdx.x] : (int)blockIdx.x;  // launch order = cost order (tg_order_kernel)
     const int KC = a.KC, R = a.R;
     float *__restrict__ dcache = a.dcache + (size_t)chain * a.Ppad;
     const int nOwnWords = a.Ppad / 4, nMaskWords = a.Ppad / 32, nDirtyWords = (a.Rp + 31) / 32;
