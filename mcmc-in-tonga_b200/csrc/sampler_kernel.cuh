@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                         }
                     }
                 }
+                tick(8);  // profile slot 8 = B1, slot 1 = B2 (+ barrier)
                 // ======================================================== B2: rescan this warp's orphans, 32 at a time
                 if (act == 2 || act == 4) {
                     __syncwarp();
