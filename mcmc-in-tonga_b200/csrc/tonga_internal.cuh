@@ -141,7 +141,7 @@ struct Philox {
     }
     __host__ __device__ inline void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
         uint32_t ka = k0, kb = k1;
-#pragma unroll
+#pragma unroll 1  // rolled: the sampler kernel is instruction-cache sensitive (profiles/README.md) and the draw is off the hot loops
         for (int i = 0; i < 10; i++) {
             uint32_t h0, l0, h1, l1;
             mulhilo(0xD2511F53u, c0, h0, l0);

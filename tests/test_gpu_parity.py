@@ -908,3 +908,35 @@ def test_checkpoint_resume_is_bit_identical(tonga, tmp_path, kind):
     assert m0["K"] == hc["K"][3, 5] and m0["phi"] == hc["phi"][3, 5] and np.array_equal(m0["ptS"], hc["ptS"][3, 5])
     assert np.array_equal(m0["cells"], hc["cells"][3, 5, :, :m0["K"]])
     a.close(); c.close(); ctx.close()
+
+
+def test_device_normal_deviates_are_standard_normal(tonga):
+    """The device draws its Gaussian proposal steps by inversion (AS 241, proposal.cuh): the first-iteration change / move steps
+    of many chains, normalised by their proposal widths, must be N(0, 1) (Kolmogorov-Smirnov, mean, variance, tails)."""
+    from scipy import stats
+    from tonga_b200.api import Chains, Context
+    ds, p = tonga
+    ctx = Context(ds, p)
+    n = 16384
+    ch = Chains(ctx, n, seed=123, hist_cap=0)
+    ch.build_starting()
+    st0 = ch.state(want_ptS=False)
+    recs = ch.run(1, record=True)["recs"][:, 0]
+    sig_zeta = p.zeta_scale * p.sig / 100
+    idx = recs["idx"]
+    chg = recs["action"] == 3
+    z = (recs["zeta"][chg] - st0["cells"][chg, 3, idx[chg]]) / sig_zeta
+    mv = recs["action"] == 4
+    box = box_of(ds)
+    zs = [z]
+    for a, key, lo, hi in ((0, "x", box[0], box[1]), (1, "y", box[2], box[3]), (2, "z", box[4], box[5])):
+        zs.append((recs[key][mv] - st0["cells"][mv, a, idx[mv]]) / ((p.sig / 100) * (hi - lo)))
+    for k, v in enumerate(zs):
+        assert len(v) > 3000
+        assert abs(v.mean()) < 4 / np.sqrt(len(v)) and abs(v.var() - 1) < 4 * np.sqrt(2 / len(v))
+        assert stats.kstest(v, "norm").pvalue > 1e-3, f"component {k}"
+        assert 0.03 < (np.abs(v) > 2).mean() < 0.06  # P(|Z| > 2) = 0.0455: the tail branch of the inversion
+    # the three move components are independent draws
+    c = np.corrcoef(np.stack(zs[1:]))
+    assert np.abs(c[np.triu_indices(3, 1)]).max() < 5 / np.sqrt(len(zs[1]))
+    ch.close(); ctx.close()

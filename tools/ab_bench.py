@@ -23,11 +23,12 @@ ms = []
 for _ in range(5):
     ch.run(1000); ms.append(ch.last_kernel_ms())
 print("%(tag)s", "%%.2f M/s" %% (1024 * 1000 / np.median(ms) / 1e3), ["%%.1f" %% m for m in ms])
-ch.profile(True); ch.run(1000); cyc = ch.profile(False, read=True)
-print("   cycles/iter A,B,C,D+E,F4,G,F1,F2:", (cyc[:, :8].mean(0) / 1000).round(0))
+if os.environ.get("AB_PROFILE"):
+    ch.profile(True); ch.run(1000); cyc = ch.profile(False, read=True)
+    print("   cycles/iter A,B,C,D+E,F4,G,F1,F2:", (cyc[:, :8].mean(0) / 1000).round(0))
 '''
 root = os.path.dirname(HERE)
-for rep in range(2):
+for rep in range(int(os.environ.get('REPS', '2'))):
     for lib in sys.argv[1:]:
         path = os.path.abspath(lib)
         subprocess.run([sys.executable, "-c", CHILD % {"root": root, "lib": path, "tag": os.path.basename(lib)}], check=True)
