@@ -95,7 +95,7 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
                                              const double *nzeta, int K, double noise, const tonga_params &pm, double sig_zeta, int lane) {
     pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
     pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
-    double uu[8];
+    double uu[8], nrm[3];
     if (mode == 0) {
         const Philox philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
         uint32_t w[4] = {0, 0, 0, 0};
@@ -110,6 +110,12 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
         const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
         const int act0 = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
         pr.action = act0 > nact ? nact : act0;
+        // the (up to) three Gaussian steps of the proposal: one inversion, lanes 0..2 in parallel -- a single copy of the code
+        // whatever the action (the kernel is instruction-cache bound, profiles/README.md)
+        const double nl = normal_icdf(lane == 0 ? uu[4] : (lane == 1 ? uu[5] : uu[6]));
+        nrm[0] = __shfl_sync(0xffffffffu, nl, 0);
+        nrm[1] = __shfl_sync(0xffffffffu, nl, 1);
+        nrm[2] = __shfl_sync(0xffffffffu, nl, 2);
     } else {
         const tonga_proposal rec = *rec_in;
         pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
@@ -119,15 +125,15 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
     if (act == 1) {  // ---- birth :76-125
         if (K < pm.max_cells) {
             if (mode == 0) {
-                pr.x = uu[2] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
-                pr.y = uu[3] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
-                pr.z = uu[4] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
+                pr.x = uu[1] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
+                pr.y = uu[2] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
+                pr.z = uu[3] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
             }
             const int ci = warp_nearest<SPACE>(nx, ny, nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
             const double czeta = ci < 0 ? 0.0 : nzeta[ci];
             pr.aux = czeta;
             if (mode == 0) {
-                pr.zeta = czeta + sig_zeta * normal_icdf(uu[5]);  // :82
+                pr.zeta = czeta + sig_zeta * nrm[0];  // :82
                 pr.u = uu[7];                     // :121
             }
             if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
@@ -152,7 +158,7 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
         if (mode == 0) {
             const int k = (int)floor(uu[1] * K);  // :184
             pr.idx = k >= K ? K - 1 : k;
-            pr.zeta = nzeta[pr.idx] + sig_zeta * normal_icdf(uu[2]);  // :188
+            pr.zeta = nzeta[pr.idx] + sig_zeta * nrm[0];  // :188
             pr.u = uu[7];                             // :214
         }
         if (pr.idx >= 0 && pr.idx < K) {
@@ -166,7 +172,7 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
             if (mode == 0) {
                 const int k = (int)floor(uu[1] * K);  // :222
                 pr.idx = k >= K ? K - 1 : k;
-                const double n0 = normal_icdf(uu[2]), n1 = normal_icdf(uu[3]), n2 = normal_icdf(uu[4]);
+                const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
                 pr.x = nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
                 pr.y = ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
                 pr.z = nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
@@ -180,7 +186,7 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
         }
     } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
         if (mode == 0) {
-            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * normal_icdf(uu[2]);  // :23,:254
+            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * nrm[0];  // :23,:254
             pr.u = uu[7];
         }
         valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
