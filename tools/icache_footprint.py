@@ -42,5 +42,7 @@ def agg_file(c):
 print("cold by file:", agg_file(cold)); print("hot by file:", agg_file(hot))
 print("\ncold code, largest source lines:")
 for (f, l), v in cold.most_common(30): print(f"  {f}:{l}  {v} SASS   no_inst samples {100 * noinst[(f, l)] / tot_ni:.1f}%")
+print("\nhot code, largest source lines:")
+for (f, l), v in hot.most_common(25): print(f"  {f}:{l}  {v} SASS   no_inst samples {100 * noinst[(f, l)] / tot_ni:.1f}%")
 print("\nno_instruction stall samples by line:")
 for (f, l), v in noinst.most_common(15): print(f"  {f}:{l}  {100 * v / tot_ni:.1f}%  (cold {cold[(f, l)]}, hot {hot[(f, l)]} SASS)")
