@@ -218,7 +218,10 @@ def main():
     st = ch.state(want_ptS=False)
     K0 = pinned_empty(st["K"].shape, np.int32); K0[:] = st["K"]
     cells0 = pinned_empty(st["cells"].shape, np.float64); cells0[:] = st["cells"]
-    hist_buf, state_buf = ch.alloc_buffers(pinned=True)  # page-locked host buffers, reused every step
+    # The e2e batch keeps its history in mapped page-locked host memory (TONGA_HISTORY_ON_HOST): the sampler stores every kept
+    # model straight into host memory while it runs, so the step's model_hist is on the host when the run returns.
+    che = Chains(ctx, n, chain_id0=rank * n, seed=args.seed, host_history=True)
+    _, state_buf = che.alloc_buffers(pinned=True)  # page-locked host buffers for the final models, reused every step
     h2d = K0.nbytes + cells0.nbytes
     d2h = 0
     e2e_t = 0.0
@@ -226,18 +229,21 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        ch.reset()
-        ch.set_models(K0, cells0)          # H2D of the start models + full evaluate
-        ch.run(args.iters)                 # the proposal loop
-        hist = ch.history(out=hist_buf)    # D2H of model_hist (nuclei, zeta, phi, ptS of every kept model)
-        fin = ch.state(out=state_buf)      # D2H of the final models
+        che.reset()
+        che.set_models(K0, cells0)         # H2D of the start models + full evaluate
+        che.run(args.iters)                # the proposal loop; kept models stream to host memory as they are produced
+        hist = che.history()               # model_hist (nuclei, zeta, phi, ptS of every kept model): already in host memory
+        fin = che.state(out=state_buf)     # D2H of the final models
+        chk = float(hist["phi"][:, 0].sum()) + float(fin["phi"].sum())  # the host reads the step's result
         t1 = time.perf_counter()
         tt = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if i >= 2:
             e2e_t += float(tt.item())
-        d2h = sum(v.nbytes for v in hist.values() if v is not None) + sum(v.nbytes for v in fin.values() if v is not None)
+        kept = int(np.minimum(hist["n_hist"], che.hist_cap).sum())
+        d2h = kept * (32 * che.KC + 8 * ctx.R + 36) + sum(v.nbytes for v in fin.values() if v is not None)  # bytes the GPU wrote to host memory
+    assert np.isfinite(chk)
     e2e_val = float(n) * world * args.iters * args.steps / e2e_t
     n_kept = int(hist["n_hist"].min())
 

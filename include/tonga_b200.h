@@ -136,8 +136,15 @@ int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int
 #define TONGA_SAMPLER_RESIDENT 1
 #define TONGA_SAMPLER_WIDE 2
 #define TONGA_SAMPLER_STREAMED 3
+/* OR-ed into `sampler`: keep the history (kept models) in mapped page-locked HOST memory.  The kernels then store every kept
+ * model straight into host memory while they run (contiguous posted writes over PCIe), so no device-to-host copy of the
+ * history follows a run; tonga_chains_history_host returns the arrays (same layouts as tonga_chains_get_history with
+ * Kcap = tonga_chains_kcap(); valid until the batch is destroyed, stable after any call that synchronises). */
+#define TONGA_HISTORY_ON_HOST 0x100
 int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                            int32_t hist_cap, int32_t sampler);
+int tonga_chains_history_host(tonga_chains *ch, void **hist_K, void **hist_cells, void **hist_phi, void **hist_ptS, void **hist_iter,
+                              void **hist_action, void **hist_accept, void **hist_next_action);
 /* TONGA_SAMPLER_RESIDENT, _WIDE or _STREAMED (0 for NULL) */
 int tonga_chains_sampler(const tonga_chains *ch);
 void tonga_chains_destroy(tonga_chains *ch);

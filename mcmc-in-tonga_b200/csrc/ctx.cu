@@ -213,6 +213,11 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     chk(upload(&ctx->d_rayid, rayid, ctx->stream));
     chk(upload(&ctx->d_ray_off, sray_off, ctx->stream));
     chk(upload(&ctx->d_ray_orig, ray_orig, ctx->stream));
+    {
+        std::vector<int32_t> ray_rank(R);
+        for (int rs = 0; rs < R; rs++) ray_rank[ray_orig[rs]] = rs;
+        chk(upload(&ctx->d_ray_rank, ray_rank, ctx->stream));
+    }
     chk(upload(&ctx->d_point_orig, point_orig, ctx->stream));
     chk(upload(&ctx->d_tS, tS_s, ctx->stream));
     chk(upload(&ctx->d_sig, sig_s, ctx->stream));
@@ -232,7 +237,7 @@ extern "C" void tonga_destroy(tonga_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dtT);
     cudaFree(ctx->d_pxf); cudaFree(ctx->d_pyf); cudaFree(ctx->d_pzf);
-    cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_ray_orig); cudaFree(ctx->d_point_orig);
+    cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_ray_orig); cudaFree(ctx->d_ray_rank); cudaFree(ctx->d_point_orig);
     cudaFree(ctx->d_tS); cudaFree(ctx->d_sig);
     cudaFree(ctx->d_tiles);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);

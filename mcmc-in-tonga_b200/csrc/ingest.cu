@@ -181,8 +181,10 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
         TG_CUDA(cudaMemcpyAsync(*dptr, h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice, s));
         return TONGA_OK;
     };
+    std::vector<int32_t> ray_rank(R);
+    for (int rs = 0; rs < R; rs++) ray_rank[ray_orig[rs]] = rs;
     int rc;
-    if ((rc = up(&ctx->d_ray_off, sray_off)) || (rc = up(&ctx->d_ray_orig, ray_orig)) || (rc = up(&ctx->d_tS, tS_s)) ||
+    if ((rc = up(&ctx->d_ray_rank, ray_rank)) || (rc = up(&ctx->d_ray_off, sray_off)) || (rc = up(&ctx->d_ray_orig, ray_orig)) || (rc = up(&ctx->d_tS, tS_s)) ||
         (rc = up(&ctx->d_sig, sig_s)) || (rc = up(&ctx->d_tiles, tiles)))
         return rc;
     int32_t *d_ray_off_orig = nullptr;  // offsets in the caller's ray order (for point_orig); freed below

@@ -194,6 +194,8 @@ struct tonga_chains {
     unsigned long long seed = 0;
     long long iter_done = 0;
     bool have_models = false;
+    bool host_history = false;  // history arrays live in mapped page-locked host memory: the kernels store the kept models straight
+                                // into host memory during the run (posted PCIe writes), no device-to-host copy afterwards
     bool wide = false;      // wide or streamed sampler (wide_kernels.cuh): lock-step launches per iteration, candidate models in global memory
     bool streamed = false;  // streamed sampler: per-point chain state (u16 owner, fl32 owner distance) in HBM, updated incrementally
     int exact_only = 0;
@@ -248,6 +250,8 @@ extern "C" int tonga_chains_create(tonga_ctx *ctx, tonga_chains **out, int32_t n
 
 extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_t nChains, int64_t chain_id0, uint64_t seed,
                                       int32_t hist_cap, int32_t sampler) {
+    const bool host_history = (sampler & TONGA_HISTORY_ON_HOST) != 0;
+    sampler &= ~TONGA_HISTORY_ON_HOST;
     if (!ctx || !out || nChains < 1 || hist_cap < 0 || sampler < TONGA_SAMPLER_AUTO || sampler > TONGA_SAMPLER_STREAMED)
         return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: bad argument");
     *out = nullptr;
@@ -295,6 +299,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->chain_id0 = chain_id0;
     ch->seed = seed;
     ch->wide = wide;
+    ch->host_history = host_history;
     ch->no_order = std::getenv("TONGA_NO_ORDER") != nullptr;
     ch->streamed = streamed;
     ch->stream_smem = stream_smem;
@@ -337,14 +342,20 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     TG_ALLOC(ch->d_perm, 4 * n);
     TG_ALLOC(ch->d_n_hist, 4 * n);
     TG_ALLOC(ch->d_model_num, 8 * n);
-    TG_ALLOC(ch->d_hist_K, 4 * n * H);
-    TG_ALLOC(ch->d_hist_cells, 8 * n * H * 4 * KC);
-    TG_ALLOC(ch->d_hist_phi, 8 * n * H);
-    TG_ALLOC(ch->d_hist_ptS, 8 * n * H * R);
-    TG_ALLOC(ch->d_hist_iter, 8 * n * H);
-    TG_ALLOC(ch->d_hist_action, 4 * n * H);
-    TG_ALLOC(ch->d_hist_accept, 4 * n * H);
-    TG_ALLOC(ch->d_hist_next, 4 * n * H);
+#define TG_HIST_ALLOC(ptr, bytes)                                                                                              \
+    do {                                                                                                                       \
+        if (host_history) TG_CUDA(cudaHostAlloc((void **)&(ptr), tg_nz(bytes), cudaHostAllocMapped | cudaHostAllocPortable));   \
+        else TG_ALLOC(ptr, bytes);                                                                                             \
+    } while (0)
+    TG_HIST_ALLOC(ch->d_hist_K, 4 * n * H);
+    TG_HIST_ALLOC(ch->d_hist_cells, 8 * n * H * 4 * KC);
+    TG_HIST_ALLOC(ch->d_hist_phi, 8 * n * H);
+    TG_HIST_ALLOC(ch->d_hist_ptS, 8 * n * H * R);
+    TG_HIST_ALLOC(ch->d_hist_iter, 8 * n * H);
+    TG_HIST_ALLOC(ch->d_hist_action, 4 * n * H);
+    TG_HIST_ALLOC(ch->d_hist_accept, 4 * n * H);
+    TG_HIST_ALLOC(ch->d_hist_next, 4 * n * H);
+#undef TG_HIST_ALLOC
     TG_ALLOC(ch->d_ptS_tmp, 8 * n * R);
     TG_ALLOC(ch->d_phi_tmp, 8 * n);
     TG_ALLOC(ch->d_mism, 8);
@@ -400,10 +411,14 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     cudaSetDevice(ch->ctx->device);
     cudaStreamSynchronize(ch->ctx->stream);
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
-                    ch->d_n_hist, ch->d_model_num, ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter,
-                    ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
+                    ch->d_n_hist, ch->d_model_num, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
                     ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active};
     for (void *p : ptrs) cudaFree(p);
+    void *hist[] = {ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter, ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next};
+    for (void *p : hist) {
+        if (ch->host_history) cudaFreeHost(p);
+        else cudaFree(p);
+    }
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
@@ -524,7 +539,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     if (ch->wide) {
         tg::WideArgs w{};
         w.prm = ctx->prm; w.R = ctx->R; w.Rp = ch->Rp; w.KC = ch->KC; w.mode = mode; w.hist_cap = ch->hist_cap; w.nIter = nIter;
-        w.seed = ch->seed; w.chain_id0 = ch->chain_id0; w.ray_orig = ctx->d_ray_orig; w.tS = ctx->d_tS; w.sig = ctx->d_sig;
+        w.seed = ch->seed; w.chain_id0 = ch->chain_id0; w.ray_orig = ctx->d_ray_orig; w.ray_rank = ctx->d_ray_rank; w.tS = ctx->d_tS; w.sig = ctx->d_sig;
         w.K = ch->d_K; w.cells = ch->d_cells; w.phi = ch->d_phi; w.noise = ch->d_noise; w.beta = ch->d_beta; w.tstar = ch->d_tstar;
         w.counts = ch->d_counts; w.pending_slot = ch->d_pending;
         w.Kc = ch->d_Kc; w.cells_c = ch->d_cells_c; w.ptS_c = ch->d_ptS_tmp; w.props = ch->d_props;
@@ -566,7 +581,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     a.pxf = ctx->d_pxf; a.pyf = ctx->d_pyf; a.pzf = ctx->d_pzf; a.tol_alpha = ctx->tol_alpha; a.tol_beta2 = ctx->tol_beta2;
     a.exact_only = ch->exact_only;
     a.prof = ch->d_prof;
-    a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig;
+    a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig; a.ray_rank = ctx->d_ray_rank;
     a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad; a.n_sm = ctx->sm_count > 0 ? ctx->sm_count : 1;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
@@ -698,24 +713,24 @@ extern "C" int tonga_chains_get_history(tonga_chains *ch, int32_t Kcap, int32_t 
     const size_t n = (size_t)ch->n, KC = (size_t)ch->KC, R = (size_t)ctx->R, H = (size_t)ch->hist_cap, nh = n * H;
     if (n_hist) TG_CUDA(cudaMemcpy(n_hist, ch->d_n_hist, 4 * n, cudaMemcpyDeviceToHost));
     if (nh == 0) return TONGA_OK;
-    if (hist_K) TG_CUDA(cudaMemcpy(hist_K, ch->d_hist_K, 4 * nh, cudaMemcpyDeviceToHost));
+    if (hist_K) TG_CUDA(cudaMemcpy(hist_K, ch->d_hist_K, 4 * nh, cudaMemcpyDefault));
     if (hist_cells) {
         if (Kcap == (int)KC) {
-            TG_CUDA(cudaMemcpy(hist_cells, ch->d_hist_cells, 8 * nh * 4 * KC, cudaMemcpyDeviceToHost));
+            TG_CUDA(cudaMemcpy(hist_cells, ch->d_hist_cells, 8 * nh * 4 * KC, cudaMemcpyDefault));
         } else {
             if (Kcap < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_get_history: Kcap < 1");
             std::vector<double> hc(nh * 4 * KC);
-            TG_CUDA(cudaMemcpy(hc.data(), ch->d_hist_cells, 8 * nh * 4 * KC, cudaMemcpyDeviceToHost));
+            TG_CUDA(cudaMemcpy(hc.data(), ch->d_hist_cells, 8 * nh * 4 * KC, cudaMemcpyDefault));
             const size_t kc = std::min((size_t)Kcap, KC);
             for (size_t i = 0; i < nh * 4; i++) std::memcpy(hist_cells + i * (size_t)Kcap, &hc[i * KC], 8 * kc);
         }
     }
-    if (hist_phi) TG_CUDA(cudaMemcpy(hist_phi, ch->d_hist_phi, 8 * nh, cudaMemcpyDeviceToHost));
-    if (hist_ptS) TG_CUDA(cudaMemcpy(hist_ptS, ch->d_hist_ptS, 8 * nh * R, cudaMemcpyDeviceToHost));
-    if (hist_iter) TG_CUDA(cudaMemcpy(hist_iter, ch->d_hist_iter, 8 * nh, cudaMemcpyDeviceToHost));
-    if (hist_action) TG_CUDA(cudaMemcpy(hist_action, ch->d_hist_action, 4 * nh, cudaMemcpyDeviceToHost));
-    if (hist_accept) TG_CUDA(cudaMemcpy(hist_accept, ch->d_hist_accept, 4 * nh, cudaMemcpyDeviceToHost));
-    if (hist_next_action) TG_CUDA(cudaMemcpy(hist_next_action, ch->d_hist_next, 4 * nh, cudaMemcpyDeviceToHost));
+    if (hist_phi) TG_CUDA(cudaMemcpy(hist_phi, ch->d_hist_phi, 8 * nh, cudaMemcpyDefault));
+    if (hist_ptS) TG_CUDA(cudaMemcpy(hist_ptS, ch->d_hist_ptS, 8 * nh * R, cudaMemcpyDefault));
+    if (hist_iter) TG_CUDA(cudaMemcpy(hist_iter, ch->d_hist_iter, 8 * nh, cudaMemcpyDefault));
+    if (hist_action) TG_CUDA(cudaMemcpy(hist_action, ch->d_hist_action, 4 * nh, cudaMemcpyDefault));
+    if (hist_accept) TG_CUDA(cudaMemcpy(hist_accept, ch->d_hist_accept, 4 * nh, cudaMemcpyDefault));
+    if (hist_next_action) TG_CUDA(cudaMemcpy(hist_next_action, ch->d_hist_next, 4 * nh, cudaMemcpyDefault));
     return TONGA_OK;
 }
 
@@ -766,14 +781,14 @@ extern "C" int tonga_chains_set_history(tonga_chains *ch, int32_t Kcap, const in
     if (nh > 0 && hist_cells && Kcap != (int)KC) return tg::fail(TONGA_ERR_ARG, "tonga_chains_set_history: Kcap must equal tonga_chains_kcap()");
     TG_CUDA(cudaMemcpy(ch->d_n_hist, n_hist, 4 * n, cudaMemcpyHostToDevice));
     if (nh == 0) return TONGA_OK;
-    if (hist_K) TG_CUDA(cudaMemcpy(ch->d_hist_K, hist_K, 4 * nh, cudaMemcpyHostToDevice));
-    if (hist_cells) TG_CUDA(cudaMemcpy(ch->d_hist_cells, hist_cells, 8 * nh * 4 * KC, cudaMemcpyHostToDevice));
-    if (hist_phi) TG_CUDA(cudaMemcpy(ch->d_hist_phi, hist_phi, 8 * nh, cudaMemcpyHostToDevice));
-    if (hist_ptS) TG_CUDA(cudaMemcpy(ch->d_hist_ptS, hist_ptS, 8 * nh * R, cudaMemcpyHostToDevice));
-    if (hist_iter) TG_CUDA(cudaMemcpy(ch->d_hist_iter, hist_iter, 8 * nh, cudaMemcpyHostToDevice));
-    if (hist_action) TG_CUDA(cudaMemcpy(ch->d_hist_action, hist_action, 4 * nh, cudaMemcpyHostToDevice));
-    if (hist_accept) TG_CUDA(cudaMemcpy(ch->d_hist_accept, hist_accept, 4 * nh, cudaMemcpyHostToDevice));
-    if (hist_next_action) TG_CUDA(cudaMemcpy(ch->d_hist_next, hist_next_action, 4 * nh, cudaMemcpyHostToDevice));
+    if (hist_K) TG_CUDA(cudaMemcpy(ch->d_hist_K, hist_K, 4 * nh, cudaMemcpyDefault));
+    if (hist_cells) TG_CUDA(cudaMemcpy(ch->d_hist_cells, hist_cells, 8 * nh * 4 * KC, cudaMemcpyDefault));
+    if (hist_phi) TG_CUDA(cudaMemcpy(ch->d_hist_phi, hist_phi, 8 * nh, cudaMemcpyDefault));
+    if (hist_ptS) TG_CUDA(cudaMemcpy(ch->d_hist_ptS, hist_ptS, 8 * nh * R, cudaMemcpyDefault));
+    if (hist_iter) TG_CUDA(cudaMemcpy(ch->d_hist_iter, hist_iter, 8 * nh, cudaMemcpyDefault));
+    if (hist_action) TG_CUDA(cudaMemcpy(ch->d_hist_action, hist_action, 4 * nh, cudaMemcpyDefault));
+    if (hist_accept) TG_CUDA(cudaMemcpy(ch->d_hist_accept, hist_accept, 4 * nh, cudaMemcpyDefault));
+    if (hist_next_action) TG_CUDA(cudaMemcpy(ch->d_hist_next, hist_next_action, 4 * nh, cudaMemcpyDefault));
     return TONGA_OK;
 }
 
@@ -850,6 +865,24 @@ extern "C" int tonga_chains_raster(tonga_chains *ch, int32_t n_nodes, const doub
     TG_CUDA(cudaMemcpyAsync(sum_out, d + o_sum, 8 * nn, cudaMemcpyDeviceToHost, s));
     TG_CUDA(cudaMemcpyAsync(sumsq_out, d + o_sq, 8 * nn, cudaMemcpyDeviceToHost, s));
     TG_CUDA(cudaStreamSynchronize(s));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_history_host(tonga_chains *ch, void **hist_K, void **hist_cells, void **hist_phi, void **hist_ptS, void **hist_iter,
+                                         void **hist_action, void **hist_accept, void **hist_next_action) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_history_host: NULL");
+    if (!ch->host_history) return tg::fail(TONGA_ERR_STATE, "tonga_chains_history_host: this batch keeps its history in device memory (create it with TONGA_HISTORY_ON_HOST)");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));  // every store of the finished runs has reached host memory
+    if (hist_K) *hist_K = ch->d_hist_K;
+    if (hist_cells) *hist_cells = ch->d_hist_cells;
+    if (hist_phi) *hist_phi = ch->d_hist_phi;
+    if (hist_ptS) *hist_ptS = ch->d_hist_ptS;
+    if (hist_iter) *hist_iter = ch->d_hist_iter;
+    if (hist_action) *hist_action = ch->d_hist_action;
+    if (hist_accept) *hist_accept = ch->d_hist_accept;
+    if (hist_next_action) *hist_next_action = ch->d_hist_next;
     return TONGA_OK;
 }
 

@@ -23,7 +23,7 @@ struct SamplerArgs {
     float tol_alpha, tol_beta2;     // screening band
     int exact_only;                 // 1 = skip the FP32 screening (pure FP64 path; used by tests)
     long long *prof;                // PROF instantiation only: [n][16] per-phase clock64 totals of thread 0
-    const int32_t *rayid, *ray_off, *ray_orig;
+    const int32_t *rayid, *ray_off, *ray_orig, *ray_rank;
     int R, Rp, KC, ldT;
     int P, Ppad;
     int n_sm;  // SM count (leader-warp rotation)
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 double *hc = a.hist_cells + h * 4 * KC;
                 for (int i = tid; i < 4 * KC; i += ST) hc[i] = s_nx[i];
                 double *hp = a.hist_ptS + h * R;
-                for (int r = tid; r < R; r += ST) hp[a.ray_orig[r]] = s_tstar[r];  // caller's ray order
+                for (int i = tid; i < R; i += ST) hp[i] = s_tstar[a.ray_rank[i]];  // caller's ray order; contiguous stores (the history may live in mapped host memory)
                 if (vtid == 0) {
                     a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = iter;
                     a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;

@@ -185,6 +185,7 @@ struct tonga_ctx {
     int32_t *d_rayid = nullptr;                                // [Ppad] sorted ray index of each flat point
     int32_t *d_ray_off = nullptr;                              // [R+1]  CSR offsets over sorted rays
     int32_t *d_ray_orig = nullptr;                             // [R]    sorted ray index -> caller's ray index
+    int32_t *d_ray_rank = nullptr;                             // [R]    caller's ray index -> sorted ray index (inverse of ray_orig)
     int32_t *d_point_orig = nullptr;                           // [Ppad] sorted flat point -> caller's flat point (-1 for padding)
     double *d_tS = nullptr, *d_sig = nullptr;                  // [R]    in sorted ray order
     int Rp = 0;                                                // R rounded up to a multiple of 2 (16-byte rows)

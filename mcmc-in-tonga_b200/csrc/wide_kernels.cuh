@@ -23,7 +23,7 @@ struct WideArgs {
     long long iter, it, nIter;
     unsigned long long seed;
     long long chain_id0;
-    const int32_t *ray_orig;
+    const int32_t *ray_orig, *ray_rank;
     const double *tS, *sig;  // sorted ray order
     // current state
     int32_t *K;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) hc[i] = cur[i];
             double *hp = a.hist_ptS + h * R;
             const double *tcur = (a.streamed && accepted && act != 5) ? tsc : ts;  // streamed: the commit pass has not copied t* yet
-            for (int r = tid; r < R; r += TG_PHI_LANES) hp[a.ray_orig[r]] = tcur[r];
+            for (int i = tid; i < R; i += TG_PHI_LANES) hp[i] = tcur[a.ray_rank[i]];  // caller's ray order, contiguous stores
             if (tid == 0) {
                 a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = a.iter;
                 a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;

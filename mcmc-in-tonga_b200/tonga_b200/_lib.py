@@ -59,6 +59,7 @@ SYMBOLS = {
     "tonga_chains_create": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int64, C.c_uint64, C.c_int32]),
     "tonga_chains_create_ex": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int32]),
     "tonga_chains_sampler": (C.c_int, [_P]),
+    "tonga_chains_history_host": (C.c_int, [_P] + [c_vpp] * 8),
     "tonga_chains_destroy": (None, [_P]),
     "tonga_chains_build_starting": (C.c_int, [_P]),
     "tonga_chains_set_models": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp]),

@@ -173,10 +173,12 @@ class Chains:
     SAMPLERS = {"auto": 0, "resident": 1, "wide": 2, "streamed": 3}
 
     def __init__(self, ctx: Context, n_chains: int, chain_id0: int = 0, seed: int = 20260000, hist_cap: int | None = None,
-                 sampler: str = "auto"):
+                 sampler: str = "auto", host_history: bool = False):
         """sampler: "resident" (chain state in shared memory, max_cells <= 126, up to ~200k ray points), "wide" (a full
         batched forward model per proposal; any size), "streamed" (per-point state in HBM, one streaming pass per proposal; any
-        ray set, 6 B per point and chain) or "auto" (resident when it fits, else streamed).  Same chains either way."""
+        ray set, 6 B per point and chain) or "auto" (resident when it fits, else streamed).  Same chains either way.
+        host_history=True keeps the kept models in mapped page-locked host memory: the kernels write them there while they run
+        and history() returns views of those arrays without any copy."""
         self.ctx, self.lib, self.n = ctx, ctx.lib, n_chains
         self.chain_id0, self.seed = int(chain_id0), int(seed)
         p = ctx.params
@@ -184,7 +186,10 @@ class Chains:
             hist_cap = int((p.n_iter - p.burn_in) / p.keep_each) + 1 if p.keep_each > 0 else 0
         self.hist_cap = hist_cap
         self._h = C.c_void_p()
-        if sampler == "auto":  # the reference-facing entry point
+        self.host_history = bool(host_history)
+        if host_history:
+            check(self.lib.tonga_chains_create_ex(ctx._h, C.byref(self._h), n_chains, chain_id0, seed, hist_cap, self.SAMPLERS[sampler] | 0x100))
+        elif sampler == "auto":  # the reference-facing entry point
             check(self.lib.tonga_chains_create(ctx._h, C.byref(self._h), n_chains, chain_id0, seed, hist_cap))
         else:
             check(self.lib.tonga_chains_create_ex(ctx._h, C.byref(self._h), n_chains, chain_id0, seed, hist_cap, self.SAMPLERS[sampler]))
@@ -270,6 +275,20 @@ class Chains:
 
     def history(self, want_ptS=True, out: dict | None = None):
         n, H, KC, R = self.n, self.hist_cap, self.KC, self.ctx.R
+        if self.host_history and out is None:  # zero-copy views of the library's mapped host arrays (valid until close())
+            ptrs = [C.c_void_p() for _ in range(8)]
+            check(self.lib.tonga_chains_history_host(self._h, *[C.byref(p) for p in ptrs]))
+            n_hist = np.zeros(n, np.int32)
+            check(self.lib.tonga_chains_get_history(self._h, KC, ip(n_hist), None, None, None, None, None, None, None, None))
+            def view(ptr, shape, dt):
+                cnt = int(np.prod(shape))
+                if cnt == 0:
+                    return np.zeros(shape, dt)
+                buf = (C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(ptr.value)
+                return np.frombuffer(buf, dtype=dt, count=cnt).reshape(shape)
+            return dict(n_hist=n_hist, K=view(ptrs[0], (n, H), np.int32), cells=view(ptrs[1], (n, H, 4, KC), np.float64),
+                        phi=view(ptrs[2], (n, H), np.float64), ptS=view(ptrs[3], (n, H, R), np.float64), iter=view(ptrs[4], (n, H), np.int64),
+                        action=view(ptrs[5], (n, H), np.int32), accept=view(ptrs[6], (n, H), np.int32), next_action=view(ptrs[7], (n, H), np.int32))
         if out is None:
             out = dict(n_hist=np.zeros(n, np.int32), K=np.zeros((n, H), np.int32), cells=np.zeros((n, H, 4, KC)),
                        phi=np.zeros((n, H)), ptS=np.zeros((n, H, R)) if want_ptS else None, iter=np.zeros((n, H), np.int64),

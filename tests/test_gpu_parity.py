@@ -940,3 +940,34 @@ def test_device_normal_deviates_are_standard_normal(tonga):
     c = np.corrcoef(np.stack(zs[1:]))
     assert np.abs(c[np.triu_indices(3, 1)]).max() < 5 / np.sqrt(len(zs[1]))
     ch.close(); ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["resident", "streamed"])
+def test_host_resident_history_equals_device_history(tonga, kind):
+    """TONGA_HISTORY_ON_HOST: the kernels store the kept models into mapped host memory while they run; same history, no copy."""
+    import copy
+    from tonga_b200.api import Chains, Context
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 400.0, 100.0, 10.0
+    ctx = Context(ds, p)
+    hs = []
+    for host in (False, True):
+        ch = Chains(ctx, 5, chain_id0=1, seed=9, sampler=kind, host_history=host)
+        ch.build_starting()
+        ch.run(250); ch.run(150)
+        h = ch.history()
+        hs.append({k: np.array(v) for k, v in h.items()})
+        if host:
+            s1, s2, cnt = ch.raster([100.0, 500.0], [0.0, 100.0], [50.0, 300.0])
+            assert cnt == int(h["n_hist"].sum()) and np.isfinite(s1).all()
+        ch.close()
+    a, b = hs
+    assert (a["n_hist"] == 30).all() and np.array_equal(a["n_hist"], b["n_hist"])
+    for key in ("K", "phi", "ptS", "iter", "action", "accept", "next_action"):
+        assert a[key].tobytes() == b[key].tobytes(), key
+    for c in range(5):
+        for j in range(30):
+            k = a["K"][c, j]
+            assert np.array_equal(a["cells"][c, j, :, :k], b["cells"][c, j, :, :k])
+    ctx.close()
