@@ -228,6 +228,8 @@ struct tonga_chains {
     int32_t *d_accept = nullptr;    // [n]
     int32_t *d_active = nullptr;    // [n + 1]: active chain list, then its length
     size_t stream_smem = 0;
+    tg::Tile *d_stiles = nullptr;   // the streamed sampler's own tiles (whole rays, <= stile_pts points)
+    int n_stiles = 0, stile_pts = 0;
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
@@ -271,7 +273,10 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     // streamed sampler: 6 B per ray point and chain of state; AUTO uses it when that fits in 60 % of the free memory
-    const size_t stream_smem = ((size_t)ctx->tile_pts + 8) * 4 + ((size_t)ctx->tile_pts + 8) / 8 + 4 + 16;
+    int stile_pts = 8192;  // tile of the streamed sampler: twice the evaluate tile (half the CTA prologues; 34 KB of shared memory)
+    if (const char *e = std::getenv("TONGA_STREAM_TILE")) stile_pts = std::max(1024, std::min(15360, std::atoi(e) & ~31));
+    stile_pts = std::max(stile_pts, ctx->max_npts);
+    const size_t stream_smem = ((size_t)stile_pts + 8) * 4 + ((size_t)stile_pts + 8) / 8 + 4 + 16;
     const bool stream_ok = pm.max_cells <= 65534 && stream_smem <= ctx->smem_optin;
     if (sampler == TONGA_SAMPLER_STREAMED && !stream_ok)
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the streamed sampler needs max_cells <= 65534 and its tile state in shared memory");
@@ -283,7 +288,19 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     }
     const bool wide = streamed || (sampler == TONGA_SAMPLER_WIDE) || !fits;
     if (wide && nChains > 65535) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the wide / streamed samplers run at most 65535 chains per batch");
-    if (streamed && (double)ctx->n_tiles * (double)nChains > 2147483647.0)
+    std::vector<tg::Tile> stiles;
+    if (streamed) {  // consecutive whole (length-sorted) rays with at most stile_pts points
+        const int R = ctx->R;
+        std::vector<int32_t> so(R + 1, 0);
+        for (int rs = 0; rs < R; rs++) so[rs + 1] = so[rs] + (ctx->h_ray_off[ctx->h_ray_orig[rs] + 1] - ctx->h_ray_off[ctx->h_ray_orig[rs]]);
+        for (int r0 = 0; r0 < R;) {
+            int r1 = r0;
+            while (r1 < R && so[r1 + 1] - so[r0] <= stile_pts) r1++;
+            stiles.push_back({r0, r1, so[r0], so[r1]});
+            r0 = r1;
+        }
+    }
+    if (streamed && (double)stiles.size() * (double)nChains > 2147483647.0)
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: tiles x chains exceeds the launch grid of the streamed sampler");
     tonga_chains *ch = new tonga_chains();
     struct Guard {  // frees a half-built batch when an allocation below fails (TG_ALLOC / TG_CUDA return early)
@@ -303,6 +320,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->no_order = std::getenv("TONGA_NO_ORDER") != nullptr;
     ch->streamed = streamed;
     ch->stream_smem = stream_smem;
+    ch->stile_pts = stile_pts;
+    ch->n_stiles = (int)stiles.size();
     ch->smem = wide ? 0 : smem_res;
     const size_t n = (size_t)nChains, KC = (size_t)ch->KC, R = (size_t)ctx->R, Rp = (size_t)ch->Rp, Pp = (size_t)ctx->Ppad, H = (size_t)hist_cap;
     TG_ALLOC(ch->d_K, 4 * n);
@@ -328,6 +347,9 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_ALLOC(ch->d_tstar_c, 8 * n * Rp);
         TG_ALLOC(ch->d_term_c, 8 * n * Rp);
         TG_ALLOC(ch->d_accept, 4 * n);
+        TG_ALLOC(ch->d_stiles, sizeof(tg::Tile) * stiles.size());
+        TG_CUDA(cudaMemcpyAsync(ch->d_stiles, stiles.data(), sizeof(tg::Tile) * stiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+        TG_CUDA(cudaStreamSynchronize(ctx->stream));  // `stiles` is a local
         TG_ALLOC(ch->d_active, 4 * (n + 1));
         TG_ALLOC(ch->d_cells_cf, 4 * n * 3 * KC);
         TG_CUDA(cudaMemsetAsync(ch->d_owner16, 0xFF, 2 * n * Pp, ctx->stream));  // the padded tail stays "none"
@@ -412,7 +434,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     cudaStreamSynchronize(ch->ctx->stream);
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active};
+                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles};
     for (void *p : ptrs) cudaFree(p);
     void *hist[] = {ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter, ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next};
     for (void *p : hist) {
@@ -550,14 +572,14 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         w.streamed = ch->streamed ? 1 : 0; w.tstar_c = ch->d_tstar_c; w.accept_flag = ch->d_accept; w.cells_cf = ch->d_cells_cf; w.term_c = ch->d_term_c;
         w.active = ch->streamed ? ch->d_active : nullptr; w.n_active = ch->streamed ? ch->d_active + ch->n : nullptr;
         tg::StreamArgs sa{};
-        sa.tiles = ctx->d_tiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
+        sa.tiles = ch->d_stiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
         sa.dtT = ctx->d_dtT; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
-        sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ctx->tile_pts;
+        sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ch->stile_pts;
         sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.cells_cf = ch->d_cells_cf; sa.n_chains = ch->n; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
-        sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ctx->n_tiles;
+        sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
         sa.term_c = ch->d_term_c; sa.tS = ctx->d_tS; sa.sig = ctx->d_sig; sa.noise = ch->d_noise;
-        const dim3 sgrid((unsigned)((size_t)ctx->n_tiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
+        const dim3 sgrid((unsigned)((size_t)ch->n_stiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int saved_exact = ctx->exact_only;
         ctx->exact_only = ch->exact_only || saved_exact;
         for (int64_t it = 0; it < nIter; it++) {
