@@ -206,6 +206,23 @@ def main():
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     mm, dphi, dts = ch.verify()  # incremental state still equals a full evaluate after the timed region
+    # posterior maps of BASELINE config 4 (outside the timed regions): rasterise the kept models of the last step on the slices of
+    # plot_model_hist (MCsub.jl:753-825) and sum the {count, sum, sum^2} accumulators over the ranks (the path's only collective)
+    from tonga_b200 import api as _api, dist as _tdist
+    t0 = time.perf_counter()
+    acc = []
+    for kind, l0, shape, X, Y, Z in _api.slice_nodes(ds, p):
+        acc.append(ch.raster(X, Y, Z))
+    t1 = time.perf_counter()
+    n_nodes = sum(len(a_[0]) for a_ in acc)
+    if world > 1:
+        dist.barrier()
+    t2 = time.perf_counter()
+    red = [_tdist.allreduce_sums(s1, s2, cnt, device="cuda") for s1, s2, cnt in acc]
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    posterior = {"slices": len(acc), "nodes": int(n_nodes), "kept_models_all_ranks": int(red[0][2]) if red else 0,
+                 "raster_ms": 1e3 * (t1 - t0), "allreduce_ms": 1e3 * (t3 - t2), "backend": "nccl" if world > 1 else "none"}
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,6 +305,7 @@ def main():
             "acceptance": {"birth_death_change_move": acc_rate, "evaluated_fraction": float(c[2].sum() / max(c[0].sum(), 1)),
                            "mean_cells": float(st["K"].mean())},
             "verify": {"owner_mismatch": mm, "max_dphi": dphi, "max_dtstar": dts},
+            "posterior": posterior,
         }
         if not args.no_cpu_baseline and world >= 1:
             rate, dt, chains = cpu_reference_arm(ds, p, args.cpu_iters, ncores)
