@@ -223,6 +223,17 @@ def main():
     t3 = time.perf_counter()
     posterior = {"slices": len(acc), "nodes": int(n_nodes), "kept_models_all_ranks": int(red[0][2]) if red else 0,
                  "raster_ms": 1e3 * (t1 - t0), "allreduce_ms": 1e3 * (t3 - t2), "backend": "nccl" if world > 1 else "none"}
+    if world > 1:  # config 4: gather of the packed kept models (K, nuclei, phi of the last <= 50 kept models of every chain) to all ranks
+        hv = _tdist.history_tensors(ch, torch.device("cuda", local_rank))
+        last = max(0, min(int(ch.hist_cap), 50))
+        local = {k: hv[k][:, :last].contiguous() for k in ("K", "cells", "phi")}
+        torch.cuda.synchronize(); dist.barrier()
+        t4 = time.perf_counter()
+        ens = _tdist.gather_ensembles(local, [n] * world)
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        posterior.update({"gather_ms": 1e3 * (t5 - t4), "gather_bytes_per_rank": int(sum(v.numel() * v.element_size() for v in local.values())),
+                          "gathered_chains": int(ens["K"].shape[0])})
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
