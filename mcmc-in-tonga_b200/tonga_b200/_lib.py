@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "..", "lib", "libtonga_b200.so")
+LIB_PATH = os.environ.get("TONGA_B200_LIB") or os.path.join(HERE, "..", "lib", "libtonga_b200.so")  # same override as julia/TongaB200.jl
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
