@@ -971,3 +971,23 @@ def test_host_resident_history_equals_device_history(tonga, kind):
             k = a["K"][c, j]
             assert np.array_equal(a["cells"][c, j, :, :k], b["cells"][c, j, :, :k])
     ctx.close()
+
+
+def test_streamed_screening_equals_exact(tonga):
+    """Streamed sampler: FP32 screening + exact recheck (default) == every comparison in exact FP64 (set_exact_only), bit for bit."""
+    from tonga_b200.api import Chains, Context
+    ds, p = tonga
+    ctx = Context(ds, p)
+    outs = []
+    for exact in (False, True):
+        ch = Chains(ctx, 6, seed=31, hist_cap=0, sampler="streamed")
+        ch.set_exact_only(exact)
+        ch.build_starting()
+        out = ch.run(300, record=True, trace=True)
+        outs.append((out, ch.state(want_owners=True)))
+        assert ch.verify() == (0, 0.0, 0.0)
+        ch.close()
+    (a, sa), (b, sb) = outs
+    assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"]) and a["phi"].tobytes() == b["phi"].tobytes()
+    assert np.array_equal(sa["owners"], sb["owners"]) and sa["ptS"].tobytes() == sb["ptS"].tobytes()
+    ctx.close()
