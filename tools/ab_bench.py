@@ -24,7 +24,11 @@ for _ in range(5):
     ch.run(1000); ms.append(ch.last_kernel_ms())
 print("%(tag)s", "%%.2f M/s" %% (1024 * 1000 / np.median(ms) / 1e3), ["%%.1f" %% m for m in ms])
 if os.environ.get("AB_PROFILE"):
-    ch.profile(True); ch.run(1000); cyc = ch.profile(False, read=True)
+    ch.profile(True); pm = []
+    for _ in range(3):
+        ch.run(1000); pm.append(ch.last_kernel_ms())
+    cyc = ch.profile(False, read=True) / 3
+    print("   instrumented build: %%.2f M/s" %% (1024 * 1000 / np.median(pm) / 1e3), ["%%.1f" %% m for m in pm])
     print("   cycles/iter A,B,C,D+E,F4,G,F1,F2:", (cyc[:, :8].mean(0) / 1000).round(0))
 '''
 root = os.path.dirname(HERE)
