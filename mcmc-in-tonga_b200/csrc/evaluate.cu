@@ -177,7 +177,7 @@ tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, co
 }
 
 int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev, const double *cells_dev,
-                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev, bool force_geometry, uint16_t *owners16_dev) {
+                    const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev, uint8_t *owners8_dev, float *dmin32_dev, bool force_geometry, uint16_t *owners16_dev, int exact_only) {
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
@@ -187,7 +187,7 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
                                                                   ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->tol_alpha, ctx->tol_beta2,
-                                                                  ctx->exact_only, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
+                                                                  exact_only < 0 ? ctx->exact_only : exact_only, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev, dmin32_dev, owners16_dev);
         TG_CUDA(cudaGetLastError());

@@ -580,8 +580,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
         sa.term_c = ch->d_term_c; sa.tS = ctx->d_tS; sa.sig = ctx->d_sig; sa.noise = ch->d_noise;
         const dim3 sgrid((unsigned)((size_t)ch->n_stiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
-        const int saved_exact = ctx->exact_only;
-        ctx->exact_only = ch->exact_only || saved_exact;
+        const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;
         for (int64_t it = 0; it < nIter; it++) {
             w.it = it; w.iter = ch->iter_done + 1 + it;
             if (ch->streamed) TG_CUDA(cudaMemsetAsync(ch->d_active + ch->n, 0, 4, s));
@@ -589,13 +588,12 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             if (ch->streamed) {
                 tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
             } else if (!ctx->prm.debug_prior) {
-                rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_Kc, ch->d_cells_c, nullptr, ch->d_ptS_tmp, nullptr, nullptr, nullptr, nullptr);
-                if (rc != TONGA_OK) { ctx->exact_only = saved_exact; return rc; }
+                rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_Kc, ch->d_cells_c, nullptr, ch->d_ptS_tmp, nullptr, nullptr, nullptr, nullptr, false, nullptr, exact);
+                if (rc != TONGA_OK) return rc;
             }
             tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
             if (ch->streamed) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
         }
-        ctx->exact_only = saved_exact;
         TG_CUDA(cudaGetLastError());
     } else {
     tg::SamplerArgs a{};

@@ -243,5 +243,6 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
                     const double *noise_dev, double *ptS_dev, double *phi_dev, int32_t *owners32_dev,
                     uint8_t *owners8_dev /* [nModels][Ppad] chain-state layout, or NULL */,
                     float *dmin32_dev /* [nModels][Ppad] fl32 squared distance to the owner (sampler cache), or NULL */, bool force_geometry = false,
-                    uint16_t *owners16_dev = nullptr /* [nModels][Ppad] streamed-sampler chain state, or NULL */);
+                    uint16_t *owners16_dev = nullptr /* [nModels][Ppad] streamed-sampler chain state, or NULL */,
+                    int exact_only = -1 /* -1: the context's setting (tonga_set_exact_only); 0 / 1: override for this call */);
 }  // namespace tg

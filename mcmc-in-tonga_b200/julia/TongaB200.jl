@@ -115,13 +115,16 @@ v_nearest(x, y, z, mx, my, mz, mv) = interpolate(mx, my, mz, mv, [x], [y], [z])[
 
 # ---- the chain farm: replaces pmap(x -> TD_inversion_function(TD_parameters, dataStruct, x), 1:n_chains) --------------
 # Returns Vector{Vector{Model}} exactly as plot_model_hist consumes it (MCsub.jl:762-767).
-function run_chains(TD_parameters, dataStruct, chains::AbstractUnitRange; seed::UInt64 = UInt64(20260000), device = 0, Model = Main.Model)
+# `sampler`: 0 = automatic (shared-memory sampler when the ray set and max_cells fit, else the HBM-streamed one, else the wide one),
+# 1 / 2 / 3 = force resident / wide / streamed (TONGA_SAMPLER_* in include/tonga_b200.h).  All give the same chains.
+function run_chains(TD_parameters, dataStruct, chains::AbstractUnitRange; seed::UInt64 = UInt64(20260000), device = 0, Model = Main.Model,
+                    sampler::Integer = 0)
     ctx = context(dataStruct, TD_parameters; device = device)
     n = length(chains)
     H = Int((TD_parameters.n_iter - TD_parameters.burn_in) / TD_parameters.keep_each) + 1   # TD_inversion_function.jl:25
     ch = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:tonga_chains_create, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Int32, Int64, UInt64, Int32),
-                ctx, ch, n, first(chains), seed, H))
+    check(ccall((:tonga_chains_create_ex, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Int32, Int64, UInt64, Int32, Int32),
+                ctx, ch, n, first(chains), seed, H, sampler))
     try
         check(ccall((:tonga_chains_build_starting, LIB), Cint, (Ptr{Cvoid},), ch[]))          # TD_inversion_function.jl:43-45
         check(ccall((:tonga_chains_run, LIB), Cint,
