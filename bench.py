@@ -313,6 +313,7 @@ def main():
             "gpu_launches": 2 * args.steps,  # per step: tg_order_kernel (launch order by nCells) + tg_sampler_kernel
             "clocks": clocks,
             "roofline": roof,
+            "evaluates_per_s": value * float(c[2].sum() / max(c[0].sum(), 1)),  # proposals that needed the forward model (a-priori rejects excluded; rank 0's mix)
             "acceptance": {"birth_death_change_move": acc_rate, "evaluated_fraction": float(c[2].sum() / max(c[0].sum(), 1)),
                            "mean_cells": float(st["K"].mean())},
             "verify": {"owner_mismatch": mm, "max_dphi": dphi, "max_dtstar": dts},
