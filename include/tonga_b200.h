@@ -78,6 +78,8 @@ int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double *rayX, cons
  * points (column-major like rayX; NaN padding).  Bit-identical to tonga_create fed with those rayL / rayU. */
 int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, const double *rayX, const double *rayY, const double *rayZ,
                              const double *U, const double *tS, const double *allSig, const tonga_params *params, int32_t device);
+/* Frees the context.  Every tonga_chains batch created on it must have been destroyed first (a batch refers to its context;
+ * the Python mirror's Context.close() and the Julia shim's `finally` blocks take care of the order). */
 void tonga_destroy(tonga_ctx *ctx);
 /* R, number of valid points P, number of segments S, padded point count used on the device */
 int tonga_info(const tonga_ctx *ctx, int32_t *R, int64_t *P, int64_t *S, int64_t *Ppad);

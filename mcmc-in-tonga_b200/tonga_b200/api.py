@@ -110,8 +110,11 @@ class Context:
         self.P, self.S, self.Ppad = P.value, S.value, Pp.value
         self.device = device
         self._fin = weakref.finalize(self, self.lib.tonga_destroy, self._h)
+        self._chains = weakref.WeakSet()  # live Chains built on this context: they must be destroyed first
 
     def close(self):
+        for ch in list(self._chains):
+            ch.close()
         self._fin()
 
     def ray_offsets(self) -> np.ndarray:
@@ -197,6 +200,7 @@ class Chains:
         self.sampler = {1: "resident", 2: "wide", 3: "streamed"}[self.lib.tonga_chains_sampler(self._h)] if hasattr(self.lib, "tonga_chains_sampler") else "resident"
         self._fin = weakref.finalize(self, self.lib.tonga_chains_destroy, self._h)
         self._ctx_keepalive = ctx
+        ctx._chains.add(self)
 
     def close(self):
         self._fin()

@@ -571,6 +571,7 @@ def test_evaluate_synthetic_config3_shape():
 
 
 def test_abi_error_paths_and_helpers(tonga):
+    import ctypes as C
     """Error behaviour at the C ABI (codes + messages, no exceptions across it) and the small helper entry points."""
     import copy
     from tonga_b200 import _lib, api
@@ -614,6 +615,23 @@ def test_abi_error_paths_and_helpers(tonga):
     p = copy.copy(p0); p.interp_style = 2
     with pytest.raises(_lib.TongaError) as e:
         api.Context(ds, p)
+    assert e.value.code == -1
+    with pytest.raises(_lib.TongaError) as e:
+        api.Context(ds, p, device_ingest=True)
+    assert e.value.code == -1
+    # device ingest: slowness matrix of the wrong shape; history in host memory asked from a device-history batch
+    import dataclasses
+    bad = dataclasses.replace(ds, U=ds.U[:-1]) if dataclasses.is_dataclass(ds) else None
+    if bad is not None:
+        with pytest.raises(_lib.TongaError):
+            api.Context(bad, p0, device_ingest=True)
+    chd = api.Chains(ctx, 1, hist_cap=2)
+    ptrs = [C.c_void_p() for _ in range(8)]
+    assert chd.lib.tonga_chains_history_host(chd._h, *[C.byref(q) for q in ptrs]) == -4
+    assert chd.lib.tonga_chains_set_progress(chd._h, -1, None, None, None) == -1
+    chd.close()
+    with pytest.raises(_lib.TongaError) as e:
+        api.Chains(ctx, 1, sampler="streamed", hist_cap=0).restore(dict(hist_cap=1, K=np.zeros(1), chain_id0=0, seed=0))
     assert e.value.code == -1
     ctx.close(); ctx2.close()
 
