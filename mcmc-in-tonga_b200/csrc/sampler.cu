@@ -228,6 +228,7 @@ struct tonga_chains {
     int32_t *d_accept = nullptr;    // [n]
     int32_t *d_active = nullptr;    // [n + 1]: active chain list, then its length
     size_t stream_smem = 0;
+    uint8_t *d_tile_changed = nullptr;  // [n][n_stiles]
     tg::Tile *d_stiles = nullptr;   // the streamed sampler's own tiles (whole rays, <= stile_pts points)
     int n_stiles = 0, stile_pts = 0;
     // scratch
@@ -348,6 +349,7 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_ALLOC(ch->d_term_c, 8 * n * Rp);
         TG_ALLOC(ch->d_accept, 4 * n);
         TG_ALLOC(ch->d_stiles, sizeof(tg::Tile) * stiles.size());
+        TG_ALLOC(ch->d_tile_changed, n * stiles.size());
         TG_CUDA(cudaMemcpyAsync(ch->d_stiles, stiles.data(), sizeof(tg::Tile) * stiles.size(), cudaMemcpyHostToDevice, ctx->stream));
         TG_CUDA(cudaStreamSynchronize(ctx->stream));  // `stiles` is a local
         TG_ALLOC(ch->d_active, 4 * (n + 1));
@@ -434,7 +436,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     cudaStreamSynchronize(ch->ctx->stream);
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles};
+                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles, ch->d_tile_changed};
     for (void *p : ptrs) cudaFree(p);
     void *hist[] = {ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter, ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next};
     for (void *p : hist) {
@@ -577,7 +579,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ch->stile_pts;
         sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.cells_cf = ch->d_cells_cf; sa.n_chains = ch->n; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
-        sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
+        sa.tile_changed = ch->d_tile_changed; sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
         sa.term_c = ch->d_term_c; sa.tS = ctx->d_tS; sa.sig = ctx->d_sig; sa.noise = ch->d_noise;
         const dim3 sgrid((unsigned)((size_t)ch->n_stiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;

@@ -246,6 +246,7 @@ struct StreamArgs {
     const double *tS, *sig, *noise;
     const int32_t *accept_flag;
     const int32_t *active, *n_active;  // chains with a candidate to process (tg_wide_propose_kernel)
+    uint8_t *tile_changed;             // [n_chains][n_tiles]: the candidate pass found a point of the tile that changes owner (birth / move)
     int n_tiles;
 };
 
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
         double *ts = a.tstar + (size_t)chain * a.Rp;
         for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) ts[r] = tsc[r];
         if (act == 3) continue;  // change: no owner moves
+        if ((act == 1 || act == 4) && !a.tile_changed[(size_t)chain * a.n_tiles + blockIdx.x / n_groups]) continue;  // no point of this tile switches
     }
     // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | queue u16[tile_pts] (orphans, then dirty rays) | counters
     const int cap = a.tile_pts + 8;  // the aligned groups may start up to 3 points before / end up to 3 points after the tile
@@ -489,6 +491,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     }
     if (COMMIT) continue;
     __syncthreads();
+    if (act == 1 || act == 4) {  // tell the commit pass whether this tile holds any switching point at all
+        int any = 0;
+        for (int i = tid; i < cap / 32 + 1; i += STREAM_THREADS) any |= (s_chg[i] != 0u);
+        any = __syncthreads_or(any | (act == 4 && s_cnt[0] > 0));  // orphans of a move always count (their owner distance changes)
+        if (tid == 0) a.tile_changed[(size_t)chain * a.n_tiles + blockIdx.x / n_groups] = (uint8_t)(any != 0);
+    }
     // ---- phase 2: t* of the tile's rays.  Rays without a changed point keep their t*; the others are listed and re-integrated
     // by the warps, one ray at a time (ray_tstar_warp: canonical left-to-right sum).
     const double *zc = cc + 3 * (size_t)a.KC;
