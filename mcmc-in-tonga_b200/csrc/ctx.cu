@@ -104,9 +104,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     for (int rs = 0; rs < R; rs++) sray_off[rs + 1] = sray_off[rs] + (ray_off[ray_orig[rs] + 1] - ray_off[ray_orig[rs]]);
     const double qnan = std::nan("");
     std::vector<double> px(Ppad, qnan), py(Ppad, qnan), pz(Ppad, qnan);
-    const int nsegmax = m > 1 ? m - 1 : 1;
-    const int ldT = ((R + 127) / 128) * 128 + (R == 0 ? 128 : 0);
-    std::vector<double> dtT((size_t)nsegmax * ldT, 0.0);
+    std::vector<double> dt(Ppad, 0.0);  // flat, point order: dt[p] = segment p -> p+1
     std::vector<int32_t> rayid(Ppad, 0), point_orig(Ppad, -1);
     std::vector<double> tS_s(R), sig_s(R);
     int64_t S = 0;
@@ -124,7 +122,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
             point_orig[dst] = ray_off[i] + k;
             if (k < np - 1) {
                 const size_t sg = (size_t)i * (m - 1) + k;
-                dtT[(size_t)k * ldT + tg::dt_col(rs)] = rayL[sg] * rayU[sg];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction)
+                dt[dst] = rayL[sg] * rayU[sg];  // rayl .* rayu is the first product of MCsub.jl:153 (host: no contraction)
                 S++;
             }
         }
@@ -157,7 +155,6 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     ctx->h_ray_orig = ray_orig;
     ctx->h_point_orig = point_orig;
     ctx->Rp = Rp;
-    ctx->ldT = ldT;
     ctx->n_tiles = (int)tiles.size();
     ctx->tile_pts = tile_pts;
     cudaDeviceProp prop;
@@ -209,7 +206,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
         chk(upload(&ctx->d_pyf, yf, ctx->stream));
         chk(upload(&ctx->d_pzf, zf, ctx->stream));
     }
-    chk(upload(&ctx->d_dtT, dtT, ctx->stream));
+    chk(upload(&ctx->d_dt, dt, ctx->stream));
     chk(upload(&ctx->d_rayid, rayid, ctx->stream));
     chk(upload(&ctx->d_ray_off, sray_off, ctx->stream));
     chk(upload(&ctx->d_ray_orig, ray_orig, ctx->stream));
@@ -235,7 +232,7 @@ extern "C" void tonga_destroy(tonga_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dtT);
+    cudaFree(ctx->d_px); cudaFree(ctx->d_py); cudaFree(ctx->d_pz); cudaFree(ctx->d_dt);
     cudaFree(ctx->d_pxf); cudaFree(ctx->d_pyf); cudaFree(ctx->d_pzf);
     cudaFree(ctx->d_rayid); cudaFree(ctx->d_ray_off); cudaFree(ctx->d_ray_orig); cudaFree(ctx->d_ray_rank); cudaFree(ctx->d_point_orig);
     cudaFree(ctx->d_tS); cudaFree(ctx->d_sig);

@@ -5,8 +5,8 @@
 //
 // Kernel 1 (tg_eval_kernel): CTA = (ray tile, model).  The model's nuclei are staged in shared memory; phase 1 is a
 // flat, fully occupied pass over the tile's points (4 points per thread held in registers while the nucleus loop
-// broadcasts each nucleus from shared memory) that produces the owner of every point; phase 2 integrates t* with one
-// thread per (length-sorted) ray in the canonical left-to-right order.  Kernel 2 (tg_phi_kernel) reduces the per-ray misfit terms in the canonical
+// broadcasts each nucleus from shared memory) that produces the owner of every point; phase 2 integrates t* in the
+// canonical order (8 lanes per ray, tstar_g8).  Kernel 2 (tg_phi_kernel) reduces the per-ray misfit terms in the canonical
 // order.  FP64 throughout, no FMA contraction in the distance (bit-exact owners).
 #include <cmath>
 #include <cstring>
@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(EVAL_THREADS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, float tol_alpha,
-               float tol_beta2, int exact_only, const double *__restrict__ dtT, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
-               const int32_t *__restrict__ point_orig, int R, int ldT, int64_t P, int64_t Ppad, int tile_pts,
+               float tol_beta2, int exact_only, const double *__restrict__ dt, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
+               const int32_t *__restrict__ point_orig, int R, int64_t P, int64_t Ppad, int tile_pts,
                double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32,
                uint16_t *__restrict__ owners16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,12 +141,18 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     }
     __syncthreads();
 
-    // ---- phase 2: t* per ray, one thread per ray (rays are length-sorted), left-to-right sum (MCsub.jl:147,153/159)
+    // ---- phase 2: t* per ray in the canonical order (tstar_g8: 8 lanes per ray, 4 length-sorted rays per warp), MCsub.jl:147,153/159
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16 ? 0.0 : s_zeta[o]; };
-    for (int r = tile.r0 + threadIdx.x; r < tile.r1; r += EVAL_THREADS) {
-        const int q0 = ray_off[r], n = ray_off[r + 1] - q0;
-        const double t = ray_tstar_seq<uint16_t>(s_owner - tile.p0, dtT, ldT, r, q0, n, zeta_of);
-        ptS[(size_t)model * R + ray_orig[r]] = t;  // caller's ray order
+    const int grp = (threadIdx.x & 31) >> 3, sub = threadIdx.x & 7;
+    for (int rb = tile.r0 + 4 * (threadIdx.x >> 5); rb < tile.r1; rb += 4 * (EVAL_THREADS / 32)) {  // warp-uniform
+        const int r = rb + grp;
+        const bool on = r < tile.r1;
+        const int q0 = on ? ray_off[r] : 0, n = on ? ray_off[r + 1] - q0 : 0;
+        const int nseg = n > 1 ? n - 1 : 0;
+        const int trip = __reduce_max_sync(0xffffffffu, (nseg + 7) >> 3);
+        const uint16_t *ow = s_owner + (q0 - tile.p0);
+        const double t = tstar_g8(nseg, trip, sub, [&](int j) { return seg_term(dt[q0 + j], zeta_of(ow[j]), zeta_of(ow[j + 1])); });
+        if (on && sub == 0) ptS[(size_t)model * R + ray_orig[r]] = t;  // caller's ray order
     }
 }
 
@@ -187,8 +193,8 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
                                                                   ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->tol_alpha, ctx->tol_beta2,
-                                                                  exact_only < 0 ? ctx->exact_only : exact_only, ctx->d_dtT, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
-                                                                  ctx->R, ctx->ldT, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
+                                                                  exact_only < 0 ? ctx->exact_only : exact_only, ctx->d_dt, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
+                                                                  ctx->R, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev, dmin32_dev, owners16_dev);
         TG_CUDA(cudaGetLastError());
     }

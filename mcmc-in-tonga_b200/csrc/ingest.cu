@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) tg_ingest_count_kernel(int m, int R, cons
 __global__ void __launch_bounds__(256)
 tg_ingest_scatter_kernel(int m, int R, const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
                          const double *__restrict__ U, const int32_t *__restrict__ ray_orig, const int32_t *__restrict__ sray_off,
-                         const int32_t *__restrict__ ray_off, int ldT, double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
+                         const int32_t *__restrict__ ray_off, double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                          float *__restrict__ pxf, float *__restrict__ pyf, float *__restrict__ pzf, int32_t *__restrict__ rayid,
-                         int32_t *__restrict__ point_orig, double *__restrict__ dtT, unsigned long long *__restrict__ maxabs_bits) {
+                         int32_t *__restrict__ point_orig, double *__restrict__ dt, unsigned long long *__restrict__ maxabs_bits) {
     const int rs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (rs >= R) return;
     const int i = ray_orig[rs];
@@ -52,7 +52,7 @@ tg_ingest_scatter_kernel(int m, int R, const double *__restrict__ X, const doubl
             const double dx = __dsub_rn(xa, x[k + 1]), dy = __dsub_rn(ya, y[k + 1]), dz = __dsub_rn(za, z[k + 1]);
             const double rayl = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
             const double rayu = __dmul_rn(0.5, __dadd_rn(u[k], u[k + 1]));
-            dtT[(size_t)k * ldT + dt_col(rs)] = __dmul_rn(rayl, rayu);
+            dt[q0 + k] = __dmul_rn(rayl, rayu);
         }
     }
     for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
@@ -157,9 +157,7 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
         tiles.push_back({r0, r1, sray_off[r0], sray_off[r1]});
         r0 = r1;
     }
-    const int nsegmax = m > 1 ? m - 1 : 1;
-    const int ldT = ((R + 127) / 128) * 128;
-    ctx->P = P; ctx->S = S; ctx->Ppad = Ppad; ctx->max_npts = max_npts; ctx->Rp = (R + 1) & ~1; ctx->ldT = ldT;
+    ctx->P = P; ctx->S = S; ctx->Ppad = Ppad; ctx->max_npts = max_npts; ctx->Rp = (R + 1) & ~1;
     ctx->n_tiles = (int)tiles.size(); ctx->tile_pts = tile_pts;
     ctx->h_ray_off = ray_off; ctx->h_ray_orig = ray_orig;
     std::vector<double> tS_s(R), sig_s(R);
@@ -199,13 +197,13 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
     TG_CUDA(cudaMalloc((void **)&ctx->d_pzf, 4 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_rayid, 4 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_point_orig, 4 * (size_t)Ppad));
-    TG_CUDA(cudaMalloc((void **)&ctx->d_dtT, 8 * (size_t)nsegmax * ldT));
-    TG_CUDA(cudaMemsetAsync(ctx->d_dtT, 0, 8 * (size_t)nsegmax * ldT, s));
+    TG_CUDA(cudaMalloc((void **)&ctx->d_dt, 8 * (size_t)Ppad));
+    TG_CUDA(cudaMemsetAsync(ctx->d_dt, 0, 8 * (size_t)Ppad, s));
     int rcs = tg::ensure_scratch(ctx, 8);
     if (rcs != TONGA_OK) return rcs;
     TG_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 8, s));
-    tg::tg_ingest_scatter_kernel<<<wgrid, 256, 0, s>>>(m, R, dX, dY, dZ, dU, ctx->d_ray_orig, ctx->d_ray_off, d_ray_off_orig, ldT, ctx->d_px, ctx->d_py,
-                                                       ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->d_rayid, ctx->d_point_orig, ctx->d_dtT,
+    tg::tg_ingest_scatter_kernel<<<wgrid, 256, 0, s>>>(m, R, dX, dY, dZ, dU, ctx->d_ray_orig, ctx->d_ray_off, d_ray_off_orig, ctx->d_px, ctx->d_py,
+                                                       ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->d_rayid, ctx->d_point_orig, ctx->d_dt,
                                                        (unsigned long long *)ctx->d_scratch);
     TG_CUDA(cudaGetLastError());
     if (Ppad > P) {

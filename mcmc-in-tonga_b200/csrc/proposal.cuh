@@ -84,18 +84,129 @@ __device__ __forceinline__ double normal_icdf(double u) {
     return q < 0.0 ? -v : v;
 }
 
-// Warp-collective (all 32 lanes of one warp call it with identical scalars): draws (mode 0, Philox4x32-10 keyed by `seed`, counter =
-// (iteration, global chain id, slot)) or takes over a recorded proposal, applies the a-priori checks of the reference and
-// evaluates v_nearest at the new / killed nucleus.  sig_zeta = zeta_scale * sig / 100 (TD_inversion_function.jl:22, hoisted by the
-// caller).  Returns `valid`
-// (1 = the candidate must be evaluated); pr.action / idx / x / y / z / zeta / u / aux are set on every lane.
+// The state-independent part of one iteration's random numbers ("raw draw"): Philox4x32-10 keyed by `seed`, counter =
+// (iteration, global chain id, slot 0..3) -> 8 uniforms uu[0..7]; action from uu[0] (rand(1:4), TD_inversion_function.jl:72),
+// uu[1..3] position / index uniforms, three standard normals by inversion of uu[4..6], uu[7] the accept uniform.
+// The resident sampler pre-generates these for a whole launch (tg_pregen_kernel, one thread per chain-iteration); the
+// wide / streamed samplers compute them with the lanes of a warp (draw_proposal).  Both give the same values.
+struct RawDraw {
+    double act, u1, u2, u3, n0, n1, n2, u7;
+};
+static_assert(sizeof(RawDraw) == 64, "RawDraw is read as 8 doubles, one per lane");
+
+__device__ __forceinline__ int action_of(double u0, int n_actions) {
+    const int nact = n_actions >= 4 ? n_actions : 4;
+    const int act0 = 1 + (int)floor(u0 * nact);  // rand(1:4), TD_inversion_function.jl:72
+    return act0 > nact ? nact : act0;
+}
+
+__device__ __forceinline__ void raw_draw_thread(RawDraw &rd, unsigned long long seed, long long iter, unsigned long long gid, int n_actions) {
+    const Philox philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    double uu[8];
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        uint32_t w[4];
+        philox((uint32_t)iter, (uint32_t)((unsigned long long)iter >> 32), (uint32_t)gid, (uint32_t)s | ((uint32_t)(gid >> 32) << 8), w);
+        uu[2 * s] = u53(w[0], w[1]);
+        uu[2 * s + 1] = u53(w[2], w[3]);
+    }
+    rd.act = (double)action_of(uu[0], n_actions);
+    rd.u1 = uu[1]; rd.u2 = uu[2]; rd.u3 = uu[3];
+    rd.n0 = normal_icdf(uu[4]); rd.n1 = normal_icdf(uu[5]); rd.n2 = normal_icdf(uu[6]);
+    rd.u7 = uu[7];
+}
+
+// Warp-collective (all 32 lanes call it with identical scalars): builds the proposal of one iteration from the raw draw
+// (mode 0; pr.action preset) or from a recorded proposal (mode 1; pr.action / idx / x / y / z / zeta / u preset), applies
+// the a-priori checks of the reference and evaluates v_nearest at the new / killed nucleus.  sig_zeta = zeta_scale * sig / 100
+// (TD_inversion_function.jl:22, hoisted by the caller).  Returns `valid` (1 = the candidate must be evaluated).
+template <int SPACE>
+__device__ __forceinline__ int assemble_proposal(Prop &pr, int mode, double u1, double u2, double u3, double n0, double n1, double n2, double u7,
+                                                 const double *nx, const double *ny, const double *nz, const double *nzeta, int K, double noise,
+                                                 const tonga_params &pm, double sig_zeta, int lane) {
+    const int act = pr.action;
+    int valid = 0;
+    if (act == 1) {  // ---- birth :76-125
+        if (K < pm.max_cells) {
+            if (mode == 0) {
+                pr.x = u1 * (pm.xmax - pm.xmin) + pm.xmin;  // :78
+                pr.y = u2 * (pm.ymax - pm.ymin) + pm.ymin;  // :79
+                pr.z = u3 * (pm.zmax - pm.zmin) + pm.zmin;  // :80
+            }
+            const int ci = warp_nearest<SPACE>(nx, ny, nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
+            const double czeta = ci < 0 ? 0.0 : nzeta[ci];
+            pr.aux = czeta;
+            if (mode == 0) {
+                pr.zeta = czeta + sig_zeta * n0;  // :82
+                pr.u = u7;                        // :121
+            }
+            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
+            else if (pm.prior == 2) valid = 1;
+            else valid = (pr.zeta > 0);  // :111
+        }
+    } else if (act == 2) {  // ---- death :126-181
+        if (K > pm.min_cells) {
+            if (mode == 0) {
+                const int k = (int)floor(u1 * K);  // :128
+                pr.idx = k >= K ? K - 1 : k;
+                pr.u = u7;  // :176
+            }
+            const int kill = pr.idx;
+            if (kill >= 0 && kill < K) {
+                const int zi = warp_nearest<SPACE>(nx, ny, nz, K, kill, nx[kill], ny[kill], nz[kill], lane);  // :146
+                pr.aux = zi < 0 ? 0.0 : nzeta[zi];
+                valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
+            }
+        }
+    } else if (act == 3) {  // ---- change :183-218
+        if (mode == 0) {
+            const int k = (int)floor(u1 * K);  // :184
+            pr.idx = k >= K ? K - 1 : k;
+            pr.zeta = nzeta[pr.idx] + sig_zeta * n0;  // :188
+            pr.u = u7;                                // :214
+        }
+        if (pr.idx >= 0 && pr.idx < K) {
+            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
+            else if (pm.prior == 2) valid = 1;
+            else valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
+            // the reference evaluates first (:191) but discards the result when invalid
+        }
+    } else if (act == 4) {  // ---- move :220-251
+        if (K > 0) {
+            if (mode == 0) {
+                const int k = (int)floor(u1 * K);  // :222
+                pr.idx = k >= K ? K - 1 : k;
+                pr.x = nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
+                pr.y = ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
+                pr.z = nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
+                pr.u = u7;                                                         // :247
+            }
+            if (pr.idx >= 0 && pr.idx < K) {
+                valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
+                         pr.z <= pm.zmax);  // :230-232
+                if (valid) { pr.ox = nx[pr.idx]; pr.oy = ny[pr.idx]; pr.oz = nz[pr.idx]; }
+            }
+        }
+    } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension, see DESIGN.md)
+        if (mode == 0) {
+            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * n0;  // :23,:254
+            pr.u = u7;
+        }
+        valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
+    }
+    pr.do_eval = valid;
+    return valid;
+}
+
+// Warp-collective: raw draw with the lanes of the warp (mode 0) or a recorded proposal (mode 1), then assemble_proposal.
+// pr.action / idx / x / y / z / zeta / u / aux are set on every lane.
 template <int SPACE>
 __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_proposal *rec_in, unsigned long long seed, long long iter,
                                              unsigned long long gid, const double *nx, const double *ny, const double *nz,
                                              const double *nzeta, int K, double noise, const tonga_params &pm, double sig_zeta, int lane) {
     pr.do_eval = 0; pr.accept = 0; pr.idx = 0;
     pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
-    double uu[8], nrm[3];
+    double uu[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nrm[3] = {0, 0, 0};
     if (mode == 0) {
         const Philox philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
         uint32_t w[4] = {0, 0, 0, 0};
@@ -107,11 +218,8 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
             uu[2 * s] = u53(w0, w1);
             uu[2 * s + 1] = u53(w2, w3);
         }
-        const int nact = pm.n_actions >= 4 ? pm.n_actions : 4;
-        const int act0 = 1 + (int)floor(uu[0] * nact);  // rand(1:4), TD_inversion_function.jl:72
-        pr.action = act0 > nact ? nact : act0;
-        // the (up to) three Gaussian steps of the proposal: one inversion, lanes 0..2 in parallel -- a single copy of the code
-        // whatever the action (the kernel is instruction-cache bound, profiles/README.md)
+        pr.action = action_of(uu[0], pm.n_actions);
+        // the (up to) three Gaussian steps of the proposal: one inversion, lanes 0..2 in parallel
         const double nl = normal_icdf(lane == 0 ? uu[4] : (lane == 1 ? uu[5] : uu[6]));
         nrm[0] = __shfl_sync(0xffffffffu, nl, 0);
         nrm[1] = __shfl_sync(0xffffffffu, nl, 1);
@@ -120,79 +228,7 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
         const tonga_proposal rec = *rec_in;
         pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
     }
-    const int act = pr.action;
-    int valid = 0;
-    if (act == 1) {  // ---- birth :76-125
-        if (K < pm.max_cells) {
-            if (mode == 0) {
-                pr.x = uu[1] * (pm.xmax - pm.xmin) + pm.xmin;  // :78
-                pr.y = uu[2] * (pm.ymax - pm.ymin) + pm.ymin;  // :79
-                pr.z = uu[3] * (pm.zmax - pm.zmin) + pm.zmin;  // :80
-            }
-            const int ci = warp_nearest<SPACE>(nx, ny, nz, K, -1, pr.x, pr.y, pr.z, lane);  // :81
-            const double czeta = ci < 0 ? 0.0 : nzeta[ci];
-            pr.aux = czeta;
-            if (mode == 0) {
-                pr.zeta = czeta + sig_zeta * nrm[0];  // :82
-                pr.u = uu[7];                     // :121
-            }
-            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :92
-            else if (pm.prior == 2) valid = 1;
-            else valid = (pr.zeta > 0);  // :111
-        }
-    } else if (act == 2) {  // ---- death :126-181
-        if (K > pm.min_cells) {
-            if (mode == 0) {
-                const int k = (int)floor(uu[1] * K);  // :128
-                pr.idx = k >= K ? K - 1 : k;
-                pr.u = uu[7];  // :176
-            }
-            const int kill = pr.idx;
-            if (kill >= 0 && kill < K) {
-                const int zi = warp_nearest<SPACE>(nx, ny, nz, K, kill, nx[kill], ny[kill], nz[kill], lane);  // :146
-                pr.aux = zi < 0 ? 0.0 : nzeta[zi];
-                valid = (pm.prior == 3) ? (pr.aux > 0) : 1;  // :165
-            }
-        }
-    } else if (act == 3) {  // ---- change :183-218
-        if (mode == 0) {
-            const int k = (int)floor(uu[1] * K);  // :184
-            pr.idx = k >= K ? K - 1 : k;
-            pr.zeta = nzeta[pr.idx] + sig_zeta * nrm[0];  // :188
-            pr.u = uu[7];                             // :214
-        }
-        if (pr.idx >= 0 && pr.idx < K) {
-            if (pm.prior == 1) valid = (pr.zeta > 0 && pr.zeta < pm.zeta_scale);  // :195
-            else if (pm.prior == 2) valid = 1;
-            else valid = (pr.zeta > 0);  // :206 (alpha = 0 otherwise)
-            // the reference evaluates first (:191) but discards the result when invalid
-        }
-    } else if (act == 4) {  // ---- move :220-251
-        if (K > 0) {
-            if (mode == 0) {
-                const int k = (int)floor(uu[1] * K);  // :222
-                pr.idx = k >= K ? K - 1 : k;
-                const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-                pr.x = nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
-                pr.y = ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
-                pr.z = nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
-                pr.u = uu[7];                                                      // :247
-            }
-            if (pr.idx >= 0 && pr.idx < K) {
-                valid = (pr.x >= pm.xmin && pr.x <= pm.xmax && pr.y >= pm.ymin && pr.y <= pm.ymax && pr.z >= pm.zmin &&
-                         pr.z <= pm.zmax);  // :230-232
-                if (valid) { pr.ox = nx[pr.idx]; pr.oy = ny[pr.idx]; pr.oz = nz[pr.idx]; }
-            }
-        }
-    } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension, see DESIGN.md)
-        if (mode == 0) {
-            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * nrm[0];  // :23,:254
-            pr.u = uu[7];
-        }
-        valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
-    }
-    pr.do_eval = valid;
-    return valid;
+    return assemble_proposal<SPACE>(pr, mode, uu[1], uu[2], uu[3], nrm[0], nrm[1], nrm[2], uu[7], nx, ny, nz, nzeta, K, noise, pm, sig_zeta, lane);
 }
 
 // The acceptance rule, TD_inversion_function.jl:96-97,107-108,113-114 (birth), :151-152,160-162,166-168 (death), :196,202-203,207-208

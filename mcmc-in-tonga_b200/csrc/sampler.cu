@@ -3,19 +3,13 @@
 //
 // One CTA (128 threads) owns one chain for the whole launch.  The chain's state lives in shared memory:
 //   owner8[Ppad]   nearest-nucleus index of every ray point (u8; 0x7F = none; bit 7 = pending tag)
-//   tstar[R]       predicted t* per ray (model.ptS)            tnew[R]  proposal's t* for touched rays
-//   nuclei SoA     x, y, z, zeta [KC]                          zlut[256] owner byte -> zeta under the proposal
-//   mask32 / dirty pending-overwrite bits per point / touched bits per ray
+//   tstar[R]       predicted t* per ray (model.ptS)
+//   nuclei SoA     x, y, z, zeta [KC] (FP64) + fl32 x, y, z;  zp / zqp[129]: owner byte -> zeta, zeta/1000 under the proposal
+//   mask32 / dirtyw  pending-overwrite bits per point / changed bits per 4-point word
 // It is loaded once per launch with TMA bulk copies (cp.async.bulk + mbarrier), nIter iterations run without any
 // global synchronisation, and it is written back once.  The ray geometry (shared by all chains) is streamed from L2
-// with 128-bit loads.  Per iteration:
-//   A  warp 0 draws (Philox4x32-10) or replays the proposal, applies the a-priori checks of the reference, evaluates
-//      v_nearest at the new / killed nucleus (warp argmin, lowest index wins ties) and builds zlut;
-//   B  all threads: the point pass of the action -- birth: d(p,new) < d(p,owner)?; death: orphans of the killed
-//      nucleus rescan the survivors; move: both; change: only marks rays.  Distances are exact FP64 (no FMA);
-//   C  one warp per touched ray re-integrates t* in the canonical order;
-//   D  canonical phi over all rays;  E  thread 0: alpha exactly as TD_inversion_function.jl:96-97,151-152,196,241;
-//   F  commit (accept) or roll back (reject) the pending owner changes;  G  traces / thinning / history.
+// with 128-bit loads.  The iteration itself is described in sampler_kernel.cuh; the state-independent random numbers of a
+// launch are generated beforehand by tg_pregen_kernel.
 // The same canonical t* / phi reductions are used by evaluate.cu, so incremental state == full evaluate bit for bit
 // (tonga_chains_verify checks that on the device).
 #include <algorithm>
@@ -28,6 +22,7 @@
 namespace tg {
 
 constexpr int ST = 128;  // threads per chain CTA (4 warps) == TG_PHI_LANES
+#define TG_RESIDENT_MAX_CHUNKS 8  // the resident sampler keeps its rays' t* in registers: R <= 128 * 8
 static_assert(ST == TG_PHI_LANES, "the canonical phi reduction is defined over 128 lanes");
 
 }  // namespace tg
@@ -83,17 +78,19 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
 // CTA -> chain order of the resident sampler.  A chain's cost per iteration falls with its nCells (fewer, larger cells: more
 // points change owner, more rays are re-integrated), and the launch lasts as long as its slowest SM.  CTAs are dealt to the
 // SMs round-robin in launch order, so launching the chains sorted by K gives every SM one chain of every cost tier.
-// perm[rank] = chain, rank = number of chains with smaller (K, index).
-__global__ void tg_order_kernel(int n, const int32_t *__restrict__ K, int32_t *__restrict__ perm) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        const int kc = K[c];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            const int kj = K[j];
-            rank += (kj < kc) || (kj == kc && j < c);
-        }
-        perm[rank] = c;
+// One CTA: counting sort on K (K <= 127 for the resident sampler), O(n).
+__global__ void __launch_bounds__(1024) tg_order_kernel(int n, const int32_t *__restrict__ K, int32_t *__restrict__ perm) {
+    __shared__ int hist[129], base[129];
+    for (int i = threadIdx.x; i < 129; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) atomicAdd(&hist[min(max(K[c], 0), 128)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < 129; i++) { base[i] = acc; acc += hist[i]; }
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) perm[atomicAdd(&base[min(max(K[c], 0), 128)], 1)] = c;  // order inside a bin is irrelevant
 }
 
 __global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
@@ -264,12 +261,14 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     if (ctx->R < 1 || ctx->P < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: empty ray set");
     const int KC0 = ((pm.max_cells + 7) / 8) * 8;
     const size_t smem_res = tg::smem_layout((int)ctx->Ppad, ctx->Rp, KC0).total;
-    const bool fits = pm.max_cells <= TG_MAX_K_U8 && smem_res <= ctx->smem_optin;
+    const bool fits = pm.max_cells <= TG_MAX_K_U8 && smem_res <= ctx->smem_optin && ctx->R <= 128 * TG_RESIDENT_MAX_CHUNKS && ctx->Ppad < (1 << 18) &&
+                      ctx->max_npts < (1 << 13);
     if (sampler == TONGA_SAMPLER_RESIDENT && !fits) {
         if (pm.max_cells > TG_MAX_K_U8)
             return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the resident sampler needs max_cells <= 126 (u8 owner state)");
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(smem_res) +
-                                                " B) exceeds shared memory; the smem-resident sampler handles ray sets up to ~200k points");
+                                                " B) exceeds shared memory, or more than " + std::to_string(128 * TG_RESIDENT_MAX_CHUNKS) +
+                                                " rays; the smem-resident sampler handles ray sets up to ~200k points");
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
@@ -406,10 +405,10 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_CUDA(cudaStreamSynchronize(s));
     }
     if (!wide) {
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     }
     if (8 * 4 * KC > 48 * 1024) {
         if (8 * 4 * KC > ctx->smem_optin) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: max_cells too large for shared memory");
@@ -547,8 +546,11 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     cudaStream_t s = ctx->stream;
     const size_t n = (size_t)ch->n, N = n * (size_t)nIter;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // resident sampler, mode 0: raw draws of one piece of the launch (64 B per chain-iteration, at most 256 MB)
+    const int64_t raw_iters = std::max<int64_t>(1, std::min<int64_t>(nIter, (int64_t)((256u << 20) / (64 * n))));
     const size_t o_rec = 0, o_acc = o_rec + (recs ? al(sizeof(tonga_proposal) * N) : 0), o_phi = o_acc + (tr_accept ? al(N) : 0),
-                 o_K = o_phi + (tr_phi ? al(8 * N) : 0), total = o_K + (tr_K ? al(4 * N) : 0);
+                 o_K = o_phi + (tr_phi ? al(8 * N) : 0), o_raw = o_K + (tr_K ? al(4 * N) : 0),
+                 total = o_raw + ((!ch->wide && mode == 0) ? al(64 * n * (size_t)raw_iters) : 0);
     int rc = tg::ensure_scratch(ctx, total);
     if (rc != TONGA_OK) return rc;
     char *d = (char *)ctx->d_scratch;
@@ -575,8 +577,8 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         w.active = ch->streamed ? ch->d_active : nullptr; w.n_active = ch->streamed ? ch->d_active + ch->n : nullptr;
         tg::StreamArgs sa{};
         sa.tiles = ch->d_stiles; sa.pxf = ctx->d_pxf; sa.pyf = ctx->d_pyf; sa.pzf = ctx->d_pzf; sa.px = ctx->d_px; sa.py = ctx->d_py; sa.pz = ctx->d_pz;
-        sa.dtT = ctx->d_dtT; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
-        sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.ldT = ctx->ldT; sa.tile_pts = ch->stile_pts;
+        sa.dt = ctx->d_dt; sa.ray_off = ctx->d_ray_off; sa.tol_alpha = ctx->tol_alpha; sa.tol_beta2 = ctx->tol_beta2;
+        sa.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0; sa.KC = ch->KC; sa.Rp = ch->Rp; sa.tile_pts = ch->stile_pts;
         sa.Ppad = ctx->Ppad; sa.props = ch->d_props; sa.Kc = ch->d_Kc; sa.cells_c = ch->d_cells_c; sa.cells_cf = ch->d_cells_cf; sa.n_chains = ch->n; sa.owner = ch->d_owner16; sa.dcache = ch->d_dcache;
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
         sa.tile_changed = ch->d_tile_changed; sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
@@ -599,33 +601,45 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         TG_CUDA(cudaGetLastError());
     } else {
     tg::SamplerArgs a{};
-    a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dtT = ctx->d_dtT; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
+    a.px = ctx->d_px; a.py = ctx->d_py; a.pz = ctx->d_pz; a.dt = ctx->d_dt; a.tS = ctx->d_tS; a.sig = ctx->d_sig;
     a.pxf = ctx->d_pxf; a.pyf = ctx->d_pyf; a.pzf = ctx->d_pzf; a.tol_alpha = ctx->tol_alpha; a.tol_beta2 = ctx->tol_beta2;
-    a.exact_only = ch->exact_only;
+    a.exact_only = (ch->exact_only || ctx->exact_only) ? 1 : 0;
     a.prof = ch->d_prof;
-    a.rayid = ctx->d_rayid; a.ray_off = ctx->d_ray_off; a.ray_orig = ctx->d_ray_orig; a.ray_rank = ctx->d_ray_rank;
-    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.ldT = ctx->ldT; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad; a.n_sm = ctx->sm_count > 0 ? ctx->sm_count : 1;
+    a.ray_off = ctx->d_ray_off; a.ray_rank = ctx->d_ray_rank;
+    a.R = ctx->R; a.Rp = ch->Rp; a.KC = ch->KC; a.P = (int)ctx->P; a.Ppad = (int)ctx->Ppad;
     a.prm = ctx->prm;
     a.K = ch->d_K; a.cells = ch->d_cells; a.phi = ch->d_phi; a.noise = ch->d_noise; a.beta = ch->d_beta;
     a.owner = ch->d_owner; a.dcache = ch->d_dcache; a.tstar = ch->d_tstar; a.counts = ch->d_counts; a.pending_slot = ch->d_pending;
-    a.iter0 = ch->iter_done + 1; a.nIter = nIter; a.mode = mode;
+    a.mode = mode; a.trace_stride = nIter;
     a.recs_in = recs_in; a.recs_out = recs_out; a.tr_accept = d_tr_accept; a.tr_phi = d_tr_phi; a.tr_K = d_tr_K;
-    a.seed = ch->seed; a.chain_id0 = ch->chain_id0;
+    a.chain_id0 = ch->chain_id0;
     a.hist_cap = ch->hist_cap; a.n_hist = ch->d_n_hist; a.model_num = ch->d_model_num;
     a.hist_K = ch->d_hist_K; a.hist_cells = ch->d_hist_cells; a.hist_phi = ch->d_hist_phi; a.hist_ptS = ch->d_hist_ptS;
     a.hist_iter = ch->d_hist_iter; a.hist_action = ch->d_hist_action; a.hist_accept = ch->d_hist_accept; a.hist_next = ch->d_hist_next;
-    if (ch->n <= 16384 && !ch->no_order) {
-        tg::tg_order_kernel<<<(ch->n + 255) / 256, 256, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
-        a.perm = ch->d_perm;
+    a.raw = (const tg::RawDraw *)(d + o_raw);
+    // the launch is cut into pieces of at most raw_iters iterations (the raw draws of a piece are generated just before it)
+    for (int64_t it0 = 0; it0 < nIter; it0 += raw_iters) {
+        const int64_t ni = std::min<int64_t>(raw_iters, nIter - it0);
+        a.it0 = it0; a.nIter = ni; a.iter0 = ch->iter_done + 1 + it0;
+        if (mode == 0) {
+            const long long tot = (long long)ch->n * ni;
+            tg::tg_pregen_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ch->n, ni, a.iter0, ch->seed, ch->chain_id0, ctx->prm.n_actions, (tg::RawDraw *)(d + o_raw));
+        }
+        a.perm = nullptr;
+        if (!ch->no_order) {
+            tg::tg_order_kernel<<<1, 1024, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
+            a.perm = ch->d_perm;
+        }
+        const bool small = ctx->R <= 128 * 3;
+        if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
+            if (small) tg::tg_sampler_kernel<3, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+        } else {
+            if (small) tg::tg_sampler_kernel<3, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+        }
+        TG_CUDA(cudaGetLastError());
     }
-    if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
-        if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
-        else tg::tg_sampler_kernel<uint32_t, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
-    } else {
-        if (ctx->Ppad <= 65536) tg::tg_sampler_kernel<uint16_t, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
-        else tg::tg_sampler_kernel<uint32_t, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
-    }
-    TG_CUDA(cudaGetLastError());
     }
     TG_CUDA(cudaEventRecord(ch->ev1, s));
     ch->iter_done += nIter;

@@ -6,11 +6,10 @@
 //   * per-segment term exactly as MCsub.jl:147,153: (rayl*rayu) * ((0.5*(za+zb)) / 1000); the division is done
 //     with a 3-op FMA sequence that returns the correctly rounded quotient (checked against `/` on 3e8 samples);
 //   * per-ray misfit term exactly as MCsub.jl:171: ((d*d)*1.0) / (sig*sig);
-//   * ONE canonical summation order, shared by the full evaluate kernel and the incremental sampler kernel, so
-//     "incremental == full" holds bit for bit on the device: t* of a ray is the plain left-to-right sum over its
-//     segments (the reference's own order -- Julia `sum`, SIMD pairwise -- is unspecified); phi is a fixed 128-lane
-//     strided sum + butterfly over the rays in length-sorted order (the reference sums k = 1..R sequentially), hence
-//     a 1e-9 relative tolerance on phi, none on the owners, and t* equal to a left-to-right CPU sum bit for bit.
+//   * ONE canonical summation order, shared by every kernel, so "incremental == full" holds bit for bit on the device:
+//     t* of a ray is an 8-lane interleaved sum + butterfly (tstar_g8; the reference's own order -- Julia `sum`, SIMD
+//     pairwise -- is unspecified); phi is a fixed 128-lane strided sum + butterfly over the rays in length-sorted order
+//     (the reference sums k = 1..R sequentially); hence a 1e-9 relative tolerance on t* and phi, none on the owners.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -80,49 +79,39 @@ __device__ __forceinline__ double warp_sum_canonical(double v) {
     return v;
 }
 
-// Canonical t* of one ray: the plain left-to-right sum over its segments (the order the CPU oracle uses too, so t* is
-// bit-identical to the oracle's).  One THREAD walks one ray; rays are sorted by length so the 32 rays of a warp finish
-// together, and dt is stored segment-major (dtT[j][ray]) so the warp's loads coalesce.  n = #points of the ray,
-// `last` = common trip bound of the warp (max n over its active lanes) to keep the loop warp-uniform.
-// Column of (length-sorted) ray r in dtT.  The sampler deals sorted rays to its 4 warps round-robin (rank = slot*128 +
-// lane*4 + warp) so that every warp gets the same mix of ray lengths; dtT columns are stored in thread order
-// (slot*128 + warp*32 + lane) so that the warp's loads still coalesce.
-__host__ __device__ __forceinline__ int dt_col(int r) { return (r & ~127) | ((r & 3) << 5) | ((r & 127) >> 2); }
-
-template <typename OwnerT, typename ZetaOf>
-__device__ __forceinline__ double ray_tstar_seq(const OwnerT *__restrict__ owner, const double *__restrict__ dtT, int ldT, int r,
-                                                int p0, int n, ZetaOf zeta_of) {
+// Canonical t* of one ray (shared by every kernel, so "incremental == full" holds bit for bit): a GROUP OF 8 LANES owns the
+// ray; lane s (0..7) adds the terms of segments j = s, s+8, s+16, ... in ascending order into an accumulator that starts
+// at 0.0, then the 8 partial sums are combined by the xor butterfly 4, 2, 1 (every lane ends with the same value).  A warp
+// integrates 4 rays at a time; `trip` is the warp-uniform number of passes (>= ceil(nseg / 8) of every group in the warp),
+// groups without a ray pass nseg = 0.  term(j) is only called for j < nseg.  The reference's own order (Julia `sum` over a
+// broadcast vector, MCsub.jl:153/159) is SIMD-pairwise and unspecified; the contract on t* is 1e-9 relative.
+// dt is stored flat, in point order: dt[p] = rayl*rayu of the segment from flat point p to p+1 (0.0 at the last point of a ray).
+template <typename TermOf>
+__device__ __forceinline__ double tstar_g8(int nseg, int trip, int sub, TermOf term) {
     double acc = 0.0;
-    if (n > 1) {
-        const double *__restrict__ col = dtT + dt_col(r);
-        double za = zeta_of(owner[p0]);
-        int j = 0;
-        for (; j + 8 <= n - 1; j += 8) {  // 8 independent dt loads in flight, then the ordered adds
-            double d[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) d[u] = col[(size_t)(j + u) * ldT];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const double zb = zeta_of(owner[p0 + j + u + 1]);
-                acc = __dadd_rn(acc, seg_term(d[u], za, zb));
-                za = zb;
-            }
-        }
-        for (; j < n - 1; j++) {
-            const double zb = zeta_of(owner[p0 + j + 1]);
-            acc = __dadd_rn(acc, seg_term(col[(size_t)j * ldT], za, zb));
-            za = zb;
-        }
+    for (int k = 0; k < trip; k++) {
+        const int j = 8 * k + sub;
+        if (j < nseg) acc = __dadd_rn(acc, term(j));
     }
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
     return acc;
 }
 
-// Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES (=128) threads (4 warps).
+// Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES (=128) threads (4 warps): thread (warp w, lane l)
+// adds the terms of the (length-sorted) rays r = 128 c + 4 l + w, c = 0, 1, ... in ascending order (so every warp gets the
+// same mix of ray lengths -- the resident sampler integrates t* of ray r on warp r & 3 and keeps it in that thread's
+// registers), then xor butterfly inside the warp, then the 4 warp sums left to right.
+__device__ __forceinline__ int phi_ray(int c, int t128) { return (c << 7) | ((t128 & 31) << 2) | (t128 >> 5); }
 // term(r) must be callable by any thread.  scratch: 4 doubles of shared memory.  Result valid in all threads.
 template <typename TermOf>
 __device__ __forceinline__ double phi_canonical_128(int R, int t128, double *scratch, TermOf term) {
     double acc = 0.0;
-    for (int r = t128; r < R; r += TG_PHI_LANES) acc = __dadd_rn(acc, term(r));
+    for (int c = 0; (c << 7) < R; c++) {
+        const int r = phi_ray(c, t128);
+        if (r < R) acc = __dadd_rn(acc, term(r));
+    }
     acc = warp_sum_canonical(acc);
     if ((t128 & 31) == 0) scratch[t128 >> 5] = acc;
     __syncthreads();
@@ -208,8 +197,7 @@ struct tonga_ctx {
     float tol_alpha = 0.f, tol_beta2 = 0.f;                    // screening band: |dc - do| <= alpha*(dc+do) + beta2 -> exact FP64 recheck
     // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
     // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.
-    double *d_dtT = nullptr;                                   // [max(m-1,1)][ldT] dt = rayL*rayU, segment-major, column dt_col(r)
-    int ldT = 0;                                               // R rounded up to a multiple of 128
+    double *d_dt = nullptr;                                    // [Ppad] dt = rayL*rayU of the segment p -> p+1 (0.0 at the last point of a ray and in the padding)
     int32_t *d_rayid = nullptr;                                // [Ppad] sorted ray index of each flat point
     int32_t *d_ray_off = nullptr;                              // [R+1]  CSR offsets over sorted rays
     int32_t *d_ray_orig = nullptr;                             // [R]    sorted ray index -> caller's ray index

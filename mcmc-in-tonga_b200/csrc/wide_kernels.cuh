@@ -133,15 +133,18 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             if (a.streamed && act != 5) {  // the candidate pass left the per-ray misfit terms: canonical sum only
                 const double *trm = a.term_c + (size_t)chain * a.Rp;
                 double acc = 0.0;
-                int r = tid;
-                for (; r + 7 * TG_PHI_LANES < R; r += 8 * TG_PHI_LANES) {  // 8 loads in flight, then the ordered adds
+                int c = 0;
+                for (; ((c + 7) << 7) + TG_PHI_LANES <= R; c += 8) {  // 8 loads in flight, then the ordered adds (canonical phi order, phi_ray)
                     double v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = trm[r + u * TG_PHI_LANES];
+                    for (int u = 0; u < 8; u++) v[u] = trm[phi_ray(c + u, tid)];
 #pragma unroll
                     for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
                 }
-                for (; r < R; r += TG_PHI_LANES) acc = __dadd_rn(acc, trm[r]);
+                for (; (c << 7) < R; c++) {
+                    const int r = phi_ray(c, tid);
+                    if (r < R) acc = __dadd_rn(acc, trm[r]);
+                }
                 acc = warp_sum_canonical(acc);
                 if ((tid & 31) == 0) scratch[tid >> 5] = acc;
                 __syncthreads();
@@ -228,10 +231,10 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
 struct StreamArgs {
     const Tile *tiles;
     const float *pxf, *pyf, *pzf;
-    const double *px, *py, *pz, *dtT;
+    const double *px, *py, *pz, *dt;
     const int32_t *ray_off;
     float tol_alpha, tol_beta2;
-    int exact_only, KC, Rp, ldT, tile_pts;
+    int exact_only, KC, Rp, tile_pts;
     long long Ppad;
     const Prop *props;
     const int32_t *Kc;        // candidate nCells (-1: nothing to evaluate)
@@ -254,24 +257,6 @@ constexpr int STREAM_THREADS = 256;
 constexpr int STREAM_GROUP = 1;  // active chains a CTA processes one after the other on its tile (coordinates re-read from L1)
 constexpr int STREAM_PPT = 4;  // points per thread and batch of phase 1 (all loads of a batch are issued before the first use)
 #define TG_NONE16S 0xFFFFu
-
-// Warp-cooperative t* of one ray in the canonical left-to-right order: the lanes compute the 32 segment terms of a batch in
-// parallel (dt load, zeta gather, seg_term); the ordered sum is then formed by adding the lanes' terms one by one, which is
-// the same sequence of additions as ray_tstar_seq.  Result valid in all lanes.
-template <typename ZetaOf>
-__device__ __forceinline__ double ray_tstar_warp(const uint16_t *owner /* of the ray's first point */, const double *__restrict__ dtT, int ldT,
-                                                 int r, int n, int lane, ZetaOf zeta_of) {
-    double acc = 0.0;
-    const double *__restrict__ col = dtT + dt_col(r);
-    for (int j0 = 0; j0 < n - 1; j0 += 32) {
-        const int j = j0 + lane;
-        double term = 0.0;
-        if (j < n - 1) term = seg_term(col[(size_t)j * ldT], zeta_of(owner[j]), zeta_of(owner[j + 1]));
-        const int cnt = min(32, n - 1 - j0);
-        for (int i = 0; i < cnt; i++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, term, i));
-    }
-    return acc;
-}
 
 template <bool COMMIT>
 __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const StreamArgs a) {
@@ -498,7 +483,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
         if (tid == 0) a.tile_changed[(size_t)chain * a.n_tiles + blockIdx.x / n_groups] = (uint8_t)(any != 0);
     }
     // ---- phase 2: t* of the tile's rays.  Rays without a changed point keep their t*; the others are listed and re-integrated
-    // by the warps, one ray at a time (ray_tstar_warp: canonical left-to-right sum).
+    // by the warps in the canonical order.
     const double *zc = cc + 3 * (size_t)a.KC;
     auto zeta_of = [&](uint16_t o) -> double { return o == TG_NONE16S ? 0.0 : zc[o]; };
     const double *ts = a.tstar + (size_t)chain * a.Rp;
@@ -520,11 +505,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     }
     __syncthreads();
     const int nd = s_cnt[1];
-    for (int e = warp; e < nd; e += STREAM_THREADS / 32) {
-        const int r = tile.r0 + s_queue[e];
-        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
-        const double t = ray_tstar_warp(s_owner + (q0 - p0a), a.dtT, a.ldT, r, n, lane, zeta_of);
-        if (lane == 0) { tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
+    for (int eb = 4 * warp; eb < nd; eb += 4 * (STREAM_THREADS / 32)) {  // canonical t* (tstar_g8): 8 lanes per ray, 4 rays per warp
+        const int e = eb + (lane >> 3);
+        const bool on = e < nd;
+        const int r = tile.r0 + (on ? s_queue[e] : 0);
+        const int q0 = on ? a.ray_off[r] : 0, n = on ? a.ray_off[r + 1] - q0 : 0;
+        const int nseg = n > 1 ? n - 1 : 0;
+        const int trip = __reduce_max_sync(0xffffffffu, (nseg + 7) >> 3);
+        const uint16_t *ow = s_owner + (q0 - p0a);
+        const double t = tstar_g8(nseg, trip, lane & 7, [&](int j) { return seg_term(a.dt[q0 + j], zeta_of(ow[j]), zeta_of(ow[j + 1])); });
+        if (on && (lane & 7) == 0) { tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
     }
     }
 }
