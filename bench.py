@@ -157,7 +157,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "shipped 381-ray Tonga geometry (tests/golden/tonga381.npz), slowness synthesised from ak135",
+            "vs_baseline": None, "dtype": "f64", "data": "shipped 381-ray Tonga geometry (tonga_b200/datasets/tonga381.npz), slowness synthesised from ak135",
             "config": {"workload": WORKLOAD, "note": "reference algorithm = C restatement of MCsub.jl/TD_inversion_function.jl (julia not installed); full evaluate per proposal as the reference does"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -303,7 +303,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "shipped 381-ray Tonga geometry (tests/golden/tonga381.npz), slowness synthesised from ak135; device Philox proposals",
+            "dtype": "f64", "data": "shipped 381-ray Tonga geometry (tonga_b200/datasets/tonga381.npz), slowness synthesised from ak135; device Philox proposals",
             "config": {"workload": WORKLOAD, "chains_per_gpu": n, "chains_total": n * world, "iters_per_step": args.iters,
                        "burn_in": int(p.burn_in), "keep_each": int(p.keep_each), "kept_models_per_chain_per_step": n_kept,
                        "prior": "uniform", "cells": [p.min_cells, p.max_cells], "parallelism": f"chain-sharded x{world}",

@@ -104,7 +104,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     for (int rs = 0; rs < R; rs++) sray_off[rs + 1] = sray_off[rs] + (ray_off[ray_orig[rs] + 1] - ray_off[ray_orig[rs]]);
     const double qnan = std::nan("");
     std::vector<double> px(Ppad, qnan), py(Ppad, qnan), pz(Ppad, qnan);
-    std::vector<double> dt(Ppad, 0.0);  // flat, point order: dt[p] = segment p -> p+1
+    std::vector<double> dt(Ppad + max_npts + 128, 0.0);  // flat, point order: dt[p] = segment p -> p+1; zero slack for unconditional batched loads
     std::vector<int32_t> rayid(Ppad, 0), point_orig(Ppad, -1);
     std::vector<double> tS_s(R), sig_s(R);
     int64_t S = 0;
@@ -188,7 +188,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     chk(upload(&ctx->d_pz, pz, ctx->stream));
     {   // fl32 copies + the rigorous screening band: with u = 2^-24 and M = max |coordinate| (points and box),
         // |D32 - D| <= 11u*D32 + 7.5u*M^2 for any evaluation order; alpha = 16u and beta = 12u*M^2 leave a 1.4x margin.
-        std::vector<float> xf(Ppad), yf(Ppad), zf(Ppad);
+        std::vector<float> xf(Ppad + TG_PT_SLACK, 0.f), yf(Ppad + TG_PT_SLACK, 0.f), zf(Ppad + TG_PT_SLACK, 0.f);
         double M = 0.0;
         for (int64_t i = 0; i < Ppad; i++) {
             xf[i] = (float)px[i]; yf[i] = (float)py[i]; zf[i] = (float)pz[i];

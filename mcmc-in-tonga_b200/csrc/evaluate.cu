@@ -178,7 +178,7 @@ tg_phi_kernel(int R, const double *__restrict__ ptS /* caller's ray order */, co
     }
     const double nz = noise ? noise[model] : 1.0;
     const double *t = ptS + (size_t)model * R;
-    const double v = phi_canonical_128(R, threadIdx.x, scratch, [&](int r) { return misfit_term(t[ray_orig[r]], tS[r], sig[r], nz); });
+    const double v = phi_canonical(R, threadIdx.x, scratch, [&](int r) { return misfit_term(t[ray_orig[r]], tS[r], sig[r], nz); });
     if (threadIdx.x == 0) phi[model] = v;
 }
 

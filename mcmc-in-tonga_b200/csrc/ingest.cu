@@ -192,13 +192,16 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
     TG_CUDA(cudaMalloc((void **)&ctx->d_px, 8 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_py, 8 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_pz, 8 * (size_t)Ppad));
-    TG_CUDA(cudaMalloc((void **)&ctx->d_pxf, 4 * (size_t)Ppad));
-    TG_CUDA(cudaMalloc((void **)&ctx->d_pyf, 4 * (size_t)Ppad));
-    TG_CUDA(cudaMalloc((void **)&ctx->d_pzf, 4 * (size_t)Ppad));
+    TG_CUDA(cudaMalloc((void **)&ctx->d_pxf, 4 * (size_t)(Ppad + TG_PT_SLACK)));
+    TG_CUDA(cudaMemsetAsync(ctx->d_pxf, 0, 4 * (size_t)(Ppad + TG_PT_SLACK), s));
+    TG_CUDA(cudaMalloc((void **)&ctx->d_pyf, 4 * (size_t)(Ppad + TG_PT_SLACK)));
+    TG_CUDA(cudaMemsetAsync(ctx->d_pyf, 0, 4 * (size_t)(Ppad + TG_PT_SLACK), s));
+    TG_CUDA(cudaMalloc((void **)&ctx->d_pzf, 4 * (size_t)(Ppad + TG_PT_SLACK)));
+    TG_CUDA(cudaMemsetAsync(ctx->d_pzf, 0, 4 * (size_t)(Ppad + TG_PT_SLACK), s));
     TG_CUDA(cudaMalloc((void **)&ctx->d_rayid, 4 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_point_orig, 4 * (size_t)Ppad));
-    TG_CUDA(cudaMalloc((void **)&ctx->d_dt, 8 * (size_t)Ppad));
-    TG_CUDA(cudaMemsetAsync(ctx->d_dt, 0, 8 * (size_t)Ppad, s));
+    TG_CUDA(cudaMalloc((void **)&ctx->d_dt, 8 * (size_t)(Ppad + max_npts + 128)));  // zero slack for unconditional batched loads
+    TG_CUDA(cudaMemsetAsync(ctx->d_dt, 0, 8 * (size_t)(Ppad + max_npts + 128), s));
     int rcs = tg::ensure_scratch(ctx, 8);
     if (rcs != TONGA_OK) return rcs;
     TG_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 8, s));

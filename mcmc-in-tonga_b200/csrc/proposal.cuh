@@ -84,6 +84,12 @@ __device__ __forceinline__ double normal_icdf(double u) {
     return q < 0.0 ? -v : v;
 }
 
+// IEEE division / natural logarithm as real function calls: the acceptance rule below has ~20 division sites over its prior
+// variants and is executed once per iteration; inlined they were 1.5 k SASS instructions of a kernel that is bound by
+// instruction supply (profiles/README.md).  Same results as the inlined operators.
+static __device__ __noinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ __noinline__ double log_fn(double a) { return log(a); }
+
 // The state-independent part of one iteration's random numbers ("raw draw"): Philox4x32-10 keyed by `seed`, counter =
 // (iteration, global chain id, slot 0..3) -> 8 uniforms uu[0..7]; action from uu[0] (rand(1:4), TD_inversion_function.jl:72),
 // uu[1..3] position / index uniforms, three standard normals by inversion of uu[4..6], uu[7] the accept uniform.
@@ -125,6 +131,7 @@ __device__ __forceinline__ int assemble_proposal(Prop &pr, int mode, double u1, 
                                                  const double *nx, const double *ny, const double *nz, const double *nzeta, int K, double noise,
                                                  const tonga_params &pm, double sig_zeta, int lane) {
     const int act = pr.action;
+    const double s100 = div_rn(pm.sig, 100);
     int valid = 0;
     if (act == 1) {  // ---- birth :76-125
         if (K < pm.max_cells) {
@@ -176,9 +183,9 @@ __device__ __forceinline__ int assemble_proposal(Prop &pr, int mode, double u1, 
             if (mode == 0) {
                 const int k = (int)floor(u1 * K);  // :222
                 pr.idx = k >= K ? K - 1 : k;
-                pr.x = nx[pr.idx] + ((pm.sig / 100) * (pm.xmax - pm.xmin)) * n0;  // :30,:226
-                pr.y = ny[pr.idx] + ((pm.sig / 100) * (pm.ymax - pm.ymin)) * n1;  // :31,:227
-                pr.z = nz[pr.idx] + ((pm.sig / 100) * (pm.zmax - pm.zmin)) * n2;  // :32,:228
+                pr.x = nx[pr.idx] + (s100 * (pm.xmax - pm.xmin)) * n0;  // :30,:226
+                pr.y = ny[pr.idx] + (s100 * (pm.ymax - pm.ymin)) * n1;  // :31,:227
+                pr.z = nz[pr.idx] + (s100 * (pm.zmax - pm.zmin)) * n2;  // :32,:228
                 pr.u = u7;                                                         // :247
             }
             if (pr.idx >= 0 && pr.idx < K) {
@@ -189,7 +196,7 @@ __device__ __forceinline__ int assemble_proposal(Prop &pr, int mode, double u1, 
         }
     } else if (act == 5) {  // ---- sigma :252-272 (dead code in the reference; extension)
         if (mode == 0) {
-            pr.zeta = noise + (pm.max_sig * pm.sig / 100) * n0;  // :23,:254
+            pr.zeta = noise + div_rn(pm.max_sig * pm.sig, 100) * n0;  // :23,:254
             pr.u = u7;
         }
         valid = (pr.zeta > 0 && pr.zeta < pm.max_sig);  // :257
@@ -232,48 +239,44 @@ __device__ __forceinline__ int draw_proposal(Prop &pr, int mode, const tonga_pro
 }
 
 // The acceptance rule, TD_inversion_function.jl:96-97,107-108,113-114 (birth), :151-152,160-162,166-168 (death), :196,202-203,207-208
-// (change), :241-242 (move), :264-267 (sigma, extension), with the reference's operation order.  K = nCells of the CURRENT
-// model, zeta_idx = current zeta[idx] (death / change), beta = inverse temperature (1 = reference), R = number of data.
+// (change), :241-242 (move), :264-267 (sigma, extension), with the reference's operation order: every variant has the form
+// (ratio * constant) * exp(argument) or exp(argument), so the branches only build the three pieces and ONE exp follows.
+// K = nCells of the CURRENT model, zeta_idx = current zeta[idx] (death / change), beta = inverse temperature (1 = reference),
+// R = number of data.
 __device__ __forceinline__ int accept_decision(const Prop &pr, int K, double phi, double phin, double zeta_idx, double noise, double beta,
                                                int R, const tonga_params &pm, double sig_zeta) {
-    const double PI = 3.141592653589793;
+    const double SQ2PI = 2.5066282746310002;  // sqrt(2 * 3.141592653589793), correctly rounded
     const int act = pr.action;
-    const double K0 = (double)K;
+    const double K0 = (double)K, zs = pm.zeta_scale;
     const double zn = pr.zeta, aux = pr.aux, u = pr.u;
     const double dphi2 = beta * ((phin - phi) / 2);
-    double alpha = 0.0;
+    if (act == 5) {  // sigma: log form :264-267
+        double la = beta * (log_fn(div_rn(noise, zn)) * (double)R) - dphi2;  // beta = 1: TD_inversion_function.jl:264
+        la = (la != la) ? la : (la < 0.0 ? la : 0.0);
+        return log_fn(u) <= la;
+    }
+    double pre = 1.0, arg = -dphi2;  // change (prior 1) :196 and move :241-242: alpha = exp(-dphi2)
     if (act == 1) {
-        const double g = ((aux - zn) * (aux - zn)) / (2 * (sig_zeta * sig_zeta));
-        if (pm.prior == 1)  // :96-97
-            alpha = ((K0) / (K0 + 1)) * ((sig_zeta * sqrt(2 * PI)) / (pm.zeta_scale)) * exp(g - dphi2);
-        else if (pm.prior == 2)  // :107-108
-            alpha = ((K0) / (K0 + 1)) * (sig_zeta / pm.zeta_scale) * exp(-(zn * zn) / (pm.zeta_scale * pm.zeta_scale) + g - dphi2);
-        else  // :113-114
-            alpha = ((K0) / (K0 + 1)) * (sqrt(2 * PI) * sig_zeta / pm.zeta_scale) * exp(-zn / pm.zeta_scale + g - dphi2);
-        return u < jl_min1(alpha);
+        const double g = div_rn((aux - zn) * (aux - zn), 2 * (sig_zeta * sig_zeta));
+        const double ratio = div_rn(K0, K0 + 1);
+        if (pm.prior == 1) { pre = ratio * div_rn(sig_zeta * SQ2PI, zs); arg = g - dphi2; }                                   // :96-97
+        else if (pm.prior == 2) { pre = ratio * div_rn(sig_zeta, zs); arg = -div_rn(zn * zn, zs * zs) + g - dphi2; }          // :107-108
+        else { pre = ratio * div_rn(SQ2PI * sig_zeta, zs); arg = -div_rn(zn, zs) + g - dphi2; }                               // :113-114
     } else if (act == 2) {
         const double zk = zeta_idx;
-        const double g = ((zk - aux) * (zk - aux)) / (2 * (sig_zeta * sig_zeta));
-        if (pm.prior == 1)  // :151-152
-            alpha = ((K0) / (K0 - 1)) * ((pm.zeta_scale) / (sig_zeta * sqrt(2 * PI))) * exp(-g - dphi2);
-        else if (pm.prior == 2)  // :160-162
-            alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / sig_zeta) * exp((zk * zk) / (2 * (pm.zeta_scale * pm.zeta_scale)) - g - dphi2);
-        else  // :166-168
-            alpha = ((K0) / (K0 - 1)) * (pm.zeta_scale / (sqrt(2 * PI) * sig_zeta)) * exp(zk / pm.zeta_scale - g - dphi2);
-        return u < jl_min1(alpha);
+        const double g = div_rn((zk - aux) * (zk - aux), 2 * (sig_zeta * sig_zeta));
+        const double ratio = div_rn(K0, K0 - 1);
+        if (pm.prior == 1) { pre = ratio * div_rn(zs, sig_zeta * SQ2PI); arg = -g - dphi2; }                                  // :151-152
+        else if (pm.prior == 2) { pre = ratio * div_rn(zs, sig_zeta); arg = div_rn(zk * zk, 2 * (zs * zs)) - g - dphi2; }     // :160-162
+        else { pre = ratio * div_rn(zs, SQ2PI * sig_zeta); arg = div_rn(zk, zs) - g - dphi2; }                                // :166-168
     } else if (act == 3) {
         const double zo = zeta_idx;
-        if (pm.prior == 1) alpha = exp(-dphi2);  // :196
-        else if (pm.prior == 2) alpha = exp((zo * zo - zn * zn) / (2 * (pm.zeta_scale * pm.zeta_scale)) - dphi2);  // :202-203
-        else alpha = exp((zo - zn) / pm.zeta_scale - dphi2);  // :207-208
-        return u < jl_min1(alpha);
-    } else if (act == 4) {
-        return u < jl_min1(exp(-dphi2));  // :241-242
+        if (pm.prior == 2) arg = div_rn(zo * zo - zn * zn, 2 * (zs * zs)) - dphi2;  // :202-203
+        else if (pm.prior == 3) arg = div_rn(zo - zn, zs) - dphi2;                 // :207-208
     }
-    // sigma: log form :264-267
-    double la = beta * (log(noise / zn) * (double)R) - dphi2;  // beta = 1: TD_inversion_function.jl:264
-    la = (la != la) ? la : (la < 0.0 ? la : 0.0);
-    return log(u) <= la;
+    const double e = exp(arg);
+    const double alpha = (act <= 2) ? pre * e : e;  // (ratio * constant) * exp(...), as the reference associates it
+    return u < jl_min1(alpha);
 }
 
 }  // namespace tg

@@ -21,9 +21,11 @@
 
 namespace tg {
 
-constexpr int ST = 128;  // threads per chain CTA (4 warps) == TG_PHI_LANES
-#define TG_RESIDENT_MAX_CHUNKS 8  // the resident sampler keeps its rays' t* in registers: R <= 128 * 8
-static_assert(ST == TG_PHI_LANES, "the canonical phi reduction is defined over 128 lanes");
+constexpr int ST = TG_PHI_LANES;  // threads per chain CTA
+constexpr int NW = TG_PHI_WARPS;  // warps per chain CTA
+#define TG_SMALL_CHUNKS ((384 + TG_PHI_LANES - 1) / TG_PHI_LANES)  // instantiation for ray sets up to 384 rays (the 381-ray Tonga set)
+#define TG_RESIDENT_MAX_CHUNKS 8  // the resident sampler keeps its rays' t* in registers: R <= ST * 8
+
 
 }  // namespace tg
 
@@ -261,13 +263,13 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     if (ctx->R < 1 || ctx->P < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_create: empty ray set");
     const int KC0 = ((pm.max_cells + 7) / 8) * 8;
     const size_t smem_res = tg::smem_layout((int)ctx->Ppad, ctx->Rp, KC0).total;
-    const bool fits = pm.max_cells <= TG_MAX_K_U8 && smem_res <= ctx->smem_optin && ctx->R <= 128 * TG_RESIDENT_MAX_CHUNKS && ctx->Ppad < (1 << 18) &&
+    const bool fits = pm.max_cells <= TG_MAX_K_U8 && smem_res <= ctx->smem_optin && ctx->R <= tg::ST * TG_RESIDENT_MAX_CHUNKS && ctx->Ppad < (1 << 18) &&
                       ctx->max_npts < (1 << 13);
     if (sampler == TONGA_SAMPLER_RESIDENT && !fits) {
         if (pm.max_cells > TG_MAX_K_U8)
             return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: the resident sampler needs max_cells <= 126 (u8 owner state)");
         return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: per-chain state (" + std::to_string(smem_res) +
-                                                " B) exceeds shared memory, or more than " + std::to_string(128 * TG_RESIDENT_MAX_CHUNKS) +
+                                                " B) exceeds shared memory, or more than " + std::to_string(tg::ST * TG_RESIDENT_MAX_CHUNKS) +
                                                 " rays; the smem-resident sampler handles ray sets up to ~200k points");
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -332,7 +334,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     TG_ALLOC(ch->d_tstar, 8 * n * Rp);
     if (!wide) {
         TG_ALLOC(ch->d_owner, n * Pp);
-        TG_ALLOC(ch->d_dcache, 4 * n * Pp);
+        TG_ALLOC(ch->d_dcache, 4 * (n * Pp + TG_PT_SLACK));
+        TG_CUDA(cudaMemsetAsync(ch->d_dcache, 0, 4 * (n * Pp + TG_PT_SLACK), ctx->stream));
         TG_ALLOC(ch->d_dcache_tmp, 4 * n * Pp);
         TG_ALLOC(ch->d_owner_tmp, n * Pp);
     } else {
@@ -405,8 +408,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_CUDA(cudaStreamSynchronize(s));
     }
     if (!wide) {
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
         TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
         TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     }
@@ -630,12 +633,12 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             tg::tg_order_kernel<<<1, 1024, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
             a.perm = ch->d_perm;
         }
-        const bool small = ctx->R <= 128 * 3;
+        const bool small = ctx->R <= tg::ST * TG_SMALL_CHUNKS;
         if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
-            if (small) tg::tg_sampler_kernel<3, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
             else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
         } else {
-            if (small) tg::tg_sampler_kernel<3, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
             else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
         }
         TG_CUDA(cudaGetLastError());

@@ -24,8 +24,13 @@
 #define TG_OWNER_NONE 0x7Fu  // u8 owner code: no nucleus closer than sqrt(1e9) (v_nearest returns 0.0, MCsub.jl:249-250)
 #define TG_OWNER_TAG 0x80u   // u8 owner bit 7: pending "switches to the proposal's implicit new owner"
 #define TG_MAX_K_U8 126      // largest nCells representable with u8 owners (indices 0..125, +1 for a birth)
-#define TG_PHI_LANES 128     // virtual lanes of the canonical phi reduction
+#ifndef TG_PHI_WARPS
+#define TG_PHI_WARPS 4       // warps of the canonical phi reduction == warps per chain of the resident sampler
+#endif
+#define TG_PHI_LANES (32 * TG_PHI_WARPS)  // lanes of the canonical phi reduction
 #define TG_PT_TILE 512       // points are padded to a multiple of this (128 threads x 4 points)
+#define TG_PT_SLACK 2048     // extra elements behind the fl32 coordinate arrays / the owner-distance cache: the resident sampler prefetches
+                             // up to two block rounds ahead without a bounds check
 
 namespace tg {
 
@@ -65,6 +70,10 @@ __device__ __forceinline__ double seg_term(double dt, double za, double zb) {
     return __dmul_rn(dt, div1000_exact(__dmul_rn(0.5, __dadd_rn(za, zb))));
 }
 
+// the general segment term as a real function call (segments that cross a cell boundary are the minority; the resident
+// sampler's hot loop keeps only the call site): zlut maps the (clamped) owner byte to zeta under the proposed model
+static __device__ __noinline__ double seg_term_mixed(double dt, const double *zlut, int oa, int ob) { return seg_term(dt, zlut[oa], zlut[ob]); }
+
 __device__ __forceinline__ double misfit_term(double pts, double ts, double sig, double noise) {
     // MCsub.jl:171:  ((ptS - tS)^2 * 1.0) / sig^2   with sig = noise * allSig (noise == 1.0 -> reference)
     const double sg = __dmul_rn(noise, sig);
@@ -98,24 +107,52 @@ __device__ __forceinline__ double tstar_g8(int nseg, int trip, int sub, TermOf t
     acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
     return acc;
 }
-
-// Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES (=128) threads (4 warps): thread (warp w, lane l)
-// adds the terms of the (length-sorted) rays r = 128 c + 4 l + w, c = 0, 1, ... in ascending order (so every warp gets the
-// same mix of ray lengths -- the resident sampler integrates t* of ray r on warp r & 3 and keeps it in that thread's
-// registers), then xor butterfly inside the warp, then the 4 warp sums left to right.
-__device__ __forceinline__ int phi_ray(int c, int t128) { return (c << 7) | ((t128 & 31) << 2) | (t128 >> 5); }
-// term(r) must be callable by any thread.  scratch: 4 doubles of shared memory.  Result valid in all threads.
-template <typename TermOf>
-__device__ __forceinline__ double phi_canonical_128(int R, int t128, double *scratch, TermOf term) {
+// The same sum with the loads of 8 passes in flight at once: load(j) fetches what term(j, loaded) needs from global memory.
+template <typename LoadOf, typename TermOf>
+__device__ __forceinline__ double tstar_g8_batched(int nseg, int trip, int sub, LoadOf load, TermOf term) {
     double acc = 0.0;
-    for (int c = 0; (c << 7) < R; c++) {
-        const int r = phi_ray(c, t128);
+    for (int k0 = 0; k0 < trip; k0 += 8) {
+        double d[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = 8 * (k0 + u) + sub;
+            d[u] = (j < nseg) ? load(j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = 8 * (k0 + u) + sub;
+            if (j < nseg) acc = __dadd_rn(acc, term(j, d[u]));
+        }
+    }
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+    return acc;
+}
+
+// Canonical phi over R per-ray terms by a group of exactly TG_PHI_LANES threads (TG_PHI_WARPS warps): thread (warp w, lane l)
+// adds the terms of the (length-sorted) rays r = LANES c + WARPS l + w, c = 0, 1, ... in ascending order (so every warp gets
+// the same mix of ray lengths -- the resident sampler integrates t* of ray r on warp r % WARPS and keeps it in that thread's
+// registers), then xor butterfly inside the warp, then the warp sums left to right.
+__device__ __forceinline__ int phi_ray(int c, int t) { return c * TG_PHI_LANES + (t & 31) * TG_PHI_WARPS + (t >> 5); }
+__device__ __forceinline__ double phi_warp_sums(const double *scratch) {
+    double tot = scratch[0];
+#pragma unroll
+    for (int w = 1; w < TG_PHI_WARPS; w++) tot = __dadd_rn(tot, scratch[w]);
+    return tot;
+}
+// term(r) must be callable by any thread.  scratch: TG_PHI_WARPS doubles of shared memory.  Result valid in all threads.
+template <typename TermOf>
+__device__ __forceinline__ double phi_canonical(int R, int t, double *scratch, TermOf term) {
+    double acc = 0.0;
+    for (int c = 0; c * TG_PHI_LANES < R; c++) {
+        const int r = phi_ray(c, t);
         if (r < R) acc = __dadd_rn(acc, term(r));
     }
     acc = warp_sum_canonical(acc);
-    if ((t128 & 31) == 0) scratch[t128 >> 5] = acc;
+    if ((t & 31) == 0) scratch[t >> 5] = acc;
     __syncthreads();
-    const double tot = __dadd_rn(__dadd_rn(__dadd_rn(scratch[0], scratch[1]), scratch[2]), scratch[3]);
+    const double tot = phi_warp_sums(scratch);
     __syncthreads();
     return tot;
 }

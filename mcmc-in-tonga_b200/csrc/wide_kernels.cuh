@@ -134,24 +134,24 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 const double *trm = a.term_c + (size_t)chain * a.Rp;
                 double acc = 0.0;
                 int c = 0;
-                for (; ((c + 7) << 7) + TG_PHI_LANES <= R; c += 8) {  // 8 loads in flight, then the ordered adds (canonical phi order, phi_ray)
+                for (; (c + 8) * TG_PHI_LANES <= R; c += 8) {  // 8 loads in flight, then the ordered adds (canonical phi order, phi_ray)
                     double v[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) v[u] = trm[phi_ray(c + u, tid)];
 #pragma unroll
                     for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
                 }
-                for (; (c << 7) < R; c++) {
+                for (; c * TG_PHI_LANES < R; c++) {
                     const int r = phi_ray(c, tid);
                     if (r < R) acc = __dadd_rn(acc, trm[r]);
                 }
                 acc = warp_sum_canonical(acc);
                 if ((tid & 31) == 0) scratch[tid >> 5] = acc;
                 __syncthreads();
-                phin = __dadd_rn(__dadd_rn(__dadd_rn(scratch[0], scratch[1]), scratch[2]), scratch[3]);
+                phin = phi_warp_sums(scratch);
                 __syncthreads();
             } else {
-                phin = phi_canonical_128(R, tid, scratch, [&](int r) {
+                phin = phi_canonical(R, tid, scratch, [&](int r) {
                     const double t = (act == 5) ? ts[r] : (a.streamed ? tsc[r] : tc[a.ray_orig[r]]);
                     return misfit_term(t, a.tS[r], a.sig[r], nz);
                 });

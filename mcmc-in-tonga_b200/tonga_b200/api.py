@@ -363,14 +363,26 @@ _CTX_CACHE: dict = {}
 _UTIL_CTX: list = []
 
 
+_CTX_CACHE_MAX = 8
+
+
 def context_for(dataStruct: DataStruct, TD_parameters: parameters, device: int = 0, n_actions: int = 4) -> Context:
-    """One Context per (dataStruct, parameters) pair, like the Julia shim's cache keyed on objectid(dataStruct)."""
-    key = (id(dataStruct), id(TD_parameters), device, n_actions)
-    ent = _CTX_CACHE.get(key)
+    """One Context per (dataStruct, resolved parameter VALUES) pair, like the Julia shim's cache keyed on objectid(dataStruct).
+
+    `parameters` is mutable: the key holds the bytes of the device-side tonga_params the Context would be built with, so a
+    mutated (or recycled-id) parameters object gets a fresh Context instead of silently reusing stale values.  Entries whose
+    dataStruct died are closed and dropped; at most _CTX_CACHE_MAX contexts stay alive (least recently used goes first)."""
+    for k in [k for k, (ref, _) in _CTX_CACHE.items() if ref() is None]:
+        _CTX_CACHE.pop(k)[1].close()
+    key = (id(dataStruct), bytes(make_params(TD_parameters, dataStruct, n_actions)), device)
+    ent = _CTX_CACHE.pop(key, None)
     if ent is None or ent[0]() is not dataStruct:
-        ctx = Context(dataStruct, TD_parameters, device, n_actions)
-        _CTX_CACHE[key] = (weakref.ref(dataStruct), ctx)
-        return ctx
+        if ent is not None:
+            ent[1].close()
+        ent = (weakref.ref(dataStruct), Context(dataStruct, TD_parameters, device, n_actions))
+    _CTX_CACHE[key] = ent  # re-inserted at the end: dict order = recency
+    while len(_CTX_CACHE) > _CTX_CACHE_MAX:
+        _CTX_CACHE.pop(next(iter(_CTX_CACHE)))[1].close()
     return ent[1]
 
 

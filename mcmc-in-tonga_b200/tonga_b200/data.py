@@ -2,7 +2,7 @@
 
   ray_lengths()      <- load_data_Tonga.jl:66-69  (rayl = |dp| per segment, rayu = mean endpoint slowness)
   domain_from_stations() <- load_data_Tonga.jl:41-49 (box = station extent +- buffer, node spacing)
-  load_tonga381()    -> DataStruct for the shipped 381-ray set (tests/golden/tonga381.npz, see make_fixtures.py)
+  load_tonga381()    -> DataStruct for the shipped 381-ray set (tonga_b200/datasets/tonga381.npz, made by tests/golden/make_fixtures.py)
   synthetic_rays()   -> BASELINE.json config 3 style synthetic ray sets
 
 Documented substitutions for the shipped data: the shipped raypaths file has no slowness `u`,
@@ -19,7 +19,7 @@ import numpy as np
 
 from .structs import DataStruct, StepRangeLen, parameters
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests", "golden")
+_DATASETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "datasets")  # input data of the package (not test fixtures)
 
 
 def ak135_slowness(z: np.ndarray, table: np.ndarray) -> np.ndarray:
@@ -89,7 +89,7 @@ def make_datastruct(x, y, z, U, tS, sig, p: parameters, box=None) -> DataStruct:
 def load_tonga381(path: str | None = None, p: parameters | None = None) -> DataStruct:
     """The shipped 381-ray Tonga set (BASELINE.json configs 1, 2, 4, 5)."""
     p = p or parameters()
-    f = np.load(path or os.path.join(_GOLDEN, "tonga381.npz"))
+    f = np.load(path or os.path.join(_DATASETS, "tonga381.npz"))
     x, y, z = pad_rays(f["npts"], f["px"], f["py"], f["pz"])
     U = ak135_slowness(z, f["ak135"])
     return make_datastruct(x, y, z, U, f["tStar"], f["error"], p)

@@ -1,14 +1,15 @@
-"""Regenerate the data fixtures under tests/golden/ from the reference's shipped data files.
+"""Regenerate the data files derived from the reference's shipped data: the package's input data set and the test fixture.
 
 Run in the build container (needs /root/reference; the GPU box does not have it):
 
     python tests/golden/make_fixtures.py
 
 Outputs
-  tonga381.npz   the 381-ray Tonga geometry + observations (Data/381raypaths.jld, Data/381traces.jld)
+  mcmc-in-tonga_b200/tonga_b200/datasets/tonga381.npz   (package input data, loaded by tonga_b200.data.load_tonga381)
+                 the 381-ray Tonga geometry + observations (Data/381raypaths.jld, Data/381traces.jld)
                  and the ak135 velocity table (Data/ak135f.txt) used to synthesise the slowness the
                  shipped raypaths file lacks.
-  model_jld.npz  the 100 stored models of the reference's only shipped *output*, model.jld (2 chains x 50),
+  tests/golden/model_jld.npz  the 100 stored models of the reference's only shipped *output*, model.jld (2 chains x 50),
                  used for invariant tests only: it belongs to an unshipped 487-ray data set.
 
 These are DATA (inputs/outputs of the reference), not reference source.
@@ -21,6 +22,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+DATASETS = os.path.join(HERE, "..", "..", "mcmc-in-tonga_b200", "tonga_b200", "datasets")
 sys.path.insert(0, os.path.join(HERE, "..", "..", "tools"))
 from jld_min import JLDFile  # noqa: E402
 
@@ -59,7 +61,7 @@ def tonga381():
     )
     assert abs(out["tStar"].sum() - 181.152908) < 1e-6
     assert abs(out["error"].sum() - 100.524106) < 1e-6
-    np.savez_compressed(os.path.join(HERE, "tonga381.npz"), **out)
+    np.savez_compressed(os.path.join(DATASETS, "tonga381.npz"), **out)
     print("tonga381.npz: P =", int(npts.sum()), "rays =", len(npts))
 
 

@@ -29,7 +29,7 @@ if os.environ.get("AB_PROFILE"):
         ch.run(1000); pm.append(ch.last_kernel_ms())
     cyc = ch.profile(False, read=True) / 3
     print("   instrumented build: %%.2f M/s" %% (1024 * 1000 / np.median(pm) / 1e3), ["%%.1f" %% m for m in pm])
-    print("   cycles/iter A,B,C,D+E,F4,G,F1,F2:", (cyc[:, :8].mean(0) / 1000).round(0))
+    print("   cycles/iter A,B2,C,D+E,F4,G,F1,F2,B1:", (cyc[:, :9].mean(0) / 1000).round(0), "sum", round(float(cyc[:, :9].mean(0).sum()) / 1000))
 '''
 root = os.path.dirname(HERE)
 for rep in range(int(os.environ.get('REPS', '2'))):
