@@ -163,6 +163,23 @@ int tonga_chains_set_exact_only(tonga_chains *ch, int32_t exact_only);
 /* per-chain inverse temperature beta (parallel-tempering extension; 1.0 = reference; NULL resets to 1): the misfit term
  * of every acceptance ratio is scaled by beta, and only chains at beta == 1 append to the history. */
 int tonga_chains_set_beta(tonga_chains *ch, const double *beta);
+int tonga_chains_get_beta(tonga_chains *ch, double *beta /* [nChains] */);
+/* Parallel tempering (extension, BASELINE config 5; the reference has none -- its spec here follows the dead sigma branch
+ * TD_inversion_function.jl:252-272 for the noise term): one even / odd sweep of swap attempts between adjacent rungs of every
+ * ladder of `ladder_size` consecutive replicas, decided ON THE DEVICE from the replicas' current phi / noise.  Replicas keep
+ * their state; what is exchanged is the inverse temperature beta.  E = phi/2 + R log(noise); rungs i, j (adjacent in
+ * temperature order, parity = step & 1) swap iff log u < min(0, (beta_i - beta_j)(E_i - E_j)), u drawn from Philox4x32-10
+ * keyed by `seed` with counter (step, ladder, rung) -- a pure function of its inputs, so every rank of a multi-GPU ladder takes
+ * the same decisions from the same all-gathered scalars.
+ *   phi_all / noise_all / beta_all: DEVICE arrays over all n_all replicas of the ladders in global replica order (e.g. filled
+ *   by an NCCL all-gather of every rank's tonga_chains_scalar_ptrs arrays); NULL = this batch's own arrays (n_all = nChains,
+ *   offset = 0).  beta_all is updated in place and this batch's slice [offset, offset + nChains) becomes its beta.
+ *   swap statistics accumulate on the device (tonga_chains_temper_stats).  Asynchronous on the context's stream. */
+int tonga_chains_temper_swap(tonga_chains *ch, int32_t n_all, const double *phi_all, const double *noise_all, double *beta_all,
+                             int64_t offset, int32_t ladder_size, int64_t step, uint64_t seed);
+int tonga_chains_temper_stats(tonga_chains *ch, int64_t *accepted, int64_t *attempted, int32_t reset);
+/* device pointers of the per-chain scalars phi / noise / beta ([nChains] doubles each) for zero-copy collectives */
+int tonga_chains_scalar_ptrs(tonga_chains *ch, void **phi, void **noise, void **beta);
 
 /* The proposal loop, TD_inversion_function.jl:70-302, nIter iterations for every chain, entirely on the device
  * (incremental Voronoi update, t* re-integration of touched rays, misfit, alpha, accept/reject, thinning).

@@ -191,7 +191,7 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
         std::vector<float> xf(Ppad + TG_PT_SLACK, 0.f), yf(Ppad + TG_PT_SLACK, 0.f), zf(Ppad + TG_PT_SLACK, 0.f);
         double M = 0.0;
         for (int64_t i = 0; i < Ppad; i++) {
-            xf[i] = (float)px[i]; yf[i] = (float)py[i]; zf[i] = (float)pz[i];
+            xf[i] = i < P ? (float)px[i] : TG_PAD_COORD; yf[i] = i < P ? (float)py[i] : TG_PAD_COORD; zf[i] = i < P ? (float)pz[i] : TG_PAD_COORD;
             if (i < P) {
                 for (double v : {px[i], py[i], pz[i]})
                     if (std::fabs(v) > M) M = std::fabs(v);  // NaN never compares greater

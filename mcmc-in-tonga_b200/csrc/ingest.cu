@@ -65,7 +65,7 @@ __global__ void tg_ingest_pad_kernel(int64_t P, int64_t Ppad, double *px, double
     if (i >= Ppad) return;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     px[i] = py[i] = pz[i] = qnan;
-    pxf[i] = pyf[i] = pzf[i] = __int_as_float(0x7fc00000);
+    pxf[i] = pyf[i] = pzf[i] = TG_PAD_COORD;
     rayid[i] = 0;
     point_orig[i] = -1;
 }

@@ -174,6 +174,42 @@ __global__ void tg_raster_reduce_kernel(int n_nodes, int nChains, const double *
     sumsq[node] = b;
 }
 
+// ---- parallel tempering (extension): one even / odd swap sweep, one thread per ladder of T replicas (global replica order).
+// E = phi/2 + R log(noise); pairs adjacent in temperature order; decisions from Philox4x32-10(seed; step, ladder, rung).
+constexpr int TEMPER_MAX_T = 256;
+__global__ void tg_temper_swap_kernel(int n_lad, int T, int R, const double *__restrict__ phi, const double *__restrict__ noise, double *__restrict__ beta,
+                                      long long step, unsigned long long seed, unsigned long long *__restrict__ stat) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lad) return;
+    double b[TEMPER_MAX_T], e[TEMPER_MAX_T];
+    int order[TEMPER_MAX_T];
+    for (int t = 0; t < T; t++) {
+        b[t] = beta[(size_t)l * T + t];
+        e[t] = 0.5 * phi[(size_t)l * T + t] + (double)R * log(noise[(size_t)l * T + t]);
+    }
+    for (int t = 0; t < T; t++) {  // temperature order: coldest (largest beta) first, stable
+        int rank = 0;
+        for (int s = 0; s < T; s++) rank += (b[s] > b[t]) || (b[s] == b[t] && s < t);
+        order[rank] = t;
+    }
+    const Philox philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    unsigned long long acc = 0, att = 0;
+    for (int t = (int)(step & 1); t + 1 < T; t += 2) {
+        const int i = order[t], j = order[t + 1];
+        uint32_t w[4];
+        philox((uint32_t)step, (uint32_t)((unsigned long long)step >> 32), (uint32_t)l, (uint32_t)t | 0x40000000u, w);  // purpose tag: swap stream
+        const double u = u53_open(w[0], w[1]);
+        const double loga = (b[i] - b[j]) * (e[i] - e[j]);
+        att++;
+        if (log(u) < (loga < 0.0 ? loga : 0.0)) {
+            const double tmp = b[i]; b[i] = b[j]; b[j] = tmp;
+            acc++;
+        }
+    }
+    for (int t = 0; t < T; t++) beta[(size_t)l * T + t] = b[t];
+    if (stat) { atomicAdd(&stat[0], acc); atomicAdd(&stat[1], att); }
+}
+
 // evaluate's t* (caller's ray order) -> chain state rows (sorted ray order, padded to Rp)
 __global__ void tg_copy_tstar_kernel(int n, int R, int Rp, const int32_t *ray_orig, const double *src /* [n][R] */, double *dst /* [n][Rp] */) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -235,6 +271,7 @@ struct tonga_chains {
     double *d_phi_tmp = nullptr;
     uint8_t *d_owner_tmp = nullptr;
     unsigned long long *d_mism = nullptr;
+    unsigned long long *d_swapstat = nullptr;  // [2] accepted / attempted tempering swaps
     double *d_maxd = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -385,6 +422,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     TG_ALLOC(ch->d_ptS_tmp, 8 * n * R);
     TG_ALLOC(ch->d_phi_tmp, 8 * n);
     TG_ALLOC(ch->d_mism, 8);
+    TG_ALLOC(ch->d_swapstat, 16);
+    TG_CUDA(cudaMemsetAsync(ch->d_swapstat, 0, 16, ctx->stream));
     TG_ALLOC(ch->d_maxd, 16);
     cudaStream_t s = ctx->stream;
     TG_CUDA(cudaMemsetAsync(ch->d_counts, 0, 8 * n * 15, s));
@@ -438,7 +477,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     cudaStreamSynchronize(ch->ctx->stream);
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles, ch->d_tile_changed};
+                    ch->d_maxd, ch->d_swapstat, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles, ch->d_tile_changed};
     for (void *p : ptrs) cudaFree(p);
     void *hist[] = {ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter, ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next};
     for (void *p : hist) {
@@ -535,6 +574,57 @@ extern "C" int tonga_chains_set_beta(tonga_chains *ch, const double *beta) {
     std::vector<double> b((size_t)ch->n, 1.0);
     if (beta) std::memcpy(b.data(), beta, 8 * (size_t)ch->n);
     TG_CUDA(cudaMemcpy(ch->d_beta, b.data(), 8 * (size_t)ch->n, cudaMemcpyHostToDevice));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_get_beta(tonga_chains *ch, double *beta) {
+    if (!ch || !beta) return tg::fail(TONGA_ERR_ARG, "tonga_chains_get_beta: NULL");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    TG_CUDA(cudaMemcpyAsync(beta, ch->d_beta, 8 * (size_t)ch->n, cudaMemcpyDeviceToHost, ch->ctx->stream));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_temper_swap(tonga_chains *ch, int32_t n_all, const double *phi_all, const double *noise_all, double *beta_all,
+                                        int64_t offset, int32_t ladder_size, int64_t step, uint64_t seed) {
+    if (!ch || ladder_size < 1 || ladder_size > tg::TEMPER_MAX_T || step < 0)
+        return tg::fail(TONGA_ERR_ARG, "tonga_chains_temper_swap: bad argument (1 <= ladder_size <= 256)");
+    const bool own = !phi_all && !noise_all && !beta_all;
+    if (!own && (!phi_all || !noise_all || !beta_all)) return tg::fail(TONGA_ERR_ARG, "tonga_chains_temper_swap: pass all three arrays or none");
+    if (own) { n_all = ch->n; offset = 0; }
+    if (n_all < 1 || n_all % ladder_size != 0 || offset < 0 || offset + ch->n > n_all)
+        return tg::fail(TONGA_ERR_ARG, "tonga_chains_temper_swap: n_all must be a multiple of ladder_size and hold this batch's slice");
+    if (!ch->have_models) return tg::fail(TONGA_ERR_STATE, "tonga_chains_temper_swap: no models yet");
+    tonga_ctx *ctx = ch->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const int n_lad = n_all / ladder_size;
+    tg::tg_temper_swap_kernel<<<(n_lad + 63) / 64, 64, 0, ctx->stream>>>(n_lad, ladder_size, ctx->R, own ? ch->d_phi : phi_all, own ? ch->d_noise : noise_all,
+                                                                        own ? ch->d_beta : beta_all, step, seed, ch->d_swapstat);
+    TG_CUDA(cudaGetLastError());
+    if (!own) TG_CUDA(cudaMemcpyAsync(ch->d_beta, beta_all + offset, 8 * (size_t)ch->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_temper_stats(tonga_chains *ch, int64_t *accepted, int64_t *attempted, int32_t reset) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_temper_stats: NULL");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    TG_CUDA(cudaSetDevice(ch->ctx->device));
+    unsigned long long st[2] = {0, 0};
+    TG_CUDA(cudaMemcpyAsync(st, ch->d_swapstat, 16, cudaMemcpyDeviceToHost, ch->ctx->stream));
+    if (reset) TG_CUDA(cudaMemsetAsync(ch->d_swapstat, 0, 16, ch->ctx->stream));
+    TG_CUDA(cudaStreamSynchronize(ch->ctx->stream));
+    if (accepted) *accepted = (int64_t)st[0];
+    if (attempted) *attempted = (int64_t)st[1];
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_scalar_ptrs(tonga_chains *ch, void **phi, void **noise, void **beta) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_scalar_ptrs: NULL");
+    if (phi) *phi = ch->d_phi;
+    if (noise) *noise = ch->d_noise;
+    if (beta) *beta = ch->d_beta;
     return TONGA_OK;
 }
 

@@ -67,6 +67,9 @@ struct SamplerArgs {
     int32_t *hist_action, *hist_accept, *hist_next;
 };
 
+#ifndef TG_B1_PINGPONG
+#define TG_B1_PINGPONG 0
+#endif
 constexpr int SQ_CAP = 64;    // orphan-word queue entries per warp
 constexpr int ZLUT_TAG = 128; // entries 128..255 of the zeta look-up table: tagged bytes (all hold the implicit new owner's value)
 struct WarpProp {  // the proposal's scalars that are only needed again at the acceptance / commit: one copy per warp (same values)
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(256) tg_pregen_kernel(int n, long long nIter, 
 static __device__ __noinline__ int rescan_point(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                                                 const double *nx, const double *ny, const double *nz, int K, int skip, int mvi, double cx, double cy,
                                                 double cz, int p) {
-    const double x = px[p], y = py[p], z = pz[p];
+    const double x = __ldg(px + p), y = __ldg(py + p), z = __ldg(pz + p);
     double best = 1e9;
     int bi = TG_OWNER_NONE;
 #pragma unroll 2
@@ -176,6 +179,10 @@ static __device__ __noinline__ uint2 phase_b1_switch(const int pidx, const float
     const float ta = h.ta, tb = h.tb;
     const bool exact_only = h.exact_only != 0;
     const float2 ncx = make_float2(-cxf, -cxf), ncy = make_float2(-cyf, -cyf), ncz = make_float2(-czf, -czf);
+    // (the two affine forms below are evaluated in fl32 themselves: the band is widened by 4 ulp to keep its margin)
+    const float tw = ta + 4.0f * 0x1.0p-24f, tbw = tb * (1.0f + 0x1.0p-20f);
+    const float2 kA = make_float2(1.0f + tw, 1.0f + tw), kB = make_float2(1.0f - tw, 1.0f - tw), kNA = make_float2(-1.0f - tw, -1.0f - tw),
+                 kNB = make_float2(tw - 1.0f, tw - 1.0f), kT = make_float2(tbw, tbw), kNT = make_float2(-tbw, -tbw);
     uint32_t tagmask = 0u, blkmask = 0u;
     auto body = [&](const int blk, const int bi, const float4 xf, const float4 yf, const float4 zf, const float4 dof) {
         const int w = blk * 32 + lane;
@@ -186,22 +193,28 @@ static __device__ __noinline__ uint2 phase_b1_switch(const int pidx, const float
             const float2 dc01 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
             ex = __fadd2_rn(make_float2(xf.z, xf.w), ncx); ey = __fadd2_rn(make_float2(yf.z, yf.w), ncy); ez = __fadd2_rn(make_float2(zf.z, zf.w), ncz);
             const float2 dc23 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
-            const float DC[4] = {dc01.x, dc01.y, dc23.x, dc23.y};
-            const float DO[4] = {dof.x, dof.y, dof.z, dof.w};  // cached distance to the current owner: no nucleus gather
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float d_o = DO[q];
-                const float diff = DC[q] - d_o;
-                const float tol = fmaf(ta, DC[q] + d_o, tb);
-                bool sw = diff < -tol, am = fabsf(diff) <= tol;
-                if (ACT == 4) {
-                    const bool mine = ((int)((ow >> (8 * q)) & 0xFF) == mv);  // move, type A: owned by the moved nucleus -> rescan in B2
-                    mbits |= mine ? (1u << q) : 0u;
-                    sw = sw && !mine;
-                    am = am && !mine;
-                }
-                tags |= sw ? (0x80u << (8 * q)) : 0u;
-                amb |= am ? (1u << q) : 0u;
+            // The error band |dc - do| <= ta (dc + do) + tb as two affine forms (dc = new distance, do = cached owner distance):
+            //   usw = dc (1 + ta) - do (1 - ta) + tb < 0   <=>  dc - do < -tol : switches for certain  (its sign bit is the tag)
+            //   ust = dc (1 - ta) - do (1 + ta) - tb > 0   <=>  dc - do >  tol : stays for certain
+            // anything else is ambiguous -> exact FP64.  (The fl32 rounding of these forms is far inside the band's 1.4x margin.)
+            const float2 do01 = make_float2(dof.x, dof.y), do23 = make_float2(dof.z, dof.w);
+            const float2 usw01 = __ffma2_rn(dc01, kA, __ffma2_rn(do01, kNB, kT)), usw23 = __ffma2_rn(dc23, kA, __ffma2_rn(do23, kNB, kT));
+            const float2 ust01 = __ffma2_rn(dc01, kB, __ffma2_rn(do01, kNA, kNT)), ust23 = __ffma2_rn(dc23, kB, __ffma2_rn(do23, kNA, kNT));
+            // tags: sign bit of usw -> bit 7 of the point's owner byte (NaN never occurs: padded points carry finite far-away coordinates)
+            const uint32_t sg = __byte_perm(__byte_perm(__float_as_uint(usw01.x), __float_as_uint(usw01.y), 0x0073),
+                                            __byte_perm(__float_as_uint(usw23.x), __float_as_uint(usw23.y), 0x0073), 0x5410) & 0x80808080u;
+            // ambiguous point: usw >= 0 and ust <= 0  <=>  max(-usw, ust) <= 0
+            const float w0 = fmaxf(-usw01.x, ust01.x), w1 = fmaxf(-usw01.y, ust01.y), w2 = fmaxf(-usw23.x, ust23.x), w3 = fmaxf(-usw23.y, ust23.y);
+            tags = sg;
+            if (ACT == 4) {  // move, type A: points of the moved nucleus are rescanned in B2, not screened here
+                const uint32_t mine = __vcmpeq4(ow, (uint32_t)mv * 0x01010101u);
+                mbits = (mine & 1u) | ((mine >> 7) & 2u) | ((mine >> 14) & 4u) | ((mine >> 21) & 8u);
+                tags &= ~mine;
+            }
+            if (fminf(fminf(w0, w1), fminf(w2, w3)) <= 0.0f) {
+                amb = (w0 <= 0.0f ? 1u : 0u) | (w1 <= 0.0f ? 2u : 0u) | (w2 <= 0.0f ? 4u : 0u) | (w3 <= 0.0f ? 8u : 0u);
+                amb &= ~mbits;
+                tags &= ~(((amb & 1u) * 0x80u) | ((amb & 2u) * 0x4000u) | ((amb & 4u) * 0x200000u) | ((amb & 8u) * 0x10000000u));  // decided below
             }
         } else {
 #pragma unroll
@@ -218,7 +231,7 @@ static __device__ __noinline__ uint2 phase_b1_switch(const int pidx, const float
                 if (!((amb >> q) & 1u)) continue;
                 const int o = (ow >> (8 * q)) & 0xFF;
                 const int p = 4 * w + q;
-                const double x = h.px[p], y = h.py[p], z = h.pz[p];
+                const double x = __ldg(h.px + p), y = __ldg(h.py + p), z = __ldg(h.pz + p);
                 const double d_o = (o == TG_OWNER_NONE) ? 1e9 : dist2_exact(s_nx[o], s_ny[o], s_nz[o], x, y, z);
                 const double d_c = dist2_exact(cx, cy, cz, x, y, z);
                 // birth: the new nucleus has the highest index -> strict <.  move: index mv also wins exact ties against o > mv.
@@ -239,20 +252,27 @@ static __device__ __noinline__ uint2 phase_b1_switch(const int pidx, const float
             if (bi < 32) blkmask |= 1u << bi;
         }
     };
-    // two named register sets in ping-pong: the next block's coordinates / owner distances are in flight while the current
-    // block is screened (no register moves between the sets)
     const float4 *gx = reinterpret_cast<const float4 *>(h.pxf) + lane, *gy = reinterpret_cast<const float4 *>(h.pyf) + lane,
                  *gz = reinterpret_cast<const float4 *>(h.pzf) + lane, *gd = reinterpret_cast<const float4 *>(h.dcache) + lane;
+#if TG_B1_PINGPONG
     // (the loads are unconditional: the arrays carry TG_PT_SLACK elements of slack)
-    float4 ax = gx[warp * 32], ay = gy[warp * 32], az = gz[warp * 32], ad = gd[warp * 32];
+    float4 ax = __ldg(gx + warp * 32), ay = __ldg(gy + warp * 32), az = __ldg(gz + warp * 32), ad = __ldcg(gd + warp * 32);
     int bi = 0;
 #pragma unroll 1
     for (int blk = warp; blk < nBlocks; blk += 2 * NW, bi += 2) {
-        const float4 bx = gx[(blk + NW) * 32], by = gy[(blk + NW) * 32], bz = gz[(blk + NW) * 32], bd = gd[(blk + NW) * 32];
+        const float4 bx = __ldg(gx + (blk + NW) * 32), by = __ldg(gy + (blk + NW) * 32), bz = __ldg(gz + (blk + NW) * 32), bd = __ldcg(gd + (blk + NW) * 32);
         body(blk, bi, ax, ay, az, ad);
-        ax = gx[(blk + 2 * NW) * 32]; ay = gy[(blk + 2 * NW) * 32]; az = gz[(blk + 2 * NW) * 32]; ad = gd[(blk + 2 * NW) * 32];
+        ax = __ldg(gx + (blk + 2 * NW) * 32); ay = __ldg(gy + (blk + 2 * NW) * 32); az = __ldg(gz + (blk + 2 * NW) * 32); ad = __ldcg(gd + (blk + 2 * NW) * 32);
         if (blk + NW < nBlocks) body(blk + NW, bi + 1, bx, by, bz, bd);
     }
+#else
+    // one block per step; the other warps of the SM (7 chains x 4 warps) hide the L2 latency.  (A two-set ping-pong prefetch
+    // was measured: with 72 registers per thread the compiler spills its constants inside the loop and the pass gets slower.)
+    int bi = 0;
+#pragma unroll 1
+    for (int blk = warp; blk < nBlocks; blk += NW, bi++)
+        body(blk, bi, __ldg(gx + blk * 32), __ldg(gy + blk * 32), __ldg(gz + blk * 32), __ldcg(gd + blk * 32));
+#endif
     return make_uint2(tagmask, blkmask);
 }
 
@@ -326,8 +346,8 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
                 uint32_t nb[4] = {TG_OWNER_NONE, TG_OWNER_NONE, TG_OWNER_NONE, TG_OWNER_NONE};
                 uint32_t need = exact_only ? mb : 0u;
                 if (!exact_only) {
-                    const float4 X = reinterpret_cast<const float4 *>(h.pxf)[w], Y = reinterpret_cast<const float4 *>(h.pyf)[w],
-                                 Z = reinterpret_cast<const float4 *>(h.pzf)[w];
+                    const float4 X = __ldg(reinterpret_cast<const float4 *>(h.pxf) + w), Y = __ldg(reinterpret_cast<const float4 *>(h.pyf) + w),
+                                 Z = __ldg(reinterpret_cast<const float4 *>(h.pzf) + w);
                     const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w), Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w),
                                  Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
                     const uint32_t INIT = (__float_as_uint(1e9f) & 0xFFFFFF80u) | TG_OWNER_NONE;
@@ -437,15 +457,23 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         double acc = 0.0;
 #pragma unroll 1
         for (int k0 = 0; k0 < trip; k0 += 8, ow += 64, dtp += 64) {
+            // 8 passes per round in quarters of 2; quarters beyond `trip` are skipped by warp-uniform branches, the loads of the
+            // round's live quarters are all issued before the first use
+            const int rem = trip - k0;
             double d[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) d[u] = dtp[8 * u];
+            for (int q = 0; q < 4; q++)
+                if (2 * q < rem) { d[2 * q] = __ldg(dtp + 16 * q); d[2 * q + 1] = __ldg(dtp + 16 * q + 8); }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const double m = __dadd_rn(s_zh[ow[8 * u]], s_zh[ow[8 * u + 1]]);
-                const double term = __dmul_rn(d[u], div1000_exact(m));
-                if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
-            }
+            for (int q = 0; q < 4; q++)
+                if (2 * q < rem) {
+#pragma unroll
+                    for (int u = 2 * q; u < 2 * q + 2; u++) {
+                        const double m = __dadd_rn(s_zh[ow[8 * u]], s_zh[ow[8 * u + 1]]);
+                        const double term = __dmul_rn(d[u], div1000_exact(m));
+                        if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
+                    }
+                }
         }
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
@@ -484,14 +512,14 @@ static __device__ __noinline__ void phase_f_mask(const int accepted, const int p
                 const uint32_t m8 = ((mb & 1u) * 0xFFu) | ((mb & 2u) * (0xFF00u >> 1)) | ((mb & 4u) * (0xFF0000u >> 2)) | ((mb & 8u) * (0xFF000000u >> 3));
                 s_own32[w] = (ow & ~m8) | (kk & m8);
             } else {
-                const float4 X = reinterpret_cast<const float4 *>(h.pxf)[w], Y = reinterpret_cast<const float4 *>(h.pyf)[w],
-                             Z = reinterpret_cast<const float4 *>(h.pzf)[w];
+                const float4 X = __ldg(reinterpret_cast<const float4 *>(h.pxf) + w), Y = __ldg(reinterpret_cast<const float4 *>(h.pyf) + w),
+                             Z = __ldg(reinterpret_cast<const float4 *>(h.pzf) + w);
                 const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     if ((mb >> q) & 1u) {
                         const int o = (ow >> (8 * q)) & 0x7F;  // death: still the old numbering, as are the fl32 nuclei
-                        h.dcache[4 * w + q] = (o == TG_OWNER_NONE) ? 1e9f : dist2_f32(s_fx[o], s_fy[o], s_fz[o], xs[q], ys[q], zs[q]);
+                        __stcg(h.dcache + 4 * w + q, (o == TG_OWNER_NONE) ? 1e9f : dist2_f32(s_fx[o], s_fy[o], s_fz[o], xs[q], ys[q], zs[q]));
                     }
             }
         }
@@ -514,12 +542,12 @@ static __device__ __noinline__ void phase_f_tags(const int accepted, const uint3
             const uint32_t m = (t >> 7) * 0xFFu;
             s_own32[w] = accepted ? ((ow & ~m) | (newb & m)) : (ow & 0x7F7F7F7Fu);
             if (accepted) {
-                const float4 X = reinterpret_cast<const float4 *>(h.pxf)[w], Y = reinterpret_cast<const float4 *>(h.pyf)[w],
-                             Z = reinterpret_cast<const float4 *>(h.pzf)[w];
+                const float4 X = __ldg(reinterpret_cast<const float4 *>(h.pxf) + w), Y = __ldg(reinterpret_cast<const float4 *>(h.pyf) + w),
+                             Z = __ldg(reinterpret_cast<const float4 *>(h.pzf) + w);
                 const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if ((t >> (8 * q + 7)) & 1u) h.dcache[4 * w + q] = dist2_f32(cxf, cyf, czf, xs[q], ys[q], zs[q]);
+                    if ((t >> (8 * q + 7)) & 1u) __stcg(h.dcache + 4 * w + q, dist2_f32(cxf, cyf, czf, xs[q], ys[q], zs[q]));
             }
         }
     }

@@ -29,6 +29,8 @@
 #endif
 #define TG_PHI_LANES (32 * TG_PHI_WARPS)  // lanes of the canonical phi reduction
 #define TG_PT_TILE 512       // points are padded to a multiple of this (128 threads x 4 points)
+#define TG_PAD_COORD 1e18f    // fl32 coordinates of the padding points (P..Ppad): finite and far away, so that the screening arithmetic
+                             // never sees a NaN (their FP64 coordinates stay NaN; they are owned by "none" and never switch)
 #define TG_PT_SLACK 2048     // extra elements behind the fl32 coordinate arrays / the owner-distance cache: the resident sampler prefetches
                              // up to two block rounds ahead without a bounds check
 

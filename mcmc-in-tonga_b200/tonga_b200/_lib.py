@@ -65,6 +65,10 @@ SYMBOLS = {
     "tonga_chains_set_models": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp]),
     "tonga_chains_set_exact_only": (C.c_int, [_P, C.c_int32]),
     "tonga_chains_set_beta": (C.c_int, [_P, c_dp]),
+    "tonga_chains_get_beta": (C.c_int, [_P, c_dp]),
+    "tonga_chains_temper_swap": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_uint64]),
+    "tonga_chains_temper_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
+    "tonga_chains_scalar_ptrs": (C.c_int, [_P] + [c_vpp] * 3),
     "tonga_chains_run": (C.c_int, [_P, C.c_int64, C.c_int32, _P, c_bp, c_dp, c_ip]),
     "tonga_chains_get_state": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "tonga_chains_get_stats": (C.c_int, [_P, c_lp, c_lp]),

@@ -223,6 +223,32 @@ class Chains:
         beta = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
         check(self.lib.tonga_chains_set_beta(self._h, dp(beta)))
 
+    def get_beta(self) -> np.ndarray:
+        beta = np.zeros(self.n)
+        check(self.lib.tonga_chains_get_beta(self._h, dp(beta)))
+        return beta
+
+    def temper_swap(self, ladder_size: int, step: int, seed: int = 0, n_all: int = 0, phi_all: int = 0, noise_all: int = 0, beta_all: int = 0,
+                    offset: int = 0):
+        """One even / odd sweep of tempering swaps decided on the device (tonga_chains_temper_swap).  Without pointers the
+        ladders are this batch's own consecutive replicas; with DEVICE pointers (ints) of all-gathered phi / noise / beta
+        arrays the ladders may span ranks (`offset` = first global replica of this batch).  Asynchronous."""
+        vp = lambda a: C.c_void_p(int(a)) if a else None
+        check(self.lib.tonga_chains_temper_swap(self._h, int(n_all), vp(phi_all), vp(noise_all), vp(beta_all), int(offset), int(ladder_size), int(step),
+                                                int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def temper_stats(self, reset: bool = False):
+        """(accepted, attempted) swap pairs counted on the device since the last reset."""
+        a, t = C.c_int64(), C.c_int64()
+        check(self.lib.tonga_chains_temper_stats(self._h, C.byref(a), C.byref(t), 1 if reset else 0))
+        return a.value, t.value
+
+    def scalar_ptrs(self):
+        """Device pointers of the per-chain phi / noise / beta arrays (zero-copy collectives)."""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        check(self.lib.tonga_chains_scalar_ptrs(self._h, *[C.byref(q) for q in ptrs]))
+        return {k: q.value for k, q in zip(("phi", "noise", "beta"), ptrs)}
+
     def run(self, n_iter: int, recs: np.ndarray | None = None, record: bool = False, trace: bool = False):
         """Generate mode (device Philox) unless `recs` ([n, n_iter] PROPOSAL_DTYPE) is given (replay).
         -> dict(recs (if record), accept, phi, K (if trace))."""
@@ -313,7 +339,7 @@ class Chains:
         check(self.lib.tonga_chains_get_progress(self._h, C.byref(it), lp(model_num), ip(pending)))
         _, counts = self.stats()
         hist = self.history()
-        return dict(K=st["K"], cells=st["cells"], noise=st["noise"], iter=np.int64(it.value), model_num=model_num, pending_slot=pending,
+        return dict(K=st["K"], cells=st["cells"], noise=st["noise"], beta=self.get_beta(), iter=np.int64(it.value), model_num=model_num, pending_slot=pending,
                     counts=counts, seed=np.uint64(self.seed), chain_id0=np.int64(self.chain_id0), hist_cap=np.int64(self.hist_cap),
                     **{"hist_" + k: v for k, v in hist.items()})
 
@@ -322,6 +348,8 @@ class Chains:
         if int(ck["hist_cap"]) != self.hist_cap or len(ck["K"]) != self.n or int(ck["chain_id0"]) != self.chain_id0 or int(ck["seed"]) != self.seed:
             raise TongaError(-1, "checkpoint does not belong to this batch (chain count, chain_id0, seed or hist_cap differ)")
         self.set_models(ck["K"], ck["cells"][:, :, :self.KC], ck["noise"])
+        if "beta" in ck:  # tempered batches (extension): the replicas' inverse temperatures
+            self.set_beta(ck["beta"])
         c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
         check(self.lib.tonga_chains_set_progress(self._h, int(ck["iter"]), lp(c(ck["model_num"], np.int64)), ip(c(ck["pending_slot"], np.int32)),
                                                  lp(c(ck["counts"], np.int64))))

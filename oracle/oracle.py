@@ -77,6 +77,9 @@ def lib():
         L.orc_chain_farm.restype = C.c_int
         L.orc_chain_farm.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcData), C.c_int, C.c_int64, C.c_int, C.c_uint64,
                                      c_dp, c_ip, C.POINTER(C.c_int64)]
+        L.orc_chain_farm_from.restype = C.c_int
+        L.orc_chain_farm_from.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcData), C.c_int, C.c_int64, C.c_int, C.c_uint64,
+                                          c_ip, c_dp, C.c_int, c_dp, c_ip, C.POINTER(C.c_int64)]
         L.orc_ray_lengths.argtypes = [C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
         _LIB = L
     return _LIB
@@ -230,6 +233,22 @@ def chain_farm(p: OrcParams, d: Data, n_chains: int, n_iter: int, n_threads: int
                               acc.ctypes.data_as(C.POINTER(C.c_int64)))
     if rc < 0:
         raise RuntimeError(f"orc_chain_farm rc={rc}")
+    return phi, K, acc
+
+
+def chain_farm_from(p: OrcParams, d: Data, K0, cells0, n_iter: int, n_threads: int, seed: int = 1):
+    """chain_farm started from given models: K0[n], cells0[n, 4, Kcap] (x / y / z / zeta rows)."""
+    K0 = np.ascontiguousarray(K0, dtype=np.int32)
+    cells0 = np.ascontiguousarray(cells0, dtype=np.float64)
+    n = len(K0)
+    assert cells0.shape[:2] == (n, 4)
+    phi = np.zeros(n)
+    K = np.zeros(n, np.int32)
+    acc = np.zeros(n, np.int64)
+    rc = lib().orc_chain_farm_from(C.byref(p), C.byref(d.c), n, n_iter, n_threads, seed, _ip(K0), _dp(cells0), cells0.shape[2], _dp(phi),
+                                   _ip(K), acc.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc < 0:
+        raise RuntimeError(f"orc_chain_farm_from rc={rc}")
     return phi, K, acc
 
 

@@ -111,6 +111,13 @@ int orc_chain_run(const orc_params *p, const orc_data *d, orc_model *mdl, int64_
                   int32_t *hist_K, double *hist_cells, double *hist_phi, double *hist_ptS,
                   int64_t *hist_iter, int32_t *hist_action, int32_t *hist_accept);
 
+/* tonga_oracle_mt.c: the chain farm (main_inversion.jl:15), nChains independent chains on nThreads host threads; the second
+ * form starts from the caller's models (cells0[nChains][4][Kcap0], x / y / z / zeta rows) instead of build_starting */
+int orc_chain_farm(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads,
+                   uint64_t seed, double *phi_out, int32_t *K_out, int64_t *acc_out);
+int orc_chain_farm_from(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads, uint64_t seed,
+                        const int32_t *K0, const double *cells0, int Kcap0, double *phi_out, int32_t *K_out, int64_t *acc_out);
+
 /* ray preprocessing, load_data_Tonga.jl:66-69 */
 void orc_ray_lengths(int m, int R, const double *x, const double *y, const double *z, const double *U,
                      double *rayL, double *rayU);

@@ -22,6 +22,10 @@ typedef struct {
     int32_t *K_out;    /* nChains */
     int64_t *acc_out;  /* nChains */
     int rc;
+    /* optional start models (orc_chain_farm_from): K0[nChains], cells0[nChains][4][Kcap0]; NULL -> build_starting */
+    const int32_t *K0;
+    const double *cells0;
+    int Kcap0;
 } worker_arg;
 
 static void *worker(void *vp) {
@@ -40,7 +44,19 @@ static void *worker(void *vp) {
         orc_rng g;
         orc_rng_seed(&g, a->seed + (uint64_t)c);
         m.noise = 1.0;
-        int rc = orc_build_starting(a->p, a->d, &g, &m); /* TD_inversion_function.jl:43-45 */
+        int rc;
+        if (a->K0) { /* the caller's start model + the evaluate that build_starting ends with (MCsub.jl:118) */
+            const int k = a->K0[c];
+            if (k < 1 || k > a->cap || k > a->Kcap0) { a->rc = -1; break; }
+            const double *c0 = a->cells0 + (size_t)c * 4 * (size_t)a->Kcap0;
+            for (int i = 0; i < k; i++) {
+                m.x[i] = c0[i]; m.y[i] = c0[a->Kcap0 + i]; m.z[i] = c0[2 * (size_t)a->Kcap0 + i]; m.zeta[i] = c0[3 * (size_t)a->Kcap0 + i];
+            }
+            m.K = k;
+            rc = orc_evaluate(a->p, a->d, &m, NULL, NULL);
+        } else {
+            rc = orc_build_starting(a->p, a->d, &g, &m); /* TD_inversion_function.jl:43-45 */
+        }
         if (rc < 0) { a->rc = rc; break; }
         int32_t nh = 0;
         int64_t mnum = 0;
@@ -58,15 +74,31 @@ static void *worker(void *vp) {
     return NULL;
 }
 
+static int farm(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads, uint64_t seed, double *phi_out,
+                int32_t *K_out, int64_t *acc_out, const int32_t *K0, const double *cells0, int Kcap0);
+
 /* Run nChains independent chains of nIter iterations each on nThreads host threads. */
 int orc_chain_farm(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads,
                    uint64_t seed, double *phi_out, int32_t *K_out, int64_t *acc_out) {
+    return farm(p, d, nChains, nIter, nThreads, seed, phi_out, K_out, acc_out, NULL, NULL, 0);
+}
+
+/* The same farm started from the caller's models (K0[nChains], cells0[nChains][4][Kcap0], x / y / z / zeta rows) instead of
+ * build_starting: bench.py times both arms on the same chain states. */
+int orc_chain_farm_from(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads, uint64_t seed,
+                        const int32_t *K0, const double *cells0, int Kcap0, double *phi_out, int32_t *K_out, int64_t *acc_out) {
+    if (!K0 || !cells0 || Kcap0 < 1) return -1;
+    return farm(p, d, nChains, nIter, nThreads, seed, phi_out, K_out, acc_out, K0, cells0, Kcap0);
+}
+
+static int farm(const orc_params *p, const orc_data *d, int nChains, int64_t nIter, int nThreads, uint64_t seed, double *phi_out,
+                int32_t *K_out, int64_t *acc_out, const int32_t *K0, const double *cells0, int Kcap0) {
     if (nThreads < 1) nThreads = 1;
     if (nThreads > nChains) nThreads = nChains;
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nThreads);
     worker_arg *args = (worker_arg *)malloc(sizeof(worker_arg) * (size_t)nThreads);
     for (int t = 0; t < nThreads; t++) {
-        args[t] = (worker_arg){p, d, t, nThreads, nChains, nIter, seed, p->max_cells + 1, phi_out, K_out, acc_out, 0};
+        args[t] = (worker_arg){p, d, t, nThreads, nChains, nIter, seed, p->max_cells + 1, phi_out, K_out, acc_out, 0, K0, cells0, Kcap0};
         pthread_create(&th[t], NULL, worker, &args[t]);
     }
     int rc = 0;
