@@ -100,6 +100,13 @@ _AK135_COARSE = np.array([  # fallback Vp(z) if no ak135 table is supplied (synt
     [660.0, 10.20], [660.0, 10.79], [760.0, 11.06]])
 
 
+def load_warm_start(path: str | None = None) -> dict:
+    """The warm start models of the headline benchmark (tools/make_warm_start.py): K[1024], cells[1024, 4, Kmax] -- the states
+    of 1024 chains of the 381-ray inversion after 20 000 iterations.  bench.py starts both of its arms from them."""
+    f = np.load(path or os.path.join(_DATASETS, "warm_start_1024.npz"))
+    return {"K": np.ascontiguousarray(f["K"], dtype=np.int32), "cells": np.ascontiguousarray(f["cells"], dtype=np.float64)}
+
+
 def synthetic_rays(R: int, seed: int = 3, pts=(150, 250), box=(1000.0, 1000.0, 660.0), n_true: int = 200,
                    zeta_scale: float = 50.0, jitter: float = 0.5, p: parameters | None = None,
                    ak135: np.ndarray | None = None) -> DataStruct:

@@ -48,14 +48,56 @@ def gather_ensembles(local: dict, counts, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return {k: v.clone() for k, v in local.items()}
-    nmax = int(max(counts))
+    nmax, even = int(max(counts)), len(set(int(c) for c in counts)) == 1
     out = {}
     for k, v in local.items():
+        if even:  # the usual case: one collective straight into the result, no padding, no concatenation
+            send = v.contiguous()
+            res = torch.empty((world * nmax,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            dist.all_gather_into_tensor(res, send, group=group)
+            out[k] = res
+            continue
         pad = torch.zeros((nmax,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
         pad[:v.shape[0]] = v
-        buf = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(buf, pad.contiguous(), group=group)
-        out[k] = torch.cat([b[:int(c)] for b, c in zip(buf, counts)], dim=0)
+        buf = torch.empty((world * nmax,) + tuple(pad.shape[1:]), dtype=v.dtype, device=v.device)  # gloo wants the concatenated shape
+        dist.all_gather_into_tensor(buf, pad, group=group)
+        buf = buf.view((world, nmax) + tuple(pad.shape[1:]))
+        out[k] = torch.cat([buf[r, :int(c)] for r, c in enumerate(counts)], dim=0)
+    return out
+
+
+def pack_history(chains, device, last: int = 50):
+    """The last `last` kept models of every chain of this rank as ONE dense tensor [n, last, 2 + 4 kmax] of doubles
+    (K, phi, then x / y / z / zeta of the valid nuclei; kmax = largest nCells among them) -- the record that is gathered for a
+    model.jld-equivalent ensemble.  The fixed-capacity device history holds 4 KC doubles of nuclei per model whatever K is."""
+    import torch
+    hv = history_tensors(chains, device)
+    last = max(0, min(int(chains.hist_cap), int(last)))
+    K = hv["K"][:, :last]
+    kmax = max(int(K.max().item()) if K.numel() else 1, 1)
+    rec = torch.empty((chains.n, last, 2 + 4 * kmax), dtype=torch.float64, device=device)
+    rec[:, :, 0] = K.to(torch.float64)
+    rec[:, :, 1] = hv["phi"][:, :last]
+    rec[:, :, 2:] = hv["cells"][:, :last, :, :kmax].reshape(chains.n, last, 4 * kmax)
+    return rec
+
+
+def allreduce_accumulators(acc, device, group=None):
+    """Sum the {sum, sum^2, count} accumulators of tonga_chains_raster over the ranks: ONE all-reduce for all slices.
+    acc: list of (s1, s2, count) per slice -> the same list, summed."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return acc
+    flat = np.concatenate([np.concatenate([s1, s2, [float(c)]]) for s1, s2, c in acc])
+    t = torch.from_numpy(flat).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t = t.cpu().numpy()
+    out, o = [], 0
+    for s1, s2, c in acc:
+        m = len(s1)
+        out.append((t[o:o + m], t[o + m:o + 2 * m], int(round(t[o + 2 * m]))))
+        o += 2 * m + 1
     return out
 
 

@@ -129,7 +129,7 @@ class _GatheredScalars:
         self.phi_v = torch.as_tensor(DeviceArray(p["phi"], (n,), "<f8"), device=dev)
         self.noise_v = torch.as_tensor(DeviceArray(p["noise"], (n,), "<f8"), device=dev)
         self.send = torch.empty((2, n), dtype=torch.float64, device=dev)
-        self.recv = torch.empty((world, 2, n), dtype=torch.float64, device=dev)
+        self.recv = torch.empty((world * 2, n), dtype=torch.float64, device=dev)  # rank-major blocks of (phi, noise)
         self.all = torch.empty((2, world * n), dtype=torch.float64, device=dev)
         self.beta = torch.as_tensor(np.ascontiguousarray(beta_all), device=dev)
         self.torch = torch
@@ -141,7 +141,7 @@ class _GatheredScalars:
         self.send[0].copy_(self.phi_v)
         self.send[1].copy_(self.noise_v)
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-        self.all.copy_(self.recv.permute(1, 0, 2).reshape(2, self.world * n))
+        self.all.copy_(self.recv.view(self.world, 2, n).permute(1, 0, 2).reshape(2, self.world * n))
         torch.cuda.current_stream().synchronize()  # the sweep runs on the library's stream
         self.chains.temper_swap(ladder_size, step, seed, n_all=self.world * n, phi_all=self.all[0].data_ptr(), noise_all=self.all[1].data_ptr(),
                                 beta_all=self.beta.data_ptr(), offset=self.rank * n)
@@ -154,6 +154,6 @@ def swap_step_distributed(E_local: np.ndarray, beta_all: np.ndarray, ladder_size
     import torch.distributed as dist
     world = dist.get_world_size(group)
     send = torch.from_numpy(np.ascontiguousarray(E_local, dtype=np.float64))
-    recv = torch.empty((world,) + tuple(send.shape), dtype=torch.float64)
+    recv = torch.empty((world * send.shape[0],) + tuple(send.shape[1:]), dtype=torch.float64)
     dist.all_gather_into_tensor(recv, send, group=group)
     return swap_step(recv.reshape(-1).numpy(), beta_all, ladder_size, step, seed)

@@ -71,3 +71,49 @@ def test_gather_is_independent_of_world_size(n_total):
     for _rank, ens in got:
         for k in ref:
             assert ens[k].shape == ref[k].shape and np.array_equal(ens[k], ref[k]), k
+
+
+def _ladder_worker(rank, world, port, n_local, T, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tonga_b200.tempering import geometric_ladder, swap_step_distributed
+        rng = np.random.default_rng(42)
+        E_all = rng.uniform(50.0, 400.0, world * n_local)            # every rank can regenerate the global energies ...
+        beta_all = np.tile(geometric_ladder(T, 50.0), world * n_local // T)
+        acc = att = 0
+        for step in range(6):
+            beta_all, a, t = swap_step_distributed(E_all[rank * n_local:(rank + 1) * n_local], beta_all, T, step, seed=13)  # ... but sends only its own
+            acc += a; att += t
+            E_all = E_all + 3.0 * np.sin(np.arange(len(E_all)) + step)   # new energies per sweep, the same on every rank
+        q.put((rank, beta_all, acc, att))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cross_rank_ladder_takes_the_single_rank_decisions():
+    """BASELINE config 5 across GPUs: a 256-rung ladder split over 2 ranks (128 replicas each).  Every rank all-gathers the
+    energies and applies the deterministic sweep; the betas must equal the single-process result bit for bit on both ranks."""
+    from tonga_b200.tempering import geometric_ladder, swap_step
+    world, n_local, T = 2, 128, 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ladder_worker, args=(r, world, port, n_local, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(42)
+    E = rng.uniform(50.0, 400.0, world * n_local)
+    beta = np.tile(geometric_ladder(T, 50.0), world * n_local // T)
+    acc = att = 0
+    for step in range(6):
+        beta, a, t = swap_step(E, beta, T, step, seed=13)
+        acc += a; att += t
+        E = E + 3.0 * np.sin(np.arange(len(E)) + step)
+    assert att == 3 * 128 + 3 * 127 and 0 < acc <= att
+    for _rank, b, a, t in got:
+        assert np.array_equal(b, beta) and (a, t) == (acc, att)

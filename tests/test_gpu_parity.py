@@ -1009,3 +1009,43 @@ def test_streamed_screening_equals_exact(tonga):
     assert a["recs"].tobytes() == b["recs"].tobytes() and np.array_equal(a["accept"], b["accept"]) and a["phi"].tobytes() == b["phi"].tobytes()
     assert np.array_equal(sa["owners"], sb["owners"]) and sa["ptS"].tobytes() == sb["ptS"].tobytes()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_device_tempering_sweep_matches_the_numpy_mirror(tonga):
+    """Extension (BASELINE config 5): the swap sweep decided on the device from the replicas' own phi / noise equals the
+    NumPy mirror (same Philox counters, same order of operations) -- the property that lets every rank of a cross-GPU ladder
+    take identical decisions.  Both ways of calling it: the batch's own arrays, and external all-gathered device arrays."""
+    import copy
+    import torch
+    from tonga_b200 import api
+    from tonga_b200.tempering import energy, geometric_ladder, swap_step
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.max_sig = 2.0
+    ctx = api.Context(ds, p, n_actions=5)
+    T, L = 16, 8
+    ch = api.Chains(ctx, T * L, seed=3, hist_cap=0)
+    ch.build_starting()
+    beta = np.tile(geometric_ladder(T, 50.0), L)
+    ch.set_beta(beta)
+    acc = att = 0
+    for step in range(6):
+        ch.run(50)
+        st = ch.state(want_ptS=False)
+        ref, a, t = swap_step(energy(st["phi"], st["noise"], ctx.R), beta, T, step, seed=21)
+        acc += a; att += t
+        if step % 2 == 0:
+            ch.temper_swap(T, step, seed=21)
+        else:  # external arrays (what a multi-rank caller passes after its all-gather): here a copy of the batch's own
+            phi_d, noise_d, beta_d = (torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (st["phi"], st["noise"], beta))
+            torch.cuda.synchronize()
+            ch.temper_swap(T, step, seed=21, n_all=T * L, phi_all=phi_d.data_ptr(), noise_all=noise_d.data_ptr(), beta_all=beta_d.data_ptr(), offset=0)
+            ctx.synchronize()
+            assert np.array_equal(beta_d.cpu().numpy(), ref)
+        beta = ch.get_beta()
+        assert np.array_equal(beta, ref), step
+    assert ch.temper_stats() == (acc, att) and 0 < acc < att
+    ck = ch.checkpoint()
+    assert np.array_equal(ck["beta"], beta)  # tempered batches resume with their temperatures
+    ch.close(); ctx.close()
