@@ -455,25 +455,25 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         const double *dtp = h.dt + tq0 + sub;
         const int nl = nseg - sub;  // this lane's segments: j = sub + 8 k < nseg  <=>  8 k < nl
         double acc = 0.0;
+        double dn[4];  // dt of the next round: the only global (L2) loads of the loop, requested one round ahead
+#pragma unroll
+        for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
 #pragma unroll 1
-        for (int k0 = 0; k0 < trip; k0 += 8, ow += 64, dtp += 64) {
-            // 8 passes per round in quarters of 2; quarters beyond `trip` are skipped by warp-uniform branches, the loads of the
-            // round's live quarters are all issued before the first use
-            const int rem = trip - k0;
-            double d[8];
+        for (int k0 = 0; k0 < trip; k0 += 4, ow += 32) {
+            // 4 passes per round, staged: all loads of a stage are issued before the first use (the per-pass chain owner byte ->
+            // halved zeta -> term is a sequence of dependent shared-memory round trips; four of them overlap)
+            double d[4], za[4], zb[4];
+            uint32_t oa[4], ob[4];
+            dtp += 32;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (2 * q < rem) { d[2 * q] = __ldg(dtp + 16 * q); d[2 * q + 1] = __ldg(dtp + 16 * q + 8); }
+            for (int u = 0; u < 4; u++) { d[u] = dn[u]; dn[u] = __ldg(dtp + 8 * u); oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (2 * q < rem) {
+            for (int u = 0; u < 4; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
 #pragma unroll
-                    for (int u = 2 * q; u < 2 * q + 2; u++) {
-                        const double m = __dadd_rn(s_zh[ow[8 * u]], s_zh[ow[8 * u + 1]]);
-                        const double term = __dmul_rn(d[u], div1000_exact(m));
-                        if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
-                    }
-                }
+            for (int u = 0; u < 4; u++) {
+                const double term = __dmul_rn(d[u], div1000_exact(__dadd_rn(za[u], zb[u])));
+                if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
+            }
         }
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
