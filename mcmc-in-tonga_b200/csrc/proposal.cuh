@@ -22,6 +22,7 @@ __device__ __noinline__ int warp_nearest(const double *nx, const double *ny, con
                                          double y, double z, int lane) {
     double best = 1e9;
     int bi = 0x7fffffff;
+#pragma unroll 1  // (code size: the kernel is bound by instruction supply; K <= 32 makes this a single trip anyway)
     for (int i = lane; i < K; i += 32) {
         if (i == skip) continue;
         const double d = dist2_exact(nx[i], ny[i], nz[i], x, y, z);

@@ -288,7 +288,7 @@ static __device__ __noinline__ uint32_t phase_b1_scan(const int act, const int p
     const int nBlocks = h.nBlocks;
     uint32_t blkmask = 0u;
     int bi = 0;
-#pragma unroll 2
+#pragma unroll 1
     for (int blk = warp; blk < nBlocks; blk += NW, bi++) {
         const int w = blk * 32 + lane;
         const uint32_t eq = __vcmpeq4(s_own32[w], kk);  // bytes owned by the killed / changed nucleus
