@@ -280,4 +280,10 @@ __device__ __forceinline__ int accept_decision(const Prop &pr, int K, double phi
     return u < jl_min1(alpha);
 }
 
+// the same as a real function call (the resident sampler keeps its per-iteration code path short: instruction supply)
+static __device__ __noinline__ int accept_decision_call(const Prop &pr, int K, double phi, double phin, double zeta_idx, double noise, double beta,
+                                                        int R, const tonga_params &pm, double sig_zeta) {
+    return accept_decision(pr, K, phi, phin, zeta_idx, noise, beta, R, pm, sig_zeta);
+}
+
 }  // namespace tg

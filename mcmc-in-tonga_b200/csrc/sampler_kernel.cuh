@@ -568,6 +568,50 @@ static __device__ __noinline__ void phase_f_renumber(const int pidx) {
     }
 }
 
+// accepted death: order-preserving delete of nucleus `pidx` (deleteat!, TD_inversion_function.jl:132-135) by one warp
+static __device__ __noinline__ void phase_f_delete(const int pidx, const int K) {
+    const Hdr &h = hdr();
+    const int lane = threadIdx.x & 31;
+    double *s_nx = reinterpret_cast<double *>(tg_smem + h.o_nuc), *s_ny = s_nx + h.KC, *s_nz = s_ny + h.KC, *s_zeta = s_nz + h.KC;
+    float *s_fx = reinterpret_cast<float *>(tg_smem + h.o_nucf), *s_fy = s_fx + h.KC, *s_fz = s_fy + h.KC;
+    double *s_zh = hdr().zh;
+    for (int s0 = 0; s0 < K - 1 - pidx; s0 += 32) {
+        const int i = pidx + s0 + lane;
+        double vx = 0, vy = 0, vz = 0, vt = 0;
+        if (i < K - 1) { vx = s_nx[i + 1]; vy = s_ny[i + 1]; vz = s_nz[i + 1]; vt = s_zeta[i + 1]; }
+        __syncwarp();
+        if (i < K - 1) {
+            s_nx[i] = vx; s_ny[i] = vy; s_nz[i] = vz; s_zeta[i] = vt; s_zh[i] = __dmul_rn(0.5, vt);
+            s_fx[i] = (float)vx; s_fy[i] = (float)vy; s_fz[i] = (float)vz;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {  // freed slot
+        s_fx[K - 1] = s_fy[K - 1] = s_fz[K - 1] = __int_as_float(0x7f800000);
+        s_zh[K - 1] = 0.0;
+    }
+}
+
+// thinning with a non-integral keep_each (TD_inversion_function.jl:278 in general): rare, kept out of the loop's code path
+static __device__ __noinline__ int keep_by_fmod(long long model_num, double keep_each) { return fmod((double)model_num, keep_each) == 0; }
+
+// the kept model -> history record (TD_inversion_function.jl:280).  Only the K valid nuclei of each axis are stored (the record
+// keeps its fixed [4][KC] layout; the rest is never read).  The copy may overlap the next iteration's phases A..B: they modify
+// neither the FP64 nuclei nor t* nor phi.
+static __device__ __noinline__ void write_history(double *__restrict__ hc, double *__restrict__ hp, const int32_t *__restrict__ ray_rank, const int K,
+                                                  const int R) {
+    const Hdr &h = hdr();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *s_nx = reinterpret_cast<const double *>(tg_smem + h.o_nuc);
+    const double *s_tstar = reinterpret_cast<const double *>(tg_smem + h.o_tstar);
+    const int KC = h.KC;
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32)
+        for (int ax = warp; ax < 4; ax += NW) hc[ax * KC + k] = s_nx[ax * KC + k];
+#pragma unroll 1
+    for (int i = tid; i < R; i += ST) hp[i] = s_tstar[__ldg(ray_rank + i)];  // caller's ray order; contiguous stores (the history may live in mapped host memory)
+}
+
 // =================================================================================================== the kernel
 template <int NCH, bool PROF>
 __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) {
@@ -780,7 +824,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 if (pm.debug_prior) phin = 1.0;  // MCsub.jl:128-136: the chain samples the prior
                 Prop pr;
                 pr.action = act; pr.idx = pidx; pr.zeta = s_prop->zeta; pr.aux = s_prop->aux; pr.u = s_prop->u;
-                accepted = accept_decision(pr, K, s_st->phi, phin, s_prop->zold, s_st->noise, s_st->beta, R, pm, sig_zeta);
+                accepted = accept_decision_call(pr, K, s_st->phi, phin, s_prop->zold, s_st->noise, s_st->beta, R, pm, sig_zeta);
             }
             tick(3);
             // ============================================================ F: commit / roll back, every warp on its own blocks and rays
@@ -796,23 +840,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             if (act == 2 && accepted) {
                 phase_f_renumber(pidx);
                 __syncthreads();  // the cache refresh above read the nuclei the delete below shifts
-                if (warp == 0) {  // order-preserving delete of the nucleus
-                    for (int s0 = 0; s0 < K - 1 - pidx; s0 += 32) {
-                        const int i = pidx + s0 + lane;
-                        double vx = 0, vy = 0, vz = 0, vt = 0;
-                        if (i < K - 1) { vx = s_nx[i + 1]; vy = s_ny[i + 1]; vz = s_nz[i + 1]; vt = s_zeta[i + 1]; }
-                        __syncwarp();
-                        if (i < K - 1) {
-                            s_nx[i] = vx; s_ny[i] = vy; s_nz[i] = vz; s_zeta[i] = vt; s_zh[i] = __dmul_rn(0.5, vt);
-                            s_fx[i] = (float)vx; s_fy[i] = (float)vy; s_fz[i] = (float)vz;
-                        }
-                        __syncwarp();
-                    }
-                    if (lane == 0) {  // freed slot
-                        s_fx[K - 1] = s_fy[K - 1] = s_fz[K - 1] = FINF;
-                        s_zh[K - 1] = 0.0;
-                    }
-                }
+                if (warp == 0) phase_f_delete(pidx, K);
             }
             if (tid == 0) {
                 if (act == 1 && accepted) {  // append!, :85-88
@@ -846,7 +874,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         if ((double)iter >= pm.burn_in) {
             mn_inc += 1;
             if (keep_i) { if (++keep_ctr == keep_i) { keep_ctr = 0; keep = 1; } }
-            else if (fmod((double)(a.model_num[chain] + mn_inc), pm.keep_each) == 0) keep = 1;
+            else keep = keep_by_fmod(a.model_num[chain] + mn_inc, pm.keep_each);
         }
         if (tid == 0) {
             if (act >= 1 && act <= 5) {
@@ -860,16 +888,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         }
         if (keep && cold) {
             if (n_hist < a.hist_cap) {
-                // Only the K valid nuclei of each axis are stored (the record keeps its fixed [4][KC] layout; the rest is never read).
-                // The copy may overlap the next iteration's phases A..B: they modify neither the FP64 nuclei nor t* nor phi.
                 const size_t hh = (size_t)chain * a.hist_cap + n_hist;
-                double *hc = a.hist_cells + hh * 4 * KC;
-#pragma unroll 1
-                for (int k = lane; k < K; k += 32)
-                    for (int ax = warp; ax < 4; ax += NW) hc[ax * KC + k] = s_nx[ax * KC + k];
-                double *hp = a.hist_ptS + hh * R;
-#pragma unroll 1
-                for (int i = tid; i < R; i += ST) hp[i] = s_tstar[a.ray_rank[i]];  // caller's ray order; contiguous stores (the history may live in mapped host memory)
+                write_history(a.hist_cells + hh * 4 * KC, a.hist_ptS + hh * R, a.ray_rank, K, R);
                 if (tid == 0) {
                     a.hist_K[hh] = K; a.hist_phi[hh] = s_st->phi; a.hist_iter[hh] = iter;
                     a.hist_action[hh] = act; a.hist_accept[hh] = accepted; a.hist_next[hh] = 0;
