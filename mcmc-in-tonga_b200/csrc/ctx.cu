@@ -189,19 +189,15 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     {   // fl32 copies + the rigorous screening band: with u = 2^-24 and M = max |coordinate| (points and box),
         // |D32 - D| <= 11u*D32 + 7.5u*M^2 for any evaluation order; alpha = 16u and beta = 12u*M^2 leave a 1.4x margin.
         std::vector<float> xf(Ppad + TG_PT_SLACK, 0.f), yf(Ppad + TG_PT_SLACK, 0.f), zf(Ppad + TG_PT_SLACK, 0.f);
-        double M = 0.0;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (int64_t i = 0; i < Ppad; i++) {
             xf[i] = i < P ? (float)px[i] : TG_PAD_COORD; yf[i] = i < P ? (float)py[i] : TG_PAD_COORD; zf[i] = i < P ? (float)pz[i] : TG_PAD_COORD;
             if (i < P) {
-                for (double v : {px[i], py[i], pz[i]})
-                    if (std::fabs(v) > M) M = std::fabs(v);  // NaN never compares greater
+                const double v[3] = {px[i], py[i], pz[i]};
+                for (int a = 0; a < 3; a++) { if (v[a] < lo[a]) lo[a] = v[a]; if (v[a] > hi[a]) hi[a] = v[a]; }  // NaN never compares
             }
         }
-        for (double v : {params->xmin, params->xmax, params->ymin, params->ymax, params->zmin, params->zmax})
-            if (std::fabs(v) > M) M = std::fabs(v);
-        const double u = 5.9604644775390625e-08;
-        ctx->tol_alpha = (float)(16.0 * u);
-        ctx->tol_beta2 = (float)(2.0 * 12.0 * u * M * M * 1.0000002);
+        tg::set_screening_bounds(ctx, lo, hi);
         chk(upload(&ctx->d_pxf, xf, ctx->stream));
         chk(upload(&ctx->d_pyf, yf, ctx->stream));
         chk(upload(&ctx->d_pzf, zf, ctx->stream));
@@ -226,6 +222,28 @@ extern "C" int tonga_create(tonga_ctx **out, int32_t m, int32_t R, const double 
     }
     *out = ctx;
     return TONGA_OK;
+}
+
+void tg::set_screening_bounds(tonga_ctx *ctx, const double lo[3], const double hi[3]) {
+    // fl32 screening band of the samplers: with u = 2^-24 and M = max |coordinate| (points and box),
+    // |D32 - D| <= 11u*D32 + 7.5u*M^2 for any evaluation order; alpha = 16u and beta = 12u*M^2 leave a 1.4x margin.
+    const tonga_params &pm = ctx->prm;
+    const double blo[3] = {pm.xmin, pm.ymin, pm.zmin}, bhi[3] = {pm.xmax, pm.ymax, pm.zmax};
+    double M = 0.0;
+    for (int a = 0; a < 3; a++) {
+        const bool pts = lo[a] <= hi[a];
+        for (double v : {pts ? lo[a] : 0.0, pts ? hi[a] : 0.0, blo[a], bhi[a]})
+            if (std::fabs(v) > M) M = std::fabs(v);
+        ctx->cen[a] = 0.5 * (blo[a] + bhi[a]);
+        if (!(std::fabs(ctx->cen[a]) < 1e300)) ctx->cen[a] = 0.0;
+        const double mc = pts ? std::max(std::fabs(lo[a] - ctx->cen[a]), std::fabs(hi[a] - ctx->cen[a])) : 0.0;
+        const double ma = pts ? std::max(std::fabs(lo[a]), std::fabs(hi[a])) : 0.0;
+        ctx->mp_cen[a] = (float)(mc * 1.000001);
+        ctx->mp_abs[a] = (float)(ma * 1.000001);
+    }
+    const double u = 5.9604644775390625e-08;
+    ctx->tol_alpha = (float)(16.0 * u);
+    ctx->tol_beta2 = (float)(2.0 * 12.0 * u * M * M * 1.0000002);
 }
 
 extern "C" void tonga_destroy(tonga_ctx *ctx) {

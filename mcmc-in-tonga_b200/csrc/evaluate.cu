@@ -19,11 +19,27 @@ constexpr int EVAL_THREADS = 256;
 constexpr int EVAL_PPT = 4;  // points per thread per pass
 #define TG_NONE16 0xFFFFu
 
+// Screening arithmetic of phase 1 (FP32, any rounding is fine: a rigorous error band decides what is re-done in FP64):
+// with c = centre of the nucleus box, p' = p - c, n' = n - c,
+//     |p - n|^2 = |p'|^2 + ( |n'|^2 - 2 p'.n' )
+// so a nucleus is four fl32 coefficients (-2 n'x, -2 n'y, -2 n'z, |n'|^2) -- ONE 128-bit shared-memory broadcast -- and a
+// (point, nucleus) pair costs 3 FMAs + 1 add, issued as packed FFMA2 / FADD2 over point pairs: 2 instructions per pair
+// instead of 3 for (dx^2 + dy^2 + dz^2).  Best and second best are kept as INTEGER min / max of the distance bits with the
+// nucleus index (mod 128) in the 7 low mantissa bits (non-negative floats order like their bits; nuclei are visited in
+// chunks of 128): 4 ALU instructions per pair instead of a compare and three selects.
+// Error band (u = 2^-24; per axis a: A_a = max |p'_a|, |n'_a| over the tile's model, M_a = max |p_a|): every one of the five
+// terms is <= 3u off (two input roundings, one operation), the four additions round partial sums bounded by
+// S = 4 sum_a A_a^2, and p' inherits the fl32 rounding of p:  |D32 - D| <= u sum_a (28 A_a^2 + 4 A_a (M_a + A_a)) =: B.
+// The index bits truncate by 2^-16 relative.  Two distances are separated for certain if
+//     d2 - d1 > alpha (d1 + d2) + beta,   alpha = 2^-16 + 2^-19,  beta = 2.5 B
+// (2 B for the two values, 25 % margin); anything else -- also a best within the band of the 1e9 "no nucleus" threshold --
+// goes to a per-tile queue and is re-scanned in exact FP64 by the whole CTA after the pass (no divergent rescans inside it).
 __global__ void __launch_bounds__(EVAL_THREADS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
-               const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, float tol_alpha,
-               float tol_beta2, int exact_only, const double *__restrict__ dt, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
+               const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, double cenx, double ceny,
+               double cenz, float mpx, float mpy, float mpz /* max |p'| per axis over the ray set */, float mux, float muy,
+               float muz /* max |p| per axis */, int exact_only, const double *__restrict__ dt, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
                const int32_t *__restrict__ point_orig, int R, int64_t P, int64_t Ppad, int tile_pts,
                double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32,
                uint16_t *__restrict__ owners16) {
@@ -32,112 +48,177 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     const Tile tile = tiles[blockIdx.x];
     const int K = Ks[model];
     if (K < 0) return;  // wide sampler: this chain has no candidate to evaluate in this iteration
-    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier | fl32 x,y,z [3][Kcap] | owner16[tile_pts]
+    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier, counters | float4 coefficients [Kcap + 2] | owner16[tile_pts] | queue16[tile_pts]
     double *s_nx = reinterpret_cast<double *>(smem_raw);
     double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zeta + Kcap);
-    float *s_fx = reinterpret_cast<float *>(s_bar + 1);
-    float *s_fy = s_fx + Kcap, *s_fz = s_fy + Kcap;
-    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_fz + Kcap);
+    int *s_nq = reinterpret_cast<int *>(s_bar + 1);
+    float *s_red = reinterpret_cast<float *>(s_nq + 2);  // [3][8] per-warp maxima
+    float4 *s_cf = reinterpret_cast<float4 *>(s_red + 24);
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_cf + Kcap + 2);
+    uint16_t *s_queue = s_owner + tile_pts;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     const double *mc = cells + (size_t)model * 4 * Kcap;
     const uint32_t nbytes = (uint32_t)(4 * Kcap * sizeof(double));
     const bool use_bulk = (nbytes >= 2048u) && ((nbytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(mc) & 15u) == 0);
     if (use_bulk) {  // one TMA bulk copy of the whole [4][Kcap] block
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             mbar_init(s_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             mbar_expect_tx(s_bar, nbytes);
             bulk_g2s(s_nx, mc, nbytes, s_bar);
         }
         mbar_wait(s_bar, 0);
     } else {
-        for (int i = threadIdx.x; i < 4 * Kcap; i += EVAL_THREADS) s_nx[i] = mc[i];
+        for (int i = tid; i < 4 * Kcap; i += EVAL_THREADS) s_nx[i] = mc[i];
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < 3 * Kcap; i += EVAL_THREADS) s_fx[i] = (float)s_nx[i];  // fl32 copies for the screening pass
+    // the model's coordinate bound (for the band), then the fl32 coefficients of the nuclei
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i = tid; i < K; i += EVAL_THREADS) {
+        ax = fmaxf(ax, fabsf((float)(s_nx[i] - cenx))); ay = fmaxf(ay, fabsf((float)(s_ny[i] - ceny))); az = fmaxf(az, fabsf((float)(s_nz[i] - cenz)));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        ax = fmaxf(ax, __shfl_xor_sync(0xffffffffu, ax, off)); ay = fmaxf(ay, __shfl_xor_sync(0xffffffffu, ay, off)); az = fmaxf(az, __shfl_xor_sync(0xffffffffu, az, off));
+    }
+    if (lane == 0) { s_red[warp] = ax; s_red[8 + warp] = ay; s_red[16 + warp] = az; }
+    if (tid == 0) s_nq[0] = 0;
     __syncthreads();
-
-    // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263).
-    // FP32 screening: best and second-best squared distance per point (4 points per thread, packed FADD2/FMUL2/FFMA2 over point
-    // pairs, each nucleus broadcast from shared memory); a point whose two best candidates are closer than the rigorous
-    // rounding-error band (or whose best is within the band of the 1e9 threshold) is re-scanned exactly in FP64, so the owners
-    // are bit-exact either way.
-    const int npts = tile.p1 - tile.p0;
-    for (int base = 0; base < npts; base += EVAL_THREADS * EVAL_PPT) {
-        int bi[EVAL_PPT];
-        float dbest[EVAL_PPT];
-        uint32_t need_exact = 0;
-        int pidx[EVAL_PPT];
-#pragma unroll
-        for (int q = 0; q < EVAL_PPT; q++) {
-            const int j = base + q * EVAL_THREADS + threadIdx.x;
-            pidx[q] = tile.p0 + (j < npts ? j : 0);
+    float tol_beta, d_off;
+    {
+        float A[3] = {mpx, mpy, mpz};
+        for (int w = 0; w < EVAL_THREADS / 32; w++) { A[0] = fmaxf(A[0], s_red[w]); A[1] = fmaxf(A[1], s_red[8 + w]); A[2] = fmaxf(A[2], s_red[16 + w]); }
+        const float Mu[3] = {mux, muy, muz};
+        float B = 0.f;
+        for (int a_ = 0; a_ < 3; a_++) {
+            const float Aa = A[a_] * 1.000001f + 1e-30f;  // (A itself was rounded to fl32)
+            B += 28.f * Aa * Aa + 4.f * Aa * (Mu[a_] + Aa);
         }
-        if (!exact_only) {
-            const float2 X01 = make_float2(pxf[pidx[0]], pxf[pidx[1]]), X23 = make_float2(pxf[pidx[2]], pxf[pidx[3]]);
-            const float2 Y01 = make_float2(pyf[pidx[0]], pyf[pidx[1]]), Y23 = make_float2(pyf[pidx[2]], pyf[pidx[3]]);
-            const float2 Z01 = make_float2(pzf[pidx[0]], pzf[pidx[1]]), Z23 = make_float2(pzf[pidx[2]], pzf[pidx[3]]);
-            float d1[EVAL_PPT], d2[EVAL_PPT];
-#pragma unroll
-            for (int q = 0; q < EVAL_PPT; q++) { d1[q] = 1e9f; d2[q] = 1e9f; bi[q] = -1; }
-#pragma unroll 2
-            for (int i = 0; i < K; i++) {
-                const float ax = -s_fx[i], ay = -s_fy[i], az = -s_fz[i];
-                const float2 nax = make_float2(ax, ax), nay = make_float2(ay, ay), naz = make_float2(az, az);
-                float2 ex = __fadd2_rn(X01, nax), ey = __fadd2_rn(Y01, nay), ez = __fadd2_rn(Z01, naz);
-                const float2 da = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
-                ex = __fadd2_rn(X23, nax); ey = __fadd2_rn(Y23, nay); ez = __fadd2_rn(Z23, naz);
-                const float2 db = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
-                const float d[EVAL_PPT] = {da.x, da.y, db.x, db.y};
-#pragma unroll
-                for (int q = 0; q < EVAL_PPT; q++) {  // (a "rarely taken update branch" variant was measured: at warp level it is taken
-                    const bool lt = d[q] < d1[q];     //  almost every step, so the branch-free selects are as fast or faster)
-                    d2[q] = lt ? d1[q] : fminf(d2[q], d[q]);
-                    bi[q] = lt ? i : bi[q];
-                    d1[q] = lt ? d[q] : d1[q];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < EVAL_PPT; q++) {
-                dbest[q] = d1[q];
-                const float tol = fmaf(tol_alpha, d1[q] + d2[q], tol_beta2);
-                if (!(d2[q] - d1[q] > tol)) need_exact |= 1u << q;  // ambiguous (d2 starts at 1e9: also covers the 1e9 threshold; NaN too)
-            }
+        B *= 5.9604644775390625e-08f * 1.00001f;
+        d_off = 1.5f * B;     // added to every |n'|^2: the computed distances stay >= 0 (non-negative floats order like their bits)
+        tol_beta = 2.5f * B + 6.0f * 5.9604644775390625e-08f * d_off;
+    }
+    for (int i = tid; i < K + 2; i += EVAL_THREADS) {
+        if (i < K) {
+            const double nx = s_nx[i] - cenx, ny = s_ny[i] - ceny, nz = s_nz[i] - cenz;
+            s_cf[i] = make_float4((float)(-2.0 * nx), (float)(-2.0 * ny), (float)(-2.0 * nz), (float)(nx * nx + ny * ny + nz * nz + (double)d_off));
         } else {
-            need_exact = (1u << EVAL_PPT) - 1u;
+            s_cf[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));  // padding nuclei (the loop visits pairs): +inf, never win
         }
-        if (need_exact) {
+    }
+    __syncthreads();
+    const float tol_alpha = 0x1.0p-16f + 0x1.0p-19f;
+    const float fcx = (float)cenx, fcy = (float)ceny, fcz = (float)cenz;
+
+    // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263)
+    const int npts = tile.p1 - tile.p0;
+    const uint32_t INF_PACK = 0x7f800000u | 0x7Fu;
+    for (int base = 0; base < npts; base += EVAL_THREADS * EVAL_PPT) {
+        int pidx[EVAL_PPT];
+        bool in[EVAL_PPT];
+#pragma unroll
+        for (int q = 0; q < EVAL_PPT; q++) {
+            const int j = base + q * EVAL_THREADS + tid;
+            in[q] = j < npts;
+            pidx[q] = tile.p0 + (in[q] ? j : 0);
+        }
+        float D1[EVAL_PPT], D2[EVAL_PPT];
+        int I1[EVAL_PPT];
+        uint32_t need_exact = exact_only ? (1u << EVAL_PPT) - 1u : 0u;
+        float xs[EVAL_PPT], ys[EVAL_PPT], zs[EVAL_PPT];
+#pragma unroll
+        for (int q = 0; q < EVAL_PPT; q++) { xs[q] = pxf[pidx[q]]; ys[q] = pyf[pidx[q]]; zs[q] = pzf[pidx[q]]; D1[q] = 1e9f; D2[q] = 1e9f; I1[q] = -1; }
+        if (!exact_only) {
+            const float2 X01 = make_float2(xs[0] - fcx, xs[1] - fcx), X23 = make_float2(xs[2] - fcx, xs[3] - fcx);
+            const float2 Y01 = make_float2(ys[0] - fcy, ys[1] - fcy), Y23 = make_float2(ys[2] - fcy, ys[3] - fcy);
+            const float2 Z01 = make_float2(zs[0] - fcz, zs[1] - fcz), Z23 = make_float2(zs[2] - fcz, zs[3] - fcz);
+            const float2 Q01 = __ffma2_rn(Z01, Z01, __ffma2_rn(Y01, Y01, __fmul2_rn(X01, X01))), Q23 = __ffma2_rn(Z23, Z23, __ffma2_rn(Y23, Y23, __fmul2_rn(X23, X23)));
 #pragma unroll 1
-            for (int q = 0; q < EVAL_PPT; q++) {
-                if (!((need_exact >> q) & 1u)) continue;
-                const double x = px[pidx[q]], y = py[pidx[q]], z = pz[pidx[q]];
-                double best = 1e9;  // mdist = 1e9, MCsub.jl:250
-                int b = -1;
-#pragma unroll 2
-                for (int i = 0; i < K; i++) {
-                    const double d = dist2_exact(s_nx[i], s_ny[i], s_nz[i], x, y, z);
-                    if (d < best) { best = d; b = i; }  // strict <: lowest index wins ties (:255)
+            for (int cb = 0; cb < K; cb += 128) {  // chunks of 128 nuclei: 7 index bits
+                const int kend = min(128, (K - cb + 1) & ~1);
+                uint32_t c1[EVAL_PPT], c2[EVAL_PPT];
+#pragma unroll
+                for (int q = 0; q < EVAL_PPT; q++) { c1[q] = INF_PACK; c2[q] = INF_PACK; }
+                const float4 *cf = s_cf + cb;
+#pragma unroll 1
+                for (int i = 0; i < kend; i += 2) {  // two nuclei per step: the ALU pipe (min / max, rt 2) is the limiter, see below
+                    const float4 cA = cf[i], cB = cf[i + 1];
+                    float dA[EVAL_PPT], dB[EVAL_PPT];
+                    {
+                        const float2 ca = make_float2(cA.x, cA.x), cbv = make_float2(cA.y, cA.y), cc = make_float2(cA.z, cA.z), ce = make_float2(cA.w, cA.w);
+                        const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
+                        const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
+                        dA[0] = da.x; dA[1] = da.y; dA[2] = db.x; dA[3] = db.y;
+                    }
+                    {
+                        const float2 ca = make_float2(cB.x, cB.x), cbv = make_float2(cB.y, cB.y), cc = make_float2(cB.z, cB.z), ce = make_float2(cB.w, cB.w);
+                        const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
+                        const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
+                        dB[0] = da.x; dB[1] = da.y; dB[2] = db.x; dB[3] = db.y;
+                    }
+#pragma unroll
+                    for (int q = 0; q < EVAL_PPT; q++) {
+                        // (best, second best) of {c1, c2, a, b} in 5 min / max operations for TWO pairs: 3.5 ALU instructions per pair
+                        // with the two packs.  The distances are >= 0 by construction (offset in the coefficients, see above).
+                        const uint32_t a_ = (__float_as_uint(dA[q]) & 0xFFFFFF80u) | (uint32_t)i, b_ = (__float_as_uint(dB[q]) & 0xFFFFFF80u) | (uint32_t)(i + 1);
+                        const uint32_t m = min(a_, b_), M = max(a_, b_);
+                        c2[q] = __vimin3_u32(c2[q], max(c1[q], m), M);
+                        c1[q] = min(c1[q], m);
+                    }
                 }
-                bi[q] = b;
-                dbest[q] = (float)best;
+#pragma unroll
+                for (int q = 0; q < EVAL_PPT; q++) {  // merge the chunk's (best, second best) into the running ones
+                    const float f1 = __uint_as_float(c1[q] & 0xFFFFFF80u), f2 = __uint_as_float(c2[q] & 0xFFFFFF80u);
+                    const bool lt = f1 < D1[q];
+                    D2[q] = lt ? fminf(D1[q], f2) : fminf(D2[q], f1);
+                    I1[q] = lt ? cb + (int)(c1[q] & 0x7Fu) : I1[q];
+                    D1[q] = lt ? f1 : D1[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < EVAL_PPT; q++) {
+                const float tol = fmaf(tol_alpha, D1[q] + D2[q], tol_beta);
+                if (!(D2[q] - D1[q] > tol)) need_exact |= 1u << q;  // ambiguous (D2 starts at 1e9: also covers the 1e9 threshold; NaN too)
             }
         }
 #pragma unroll
         for (int q = 0; q < EVAL_PPT; q++) {
-            const int j = base + q * EVAL_THREADS + threadIdx.x;
-            if (j < npts) {
-                s_owner[j] = bi[q] < 0 ? (uint16_t)TG_NONE16 : (uint16_t)bi[q];
-                const int64_t p = tile.p0 + j;
-                if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi[q];  // caller's flat order
-                if (owners8) owners8[(size_t)model * Ppad + p] = bi[q] < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi[q];
-                if (owners16) owners16[(size_t)model * Ppad + p] = s_owner[j];  // streamed sampler's chain state
-                if (dmin32) dmin32[(size_t)model * Ppad + p] = bi[q] < 0 ? 1e9f : dbest[q];  // owner distance cache of the sampler
-            }
+            const int j = base + q * EVAL_THREADS + tid;
+            if (!in[q]) continue;
+            if ((need_exact >> q) & 1u) { s_queue[atomicAdd(&s_nq[0], 1)] = (uint16_t)j; continue; }
+            const int bi = I1[q];
+            s_owner[j] = bi < 0 ? (uint16_t)TG_NONE16 : (uint16_t)bi;
+            const int64_t p = tile.p0 + j;
+            if (owners32) owners32[(size_t)model * P + point_orig[p]] = bi;  // caller's flat order
+            if (owners8) owners8[(size_t)model * Ppad + p] = bi < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)bi;
+            if (owners16) owners16[(size_t)model * Ppad + p] = s_owner[j];  // streamed sampler's chain state
+            if (dmin32)  // owner distance cache of the samplers: the direct fl32 form they use themselves
+                dmin32[(size_t)model * Ppad + p] = bi < 0 ? 1e9f : dist2_f32((float)s_nx[bi], (float)s_ny[bi], (float)s_nz[bi], xs[q], ys[q], zs[q]);
         }
+    }
+    __syncthreads();
+    // ---- the queue: exact FP64 re-scan (MCsub.jl:252-259: strict <, lowest index wins ties, 1e9 start value)
+    const int nq = s_nq[0];
+    for (int qi = tid; qi < nq; qi += EVAL_THREADS) {
+        const int j = s_queue[qi];
+        const int64_t p = tile.p0 + j;
+        const double x = px[p], y = py[p], z = pz[p];
+        double best = 1e9;  // mdist = 1e9, MCsub.jl:250
+        int b = -1;
+#pragma unroll 2
+        for (int i = 0; i < K; i++) {
+            const double d = dist2_exact(s_nx[i], s_ny[i], s_nz[i], x, y, z);
+            if (d < best) { best = d; b = i; }  // strict <: lowest index wins ties (:255)
+        }
+        s_owner[j] = b < 0 ? (uint16_t)TG_NONE16 : (uint16_t)b;
+        if (owners32) owners32[(size_t)model * P + point_orig[p]] = b;
+        if (owners8) owners8[(size_t)model * Ppad + p] = b < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)b;
+        if (owners16) owners16[(size_t)model * Ppad + p] = s_owner[j];
+        if (dmin32) dmin32[(size_t)model * Ppad + p] = b < 0 ? 1e9f : (float)best;
     }
     __syncthreads();
 
@@ -187,12 +268,13 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
-        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + sizeof(float) * 3 * (size_t)Kcap + sizeof(uint16_t) * (size_t)ctx->tile_pts;
+        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + 8 + 96 + 16 * ((size_t)Kcap + 2) + 2 * sizeof(uint16_t) * (size_t)ctx->tile_pts;
         if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
-                                                                  ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->tol_alpha, ctx->tol_beta2,
+                                                                  ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->cen[0], ctx->cen[1], ctx->cen[2],
+                                                                  ctx->mp_cen[0], ctx->mp_cen[1], ctx->mp_cen[2], ctx->mp_abs[0], ctx->mp_abs[1], ctx->mp_abs[2],
                                                                   exact_only < 0 ? ctx->exact_only : exact_only, ctx->d_dt, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev, dmin32_dev, owners16_dev);

@@ -33,20 +33,21 @@ tg_ingest_scatter_kernel(int m, int R, const double *__restrict__ X, const doubl
                          const double *__restrict__ U, const int32_t *__restrict__ ray_orig, const int32_t *__restrict__ sray_off,
                          const int32_t *__restrict__ ray_off, double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                          float *__restrict__ pxf, float *__restrict__ pyf, float *__restrict__ pzf, int32_t *__restrict__ rayid,
-                         int32_t *__restrict__ point_orig, double *__restrict__ dt, unsigned long long *__restrict__ maxabs_bits) {
+                         int32_t *__restrict__ point_orig, double *__restrict__ dt, unsigned long long *__restrict__ range_bits /* [6]: ordered bits of lo x,y,z, hi x,y,z */) {
     const int rs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (rs >= R) return;
     const int i = ray_orig[rs];
     const int q0 = sray_off[rs], np = sray_off[rs + 1] - q0, o0 = ray_off[i];
     const double *x = X + (size_t)i * m, *y = Y + (size_t)i * m, *z = Z + (size_t)i * m, *u = U + (size_t)i * m;
-    double mx = 0.0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int k = lane; k < np; k += 32) {
         const double xa = x[k], ya = y[k], za = z[k];
         px[q0 + k] = xa; py[q0 + k] = ya; pz[q0 + k] = za;
         pxf[q0 + k] = (float)xa; pyf[q0 + k] = (float)ya; pzf[q0 + k] = (float)za;
         rayid[q0 + k] = rs;
         point_orig[q0 + k] = o0 + k;
-        mx = fmax(mx, fmax(fabs(xa), fmax(fabs(ya), fabs(za))));  // fmax ignores NaN
+        lo[0] = fmin(lo[0], xa); lo[1] = fmin(lo[1], ya); lo[2] = fmin(lo[2], za);  // fmin / fmax ignore NaN
+        hi[0] = fmax(hi[0], xa); hi[1] = fmax(hi[1], ya); hi[2] = fmax(hi[2], za);
         if (k < np - 1) {
             // load_data_Tonga.jl:66-69: rayl = sqrt(dx^2 + dy^2 + dz^2), rayu = 0.5 (U_k + U_k+1); MCsub.jl:153: rayl .* rayu
             const double dx = __dsub_rn(xa, x[k + 1]), dy = __dsub_rn(ya, y[k + 1]), dz = __dsub_rn(za, z[k + 1]);
@@ -55,8 +56,14 @@ tg_ingest_scatter_kernel(int m, int R, const double *__restrict__ X, const doubl
             dt[q0 + k] = __dmul_rn(rayl, rayu);
         }
     }
-    for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-    if (lane == 0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order like their bits
+    for (int a = 0; a < 3; a++) {
+        for (int s = 16; s > 0; s >>= 1) { lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], s)); hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], s)); }
+        if (lane == 0) {  // order-preserving map of doubles to unsigned integers
+            const unsigned long long bl = (unsigned long long)__double_as_longlong(lo[a]), bh = (unsigned long long)__double_as_longlong(hi[a]);
+            atomicMin(range_bits + a, bl ^ ((bl >> 63) ? ~0ull : 0x8000000000000000ull));
+            atomicMax(range_bits + 3 + a, bh ^ ((bh >> 63) ? ~0ull : 0x8000000000000000ull));
+        }
+    }
 }
 
 __global__ void tg_ingest_pad_kernel(int64_t P, int64_t Ppad, double *px, double *py, double *pz, float *pxf, float *pyf, float *pzf,
@@ -202,9 +209,10 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
     TG_CUDA(cudaMalloc((void **)&ctx->d_point_orig, 4 * (size_t)Ppad));
     TG_CUDA(cudaMalloc((void **)&ctx->d_dt, 8 * (size_t)(Ppad + max_npts + 128)));  // zero slack for unconditional batched loads
     TG_CUDA(cudaMemsetAsync(ctx->d_dt, 0, 8 * (size_t)(Ppad + max_npts + 128), s));
-    int rcs = tg::ensure_scratch(ctx, 8);
+    int rcs = tg::ensure_scratch(ctx, 48);
     if (rcs != TONGA_OK) return rcs;
-    TG_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 8, s));
+    TG_CUDA(cudaMemsetAsync(ctx->d_scratch, 0xFF, 24, s));             // lo: atomicMin from all ones
+    TG_CUDA(cudaMemsetAsync((char *)ctx->d_scratch + 24, 0, 24, s));  // hi: atomicMax from zero
     tg::tg_ingest_scatter_kernel<<<wgrid, 256, 0, s>>>(m, R, dX, dY, dZ, dU, ctx->d_ray_orig, ctx->d_ray_off, d_ray_off_orig, ctx->d_px, ctx->d_py,
                                                        ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->d_rayid, ctx->d_point_orig, ctx->d_dt,
                                                        (unsigned long long *)ctx->d_scratch);
@@ -215,15 +223,18 @@ extern "C" int tonga_create_from_points(tonga_ctx **out, int32_t m, int32_t R, c
         TG_CUDA(cudaGetLastError());
     }
     ctx->h_point_orig.resize(Ppad);
-    double M = 0.0;
+    unsigned long long rb[6];
     TG_CUDA(cudaMemcpyAsync(ctx->h_point_orig.data(), ctx->d_point_orig, 4 * (size_t)Ppad, cudaMemcpyDeviceToHost, s));
-    TG_CUDA(cudaMemcpyAsync(&M, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaMemcpyAsync(rb, ctx->d_scratch, 48, cudaMemcpyDeviceToHost, s));
     TG_CUDA(cudaStreamSynchronize(s));
-    for (double v : {params->xmin, params->xmax, params->ymin, params->ymax, params->zmin, params->zmax})
-        if (std::fabs(v) > M) M = std::fabs(v);
-    const double u = 5.9604644775390625e-08;  // the screening band of tonga_create
-    ctx->tol_alpha = (float)(16.0 * u);
-    ctx->tol_beta2 = (float)(2.0 * 12.0 * u * M * M * 1.0000002);
+    double lo[3], hi[3];
+    for (int a = 0; a < 6; a++) {
+        const unsigned long long b = rb[a] ^ ((rb[a] >> 63) ? 0x8000000000000000ull : ~0ull);
+        double v;
+        std::memcpy(&v, &b, 8);
+        (a < 3 ? lo[a] : hi[a - 3]) = v;
+    }
+    tg::set_screening_bounds(ctx, lo, hi);  // the bands of tonga_create
     g.armed = false;
     *out = ctx;
     return TONGA_OK;

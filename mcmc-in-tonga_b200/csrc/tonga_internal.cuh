@@ -234,6 +234,8 @@ struct tonga_ctx {
     float *d_pxf = nullptr, *d_pyf = nullptr, *d_pzf = nullptr; // [Ppad] fl32 copies for the FP32 screening pass
     int exact_only = 0;                                        // 1: full evaluate without FP32 screening (tonga_set_exact_only)
     float tol_alpha = 0.f, tol_beta2 = 0.f;                    // screening band: |dc - do| <= alpha*(dc+do) + beta2 -> exact FP64 recheck
+    double cen[3] = {0, 0, 0};                                 // centre of the nucleus box: origin of the full evaluate's screening arithmetic
+    float mp_cen[3] = {0, 0, 0}, mp_abs[3] = {0, 0, 0};        // per axis: max |p - cen| and max |p| over the ray points (its error band)
     // Internally rays are SORTED by length (descending); "flat point order" on the device is the CSR order of the sorted
     // rays.  ray_orig / point_orig map back to the caller's order at the API boundary.
     double *d_dt = nullptr;                                    // [Ppad] dt = rayL*rayU of the segment p -> p+1 (0.0 at the last point of a ray and in the padding)
@@ -263,6 +265,8 @@ struct tonga_ctx {
 };
 
 namespace tg {
+// screening bounds from the per-axis range [lo, hi] of the ray points and the nucleus box of ctx->prm (both creation paths)
+void set_screening_bounds(tonga_ctx *ctx, const double lo[3], const double hi[3]);
 int ensure_scratch(tonga_ctx *ctx, size_t bytes);
 int ensure_pinned(tonga_ctx *ctx, size_t bytes);
 // launches (all asynchronous on ctx->stream)
