@@ -640,7 +640,8 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     const size_t n = (size_t)ch->n, N = n * (size_t)nIter;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // resident sampler, mode 0: raw draws of one piece of the launch (64 B per chain-iteration, at most 256 MB)
-    const int64_t raw_iters = std::max<int64_t>(1, std::min<int64_t>(nIter, (int64_t)((256u << 20) / (64 * n))));
+    int64_t raw_iters = std::max<int64_t>(1, std::min<int64_t>(nIter, (int64_t)((256u << 20) / (64 * n))));
+    if (const char *e = std::getenv("TONGA_RAW_ITERS")) raw_iters = std::max<int64_t>(1, std::min<int64_t>(raw_iters, std::atoll(e)));  // tests: force the cut
     const size_t o_rec = 0, o_acc = o_rec + (recs ? al(sizeof(tonga_proposal) * N) : 0), o_phi = o_acc + (tr_accept ? al(N) : 0),
                  o_K = o_phi + (tr_phi ? al(8 * N) : 0), o_raw = o_K + (tr_K ? al(4 * N) : 0),
                  total = o_raw + ((!ch->wide && mode == 0) ? al(64 * n * (size_t)raw_iters) : 0);

@@ -463,8 +463,12 @@ def build_starting(TD_parameters: parameters, dataStruct: DataStruct, seed: int 
 
 def history_to_models(hist: dict, dataStruct: DataStruct, likelihood: float, reference_aliasing: bool = False):
     """Packed history -> Vector{Vector{Model}} as `plot_model_hist` consumes it (MCsub.jl:762-767).
-    reference_aliasing=True reproduces the stored action/accept of the reference (next iteration's action, accept = 0:
-    TD_inversion_function.jl:73-74 mutate the object already pushed at :280)."""
+    reference_aliasing=True APPROXIMATES the aliasing artefact of the reference's stored models: `push!(model_hist, model)`
+    (TD_inversion_function.jl:280) stores a reference, and :73-74 keep rewriting model.action / model.accept of that object on
+    every later iteration until an accepted proposal rebinds `model`.  The reference therefore stores the action of the first
+    later iteration whose proposal was accepted (and accept = 0); this flag stores the action of the NEXT iteration only
+    (the one value the device keeps, hist_next) and accept = 0 -- exact when that proposal is accepted, an approximation
+    otherwise.  Nuclei, zeta, phi and ptS are unaffected by the artefact."""
     out = []
     for c in range(len(hist["n_hist"])):
         ms = []

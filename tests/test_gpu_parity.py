@@ -1049,3 +1049,36 @@ def test_device_tempering_sweep_matches_the_numpy_mirror(tonga):
     ck = ch.checkpoint()
     assert np.array_equal(ck["beta"], beta)  # tempered batches resume with their temperatures
     ch.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_long_runs_are_cut_into_launches_without_a_trace(tonga, monkeypatch):
+    """The resident sampler pre-generates the raw draws of a launch and cuts long runs into pieces (256 MB of draws at most).
+    The pieces must be invisible: records, traces, history, counters and the final state equal the uncut run's bit for bit."""
+    from tonga_b200 import api
+    ds, p0 = tonga
+    import copy
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 120.0, 40.0, 7.0
+    ctx = api.Context(ds, p)
+    res = []
+    for cut in (None, "37"):
+        if cut is None:
+            monkeypatch.delenv("TONGA_RAW_ITERS", raising=False)
+        else:
+            monkeypatch.setenv("TONGA_RAW_ITERS", cut)
+        ch = api.Chains(ctx, 6, seed=77, hist_cap=16)
+        ch.build_starting()
+        out = ch.run(120, record=True, trace=True)
+        res.append((out, ch.state(), ch.history(), ch.stats(), ch.verify()))
+        ch.close()
+    (o0, s0, h0, t0, v0), (o1, s1, h1, t1, v1) = res
+    assert v0 == v1 == (0, 0.0, 0.0)
+    assert o0["recs"].tobytes() == o1["recs"].tobytes() and np.array_equal(o0["accept"], o1["accept"]) and o0["phi"].tobytes() == o1["phi"].tobytes()
+    assert np.array_equal(o0["K"], o1["K"]) and t0[0] == t1[0] and np.array_equal(t0[1], t1[1])
+    for k in ("K", "phi", "ptS"):
+        assert np.array_equal(s0[k], s1[k]), k
+    assert np.array_equal(h0["n_hist"], h1["n_hist"]) and (h0["n_hist"] == 11).all()
+    for k in ("K", "phi", "ptS", "iter", "action", "accept", "next_action"):
+        assert np.array_equal(h0[k], h1[k]), k
+    ctx.close()
