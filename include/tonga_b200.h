@@ -32,6 +32,7 @@ extern "C" {
 #define TONGA_ERR_CAPACITY (-3) /* model / shared-memory / history capacity exceeded                  */
 #define TONGA_ERR_STATE (-4)    /* call order (e.g. run before models were set)                       */
 #define TONGA_ERR_DATA (-5)     /* ray data on which the Julia code would throw (DimensionMismatch)   */
+#define TONGA_ERR_PEER (-6)     /* ray-sharded run: a peer rank did not publish its exchange in time  */
 
 typedef struct tonga_ctx tonga_ctx;       /* device-resident ray geometry + observations (one per GPU)        */
 typedef struct tonga_chains tonga_chains; /* a batch of independent RJ-MCMC chains resident on that GPU       */
@@ -180,6 +181,31 @@ int tonga_chains_temper_swap(tonga_chains *ch, int32_t n_all, const double *phi_
 int tonga_chains_temper_stats(tonga_chains *ch, int64_t *accepted, int64_t *attempted, int32_t reset);
 /* device pointers of the per-chain scalars phi / noise / beta ([nChains] doubles each) for zero-copy collectives */
 int tonga_chains_scalar_ptrs(tonga_chains *ch, void **phi, void **noise, void **beta);
+
+/* ---- ray sharding of a STREAMED batch over the GPUs of one node (BASELINE config 3; SURVEY 8e: the seam is evaluate's ray
+ * loop, MCsub.jl:142, and the one exchange per proposal is the sum over rays of the misfit, MCsub.jl:169-172).
+ * Rank `rank` of `world` (one process per GPU, every rank holding the same batch: same ray set, nChains, chain_id0, seed,
+ * start models) maintains the per-point state of a contiguous range of the sampler's ray tiles only (tonga_shard_range); the
+ * models, phi, t*, counters and the history are replicated: every rank draws the same proposals and takes the same decisions.
+ * Per proposal the candidate pass of a rank writes (t*, misfit term) of its rays into the exchange block of EVERY rank over
+ * peer memory (NVLink P2P stores issued by the kernel itself), raises its sequence flag there, and the accept kernel waits
+ * for all flags before it sums the terms in the canonical order -- so a sharded run is bit-identical to the unsharded one.
+ *   shard_init     allocates this rank's exchange block (a separate cudaMalloc, exportable with tonga_ipc_export) and returns it;
+ *   shard_connect  peer_bases[world]: device pointers, valid on THIS rank's device, of every rank's block (own entry ignored):
+ *                  tonga_ipc_open of the peers' handles, or plain pointers when the shards live in one process;
+ *   then build_starting / set_models / run / get_state / get_history as usual, called by all ranks with the same arguments
+ *   (tonga_chains_run returns TONGA_ERR_PEER if a peer fails to show up within TONGA_SHARD_TIMEOUT_MS, default 30000).
+ * get_state's owners are -2 outside the rank's own points; verify checks the own points (and all of t*, phi). */
+int tonga_chains_shard_init(tonga_chains *ch, int32_t rank, int32_t world, void **xch_base, uint64_t *xch_bytes);
+int tonga_chains_shard_connect(tonga_chains *ch, void *const *peer_bases);
+int tonga_chains_shard_info(const tonga_chains *ch, int32_t *rank, int32_t *world, int32_t *ray0, int32_t *ray1, int64_t *point0,
+                            int64_t *point1); /* own rays / points in the library's (length-sorted) order */
+/* own tiles [tile0, tile1) of rank `rank`: contiguous, disjoint, covering 0..n_tiles (host arithmetic only) */
+int tonga_shard_range(int32_t n_tiles, int32_t rank, int32_t world, int32_t *tile0, int32_t *tile1);
+/* CUDA IPC for hosts without another way to pass device pointers between the per-GPU processes: handle = 64 bytes */
+int tonga_ipc_export(const void *dev_ptr, unsigned char *handle);
+int tonga_ipc_open(int32_t device, const unsigned char *handle, void **dev_ptr);
+int tonga_ipc_close(int32_t device, void *dev_ptr);
 
 /* The proposal loop, TD_inversion_function.jl:70-302, nIter iterations for every chain, entirely on the device
  * (incremental Voronoi update, t* re-integration of touched rays, misfit, alpha, accept/reject, thinning).

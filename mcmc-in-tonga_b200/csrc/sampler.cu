@@ -95,14 +95,14 @@ __global__ void __launch_bounds__(1024) tg_order_kernel(int n, const int32_t *__
     for (int c = threadIdx.x; c < n; c += blockDim.x) perm[atomicAdd(&base[min(max(K[c], 0), 128)], 1)] = c;  // order inside a bin is irrelevant
 }
 
-__global__ void tg_verify_kernel(int n, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
+__global__ void tg_verify_kernel(int n, int64_t P0, int64_t P, int64_t Ppad, int R, int Rp, const int32_t *ray_orig, const uint8_t *own_a,
                                  const uint8_t *own_b, const uint16_t *own16_a, const uint16_t *own16_b, const double *ts_a /* [n][Rp] sorted rays */,
                                  const double *ts_b /* [n][R] caller's ray order */, const double *phi_a, const double *phi_b,
                                  const float *dc_a, const float *dc_b, float tol_alpha, float tol_beta2,
                                  unsigned long long *mism, double *maxd /* [2] as ordered uint64 bits */) {
     const int chain = blockIdx.y;
     unsigned long long local = 0;
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t p = P0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)  // [P0, P): a ray shard's own points
     {
         if (own16_a) local += own16_a[(size_t)chain * Ppad + p] != own16_b[(size_t)chain * Ppad + p];  // streamed sampler
         else local += own_a[(size_t)chain * Ppad + p] != own_b[(size_t)chain * Ppad + p];
@@ -266,6 +266,14 @@ struct tonga_chains {
     uint8_t *d_tile_changed = nullptr;  // [n][n_stiles]
     tg::Tile *d_stiles = nullptr;   // the streamed sampler's own tiles (whole rays, <= stile_pts points)
     int n_stiles = 0, stile_pts = 0;
+    std::vector<tg::Tile> h_stiles;
+    // ray sharding of the streamed sampler (tonga_chains_shard_init / _connect)
+    int sh_rank = 0, sh_world = 1, sh_tile0 = 0, sh_tile1 = 0;
+    bool sh_connected = false;
+    unsigned char *d_xch = nullptr;      // own exchange block: flags | err | term[2][n][Rp] | tsc[2][n][Rp]
+    size_t xch_bytes = 0, xch_hdr = 0;
+    unsigned char *sh_peer[tg::TG_MAX_SHARDS] = {};
+    unsigned long long sh_seq = 0;       // exchanges published so far
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
@@ -361,6 +369,8 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->stream_smem = stream_smem;
     ch->stile_pts = stile_pts;
     ch->n_stiles = (int)stiles.size();
+    ch->h_stiles = stiles;
+    ch->sh_tile1 = ch->n_stiles;
     ch->smem = wide ? 0 : smem_res;
     const size_t n = (size_t)nChains, KC = (size_t)ch->KC, R = (size_t)ctx->R, Rp = (size_t)ch->Rp, Pp = (size_t)ctx->Ppad, H = (size_t)hist_cap;
     TG_ALLOC(ch->d_K, 4 * n);
@@ -485,6 +495,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
         else cudaFree(p);
     }
     if (ch->d_prof) cudaFree(ch->d_prof);
+    if (ch->d_xch) cudaFree(ch->d_xch);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
     delete ch;
@@ -677,20 +688,46 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         sa.tstar = ch->d_tstar; sa.tstar_c = ch->d_tstar_c; sa.accept_flag = ch->d_accept;
         sa.tile_changed = ch->d_tile_changed; sa.active = ch->d_active; sa.n_active = ch->d_active + ch->n; sa.n_tiles = ch->n_stiles;
         sa.term_c = ch->d_term_c; sa.tS = ctx->d_tS; sa.sig = ctx->d_sig; sa.noise = ch->d_noise;
-        const dim3 sgrid((unsigned)((size_t)ch->n_stiles * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
+        const bool sharded = ch->streamed && ch->sh_world > 1;
+        if (sharded && !ch->sh_connected) return tg::fail(TONGA_ERR_STATE, "tonga_chains_run: ray-sharded batch is not connected (tonga_chains_shard_connect)");
+        tg::ShardArgs sh{};
+        sh.rank = 0; sh.world = 1; sh.tile0 = 0; sh.tile1 = ch->n_stiles;
+        const size_t xbuf = 8 * n * (size_t)ch->Rp;  // one (term or t*) buffer of one parity
+        if (sharded) {
+            sh.rank = ch->sh_rank; sh.world = ch->sh_world; sh.tile0 = ch->sh_tile0; sh.tile1 = ch->sh_tile1;
+            sh.flags = (unsigned long long *)ch->d_xch; sh.err = (int *)(ch->d_xch + 128 * (size_t)ch->sh_world);
+            double tmo = 30e3;
+            if (const char *e = std::getenv("TONGA_SHARD_TIMEOUT_MS")) tmo = std::max(1.0, std::atof(e));
+            sh.timeout_ns = (unsigned long long)(tmo * 1e6);
+            for (int g = 0; g < sh.world; g++) sh.peer_base[g] = ch->sh_peer[g];
+            TG_CUDA(cudaMemsetAsync(sh.err, 0, 4, s));
+        }
+        const dim3 sgrid((unsigned)((size_t)(sh.tile1 - sh.tile0) * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;
         for (int64_t it = 0; it < nIter; it++) {
             w.it = it; w.iter = ch->iter_done + 1 + it;
+            if (sharded) {  // this iteration's exchange: sequence number, parity buffers in every rank's block
+                sh.seq = ++ch->sh_seq;
+                const size_t par = (size_t)(sh.seq & 1ull);
+                for (int g = 0; g < sh.world; g++) {
+                    sh.peer_term[g] = (double *)(ch->sh_peer[g] + ch->xch_hdr + par * xbuf);
+                    sh.peer_tsc[g] = (double *)(ch->sh_peer[g] + ch->xch_hdr + (2 + par) * xbuf);
+                }
+                w.term_c = sa.term_c = sh.peer_term[sh.rank];
+                w.tstar_c = sa.tstar_c = sh.peer_tsc[sh.rank];
+            }
+            w.sh = sh; sa.sh = sh;
             if (ch->streamed) TG_CUDA(cudaMemsetAsync(ch->d_active + ch->n, 0, 4, s));
             tg::tg_wide_propose_kernel<<<ch->n, tg::WIDE_PROPOSE_THREADS, 0, s>>>(w);
             if (ch->streamed) {
-                tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
+                if (sgrid.x > 0) tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
+                if (sharded) tg::tg_shard_signal_kernel<<<1, 32, 0, s>>>(sh);
             } else if (!ctx->prm.debug_prior) {
                 rc = tg::launch_evaluate(ctx, ch->n, ch->KC, ch->d_Kc, ch->d_cells_c, nullptr, ch->d_ptS_tmp, nullptr, nullptr, nullptr, nullptr, false, nullptr, exact);
                 if (rc != TONGA_OK) return rc;
             }
             tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
-            if (ch->streamed) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
+            if (ch->streamed && sgrid.x > 0) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
         }
         TG_CUDA(cudaGetLastError());
     } else {
@@ -743,6 +780,92 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     if (tr_K) TG_CUDA(cudaMemcpyAsync(tr_K, d + o_K, 4 * N, cudaMemcpyDeviceToHost, s));
     TG_CUDA(cudaStreamSynchronize(s));
     TG_CUDA(cudaEventElapsedTime(&ch->last_ms, ch->ev0, ch->ev1));
+    if (ch->streamed && ch->sh_world > 1) {
+        int err = 0;
+        TG_CUDA(cudaMemcpy(&err, ch->d_xch + 128 * (size_t)ch->sh_world, 4, cudaMemcpyDeviceToHost));
+        if (err) return tg::fail(TONGA_ERR_PEER, "tonga_chains_run: a ray-shard peer did not publish its exchange in time (the ranks must call run with the same arguments); the batch's state is undefined");
+    }
+    return TONGA_OK;
+}
+
+// ---- ray sharding of the streamed sampler -------------------------------------------------------------------------------
+extern "C" int tonga_chains_shard_init(tonga_chains *ch, int32_t rank, int32_t world, void **xch_base, uint64_t *xch_bytes) {
+    if (!ch || world < 1 || world > tg::TG_MAX_SHARDS || rank < 0 || rank >= world) return tg::fail(TONGA_ERR_ARG, "tonga_chains_shard_init: bad argument (1 <= world <= 16)");
+    if (!ch->streamed) return tg::fail(TONGA_ERR_STATE, "tonga_chains_shard_init: ray sharding needs the STREAMED sampler");
+    if (ch->d_xch) return tg::fail(TONGA_ERR_STATE, "tonga_chains_shard_init: already initialised");
+    tonga_ctx *ctx = ch->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    // own tiles: a contiguous range, balanced by ray points (tiles hold whole rays; every tile is <= stile_pts points)
+    int t0 = 0, t1 = 0;
+    tonga_shard_range(ch->n_stiles, rank, world, &t0, &t1);
+    ch->sh_rank = rank; ch->sh_world = world; ch->sh_tile0 = t0; ch->sh_tile1 = t1;
+    ch->xch_hdr = (128 * (size_t)(world + 1) + 255) & ~(size_t)255;
+    ch->xch_bytes = ch->xch_hdr + 4 * 8 * (size_t)ch->n * (size_t)ch->Rp;
+    TG_CUDA(cudaMalloc((void **)&ch->d_xch, ch->xch_bytes));
+    TG_CUDA(cudaMemset(ch->d_xch, 0, ch->xch_bytes));
+    ch->sh_peer[rank] = ch->d_xch;
+    ch->sh_connected = (world == 1);
+    if (xch_base) *xch_base = ch->d_xch;
+    if (xch_bytes) *xch_bytes = ch->xch_bytes;
+    return TONGA_OK;
+}
+
+extern "C" int tonga_shard_range(int32_t n_tiles, int32_t rank, int32_t world, int32_t *tile0, int32_t *tile1) {
+    if (n_tiles < 0 || world < 1 || rank < 0 || rank >= world || !tile0 || !tile1) return tg::fail(TONGA_ERR_ARG, "tonga_shard_range: bad argument");
+    *tile0 = (int32_t)(((int64_t)n_tiles * rank) / world);
+    *tile1 = (int32_t)(((int64_t)n_tiles * (rank + 1)) / world);
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_shard_connect(tonga_chains *ch, void *const *peer_bases) {
+    if (!ch || !peer_bases) return tg::fail(TONGA_ERR_ARG, "tonga_chains_shard_connect: NULL");
+    if (!ch->d_xch) return tg::fail(TONGA_ERR_STATE, "tonga_chains_shard_connect: call tonga_chains_shard_init first");
+    std::lock_guard<std::mutex> lk(ch->ctx->mu);
+    for (int g = 0; g < ch->sh_world; g++) {
+        if (g == ch->sh_rank) continue;
+        if (!peer_bases[g]) return tg::fail(TONGA_ERR_ARG, "tonga_chains_shard_connect: NULL peer block");
+        ch->sh_peer[g] = (unsigned char *)peer_bases[g];
+    }
+    ch->sh_connected = true;
+    return TONGA_OK;
+}
+
+extern "C" int tonga_chains_shard_info(const tonga_chains *ch, int32_t *rank, int32_t *world, int32_t *ray0, int32_t *ray1, int64_t *point0, int64_t *point1) {
+    if (!ch) return tg::fail(TONGA_ERR_ARG, "tonga_chains_shard_info: NULL");
+    if (rank) *rank = ch->sh_rank;
+    if (world) *world = ch->sh_world;
+    const bool any = ch->streamed && ch->sh_tile1 > ch->sh_tile0;
+    const int r0 = !ch->streamed ? 0 : (any ? ch->h_stiles[ch->sh_tile0].r0 : 0), r1 = !ch->streamed ? ch->ctx->R : (any ? ch->h_stiles[ch->sh_tile1 - 1].r1 : 0);
+    const int64_t p0 = !ch->streamed ? 0 : (any ? ch->h_stiles[ch->sh_tile0].p0 : 0), p1 = !ch->streamed ? ch->ctx->P : (any ? ch->h_stiles[ch->sh_tile1 - 1].p1 : 0);
+    if (ray0) *ray0 = r0;
+    if (ray1) *ray1 = r1;
+    if (point0) *point0 = p0;
+    if (point1) *point1 = p1;
+    return TONGA_OK;
+}
+
+// CUDA IPC helpers for hosts that have no other way to exchange device pointers between the per-GPU processes
+extern "C" int tonga_ipc_export(const void *dev_ptr, unsigned char *handle /* [64] */) {
+    if (!dev_ptr || !handle) return tg::fail(TONGA_ERR_ARG, "tonga_ipc_export: NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    TG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    std::memcpy(handle, &h, 64);
+    return TONGA_OK;
+}
+extern "C" int tonga_ipc_open(int32_t device, const unsigned char *handle /* [64] */, void **dev_ptr) {
+    if (!handle || !dev_ptr) return tg::fail(TONGA_ERR_ARG, "tonga_ipc_open: NULL");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    TG_CUDA(cudaSetDevice(device));
+    TG_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TONGA_OK;
+}
+extern "C" int tonga_ipc_close(int32_t device, void *dev_ptr) {
+    if (!dev_ptr) return TONGA_OK;
+    TG_CUDA(cudaSetDevice(device));
+    TG_CUDA(cudaIpcCloseMemHandle(dev_ptr));
     return TONGA_OK;
 }
 
@@ -798,10 +921,13 @@ extern "C" int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K
     if (owners && ch->streamed) {
         std::vector<uint16_t> ho(n * Pp);
         TG_CUDA(cudaMemcpy(ho.data(), ch->d_owner16, 2 * n * Pp, cudaMemcpyDeviceToHost));
+        int64_t sp0 = 0, sp1 = (int64_t)P;
+        if (ch->sh_world > 1) tonga_chains_shard_info(ch, nullptr, nullptr, nullptr, nullptr, &sp0, &sp1);
         for (size_t i = 0; i < n; i++)
             for (size_t p = 0; p < P; p++) {
                 const uint16_t o = ho[i * Pp + p];
-                owners[i * P + (size_t)ctx->h_point_orig[p]] = (o == 0xFFFFu) ? -1 : (int32_t)o;
+                const bool mine = (int64_t)p >= sp0 && (int64_t)p < sp1;  // ray-sharded: -2 = a point of another rank's shard
+                owners[i * P + (size_t)ctx->h_point_orig[p]] = !mine ? -2 : ((o == 0xFFFFu) ? -1 : (int32_t)o);
             }
     } else if (owners && ch->wide) {  // no resident owner state: one forward model of the current models (caller's point order)
         int rc = tg::ensure_scratch(ctx, 4 * n * P);
@@ -944,7 +1070,9 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
     TG_CUDA(cudaMemsetAsync(ch->d_mism, 0, 8, s));
     TG_CUDA(cudaMemsetAsync(ch->d_maxd, 0, 16, s));
     dim3 grid(ch->streamed ? 64 : 8, ch->n);
-    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, (ch->wide && !ch->streamed) ? 0 : ctx->P, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp,
+    int64_t vp0 = 0, vp1 = (ch->wide && !ch->streamed) ? 0 : ctx->P;
+    if (ch->streamed && ch->sh_world > 1) tonga_chains_shard_info(ch, nullptr, nullptr, nullptr, nullptr, &vp0, &vp1);  // the per-point state of the other shards' points is not maintained here
+    tg::tg_verify_kernel<<<grid, 256, 0, s>>>(ch->n, vp0, vp1, ctx->Ppad, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_owner, ch->d_owner_tmp,
                                               ch->d_owner16, own16_tmp, ch->d_tstar, ch->d_ptS_tmp,
                                               ch->d_phi, ch->d_phi_tmp, ch->d_dcache, dc_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());

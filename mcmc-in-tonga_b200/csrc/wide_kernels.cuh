@@ -17,6 +17,60 @@
 
 namespace tg {
 
+// ---- ray sharding of the streamed sampler ("alternative for config 3": the seam is the ray loop MCsub.jl:142).
+// Rank g of `world` owns a contiguous range of the streamed sampler's tiles (whole rays) and keeps the per-point state of
+// those points only up to date; proposals, models, phi, t*, counters and history are replicated (every rank draws the same
+// Philox proposals and takes the same decisions).  The one exchange step per proposal -- t* and the misfit term of every ray
+// under the candidate models -- is fused into the candidate pass: the kernel stores each ray's (t*, term) into the exchange
+// block of EVERY rank over peer memory (NVLink P2P stores; plain stores for the own block), tg_shard_signal_kernel then
+// raises this rank's sequence flag in every rank's block, and the accept kernel waits until all ranks' flags have reached
+// the iteration's sequence number before it sums the terms in the canonical order.  Buffers alternate with the parity of
+// the sequence number: a rank can be at most one exchange ahead of the slowest one (it needs that rank's flag to pass its own
+// accept kernel), so the buffer being filled is never the one a slower rank still reads.
+constexpr int TG_MAX_SHARDS = 16;
+struct ShardArgs {
+    int rank, world;                  // world <= 1: not sharded
+    int tile0, tile1;                 // own tiles of the streamed sampler
+    unsigned long long seq;           // sequence number of this iteration's exchange (monotonic over the batch's lifetime)
+    unsigned long long timeout_ns;    // bound of the accept kernel's wait (a missing peer must not hang the GPU)
+    unsigned long long *flags;        // own exchange block: flags[16 * w] = last sequence number rank w has published
+    int *err;                         // own exchange block: set when a wait timed out
+    unsigned char *peer_base[TG_MAX_SHARDS];  // exchange blocks of all ranks (peer_base[rank] = own)
+    double *peer_tsc[TG_MAX_SHARDS];          // [n][Rp] candidate t* buffer of this parity in rank w's block
+    double *peer_term[TG_MAX_SHARDS];         // [n][Rp] candidate misfit terms, same
+};
+__device__ __forceinline__ unsigned long long tg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// every rank's flag in every rank's block: "my stores of exchange `seq` are performed" (stream order puts this kernel after the
+// candidate pass; the system-scope fence + release store make the pass's peer stores visible before the flag)
+__global__ void tg_shard_signal_kernel(const ShardArgs sh) {
+    __threadfence_system();
+    const int w = threadIdx.x;
+    if (w < sh.world) {
+        unsigned long long *f = reinterpret_cast<unsigned long long *>(sh.peer_base[w]) + 16 * sh.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sh.seq) : "memory");
+    }
+}
+// wait (threads 0..world-1 of the CTA, then a CTA barrier) until every rank has published exchange `seq`
+__device__ __forceinline__ void shard_wait(const ShardArgs &sh, int tid) {
+    if (sh.world <= 1) return;
+    if (tid < sh.world) {
+        const unsigned long long *f = sh.flags + 16 * tid;
+        const unsigned long long t0 = tg_globaltimer();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= sh.seq) break;
+            if (tg_globaltimer() - t0 > sh.timeout_ns) { atomicExch(sh.err, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+}
+
 struct WideArgs {
     tonga_params prm;
     int R, Rp, KC, mode, hist_cap;
@@ -43,6 +97,7 @@ struct WideArgs {
     int32_t *active;        // [n] chains whose candidate needs the point pass this iteration (any order)
     int32_t *n_active;      // [1], zeroed by the host before the propose kernel
     int32_t *accept_flag;   // [n]
+    ShardArgs sh;           // ray sharding (streamed sampler): the accept kernel waits for every rank's candidate pass
     // streams / traces
     const tonga_proposal *recs_in;
     tonga_proposal *recs_out;
@@ -124,6 +179,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
     const double *tc = a.ptS_c + (size_t)chain * R;        // wide: candidate t*, caller's ray order
     const double *tsc = a.tstar_c + (size_t)chain * a.Rp;  // streamed: candidate t*, sorted ray order
     int accepted = 0;
+    shard_wait(a.sh, tid);  // ray-sharded: (t*, term) of the other ranks' rays have arrived in this rank's exchange block
     if (do_eval) {
         double phin;
         if (pm.debug_prior) {
@@ -137,13 +193,13 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 for (; (c + 8) * TG_PHI_LANES <= R; c += 8) {  // 8 loads in flight, then the ordered adds (canonical phi order, phi_ray)
                     double v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = trm[phi_ray(c + u, tid)];
+                    for (int u = 0; u < 8; u++) v[u] = __ldcg(trm + phi_ray(c + u, tid));  // L2: peers write these rows
 #pragma unroll
                     for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
                 }
                 for (; c * TG_PHI_LANES < R; c++) {
                     const int r = phi_ray(c, tid);
-                    if (r < R) acc = __dadd_rn(acc, trm[r]);
+                    if (r < R) acc = __dadd_rn(acc, __ldcg(trm + r));
                 }
                 acc = warp_sum_canonical(acc);
                 if ((tid & 31) == 0) scratch[tid >> 5] = acc;
@@ -168,6 +224,8 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) cur[i] = cand[i];
                 if (!a.streamed && !pm.debug_prior)  // streamed: the commit pass copies t* tile by tile
                     for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tc[a.ray_orig[r]];
+                if (a.streamed && a.sh.world > 1)  // ray-sharded: t* is replicated, the commit pass only sees this rank's tiles
+                    for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = __ldcg(tsc + r);
             }
             phi = phin;
             if (act == 1) K += 1;
@@ -192,7 +250,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) hc[i] = cur[i];
             double *hp = a.hist_ptS + h * R;
             const double *tcur = (a.streamed && accepted && act != 5) ? tsc : ts;  // streamed: the commit pass has not copied t* yet
-            for (int i = tid; i < R; i += TG_PHI_LANES) hp[i] = tcur[a.ray_rank[i]];  // caller's ray order, contiguous stores
+            for (int i = tid; i < R; i += TG_PHI_LANES) hp[i] = __ldcg(tcur + a.ray_rank[i]);  // caller's ray order, contiguous stores
             if (tid == 0) {
                 a.hist_K[h] = K; a.hist_phi[h] = phi; a.hist_iter[h] = a.iter;
                 a.hist_action[h] = act; a.hist_accept[h] = accepted; a.hist_next[h] = 0;
@@ -251,6 +309,7 @@ struct StreamArgs {
     const int32_t *active, *n_active;  // chains with a candidate to process (tg_wide_propose_kernel)
     uint8_t *tile_changed;             // [n_chains][n_tiles]: the candidate pass found a point of the tile that changes owner (birth / move)
     int n_tiles;
+    ShardArgs sh;                      // ray sharding: the launch covers tiles [sh.tile0, sh.tile1); (t*, term) go to every rank's block
 };
 
 constexpr int STREAM_THREADS = 256;
@@ -270,7 +329,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     const int n_groups = (a.n_chains + STREAM_GROUP - 1) / STREAM_GROUP;
     const int grp = blockIdx.x % n_groups;
     if (grp * STREAM_GROUP >= n_active) return;
-    const Tile tile = a.tiles[blockIdx.x / n_groups];
+    const int tidx = a.sh.tile0 + blockIdx.x / n_groups;  // (tile0 = 0 unless ray-sharded)
+    const Tile tile = a.tiles[tidx];
     for (int ci = grp * STREAM_GROUP; ci < min(n_active, (grp + 1) * STREAM_GROUP); ci++) {
     __syncthreads();  // the previous chain's shared-memory state is free
     const int chain = a.active[ci];
@@ -281,9 +341,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     if (COMMIT) {  // the accepted candidate's t* becomes the chain's
         const double *tsc = a.tstar_c + (size_t)chain * a.Rp;
         double *ts = a.tstar + (size_t)chain * a.Rp;
-        for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) ts[r] = tsc[r];
+        if (a.sh.world <= 1)  // (ray-sharded: the accept kernel has copied the whole replicated row)
+            for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) ts[r] = tsc[r];
         if (act == 3) continue;  // change: no owner moves
-        if ((act == 1 || act == 4) && !a.tile_changed[(size_t)chain * a.n_tiles + blockIdx.x / n_groups]) continue;  // no point of this tile switches
+        if ((act == 1 || act == 4) && !a.tile_changed[(size_t)chain * a.n_tiles + tidx]) continue;  // no point of this tile switches
     }
     // shared layout: owner16[tile_pts] | changed bitmap [tile_pts/32] | queue u16[tile_pts] (orphans, then dirty rays) | counters
     const int cap = a.tile_pts + 8;  // the aligned groups may start up to 3 points before / end up to 3 points after the tile
@@ -480,7 +541,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
         int any = 0;
         for (int i = tid; i < cap / 32 + 1; i += STREAM_THREADS) any |= (s_chg[i] != 0u);
         any = __syncthreads_or(any | (act == 4 && s_cnt[0] > 0));  // orphans of a move always count (their owner distance changes)
-        if (tid == 0) a.tile_changed[(size_t)chain * a.n_tiles + blockIdx.x / n_groups] = (uint8_t)(any != 0);
+        if (tid == 0) a.tile_changed[(size_t)chain * a.n_tiles + tidx] = (uint8_t)(any != 0);
     }
     // ---- phase 2: t* of the tile's rays.  Rays without a changed point keep their t*; the others are listed and re-integrated
     // by the warps in the canonical order.
@@ -490,6 +551,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
     double *tsc = a.tstar_c + (size_t)chain * a.Rp;
     double *trm = a.term_c + (size_t)chain * a.Rp;
     const double nz = a.noise[chain];
+    // (t*, term) of a ray: own buffers, and -- ray-sharded -- the same row of every other rank's exchange block (P2P stores)
+    auto publish = [&](int r, double t, double term) {
+        tsc[r] = t; trm[r] = term;
+        for (int w = 0; w < a.sh.world; w++)
+            if (w != a.sh.rank) { a.sh.peer_tsc[w][(size_t)chain * a.Rp + r] = t; a.sh.peer_term[w][(size_t)chain * a.Rp + r] = term; }
+    };
     for (int r = tile.r0 + tid; r < tile.r1; r += STREAM_THREADS) {
         const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
         const int j0 = (int)(q0 - p0a), j1 = j0 + n;  // bit range [j0, j1) of the changed bitmap
@@ -501,7 +568,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
             dirty |= bits != 0u;
         }
         if (dirty) s_queue[atomicAdd(&s_cnt[1], 1)] = (uint16_t)(r - tile.r0);
-        else { const double t = ts[r]; tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
+        else { const double t = ts[r]; publish(r, t, misfit_term(t, a.tS[r], a.sig[r], nz)); }
     }
     __syncthreads();
     const int nd = s_cnt[1];
@@ -514,7 +581,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 5) tg_stream_kernel(const Stre
         const int trip = __reduce_max_sync(0xffffffffu, (nseg + 7) >> 3);
         const uint16_t *ow = s_owner + (q0 - p0a);
         const double t = tstar_g8(nseg, trip, lane & 7, [&](int j) { return seg_term(a.dt[q0 + j], zeta_of(ow[j]), zeta_of(ow[j + 1])); });
-        if (on && (lane & 7) == 0) { tsc[r] = t; trm[r] = misfit_term(t, a.tS[r], a.sig[r], nz); }
+        if (on && (lane & 7) == 0) publish(r, t, misfit_term(t, a.tS[r], a.sig[r], nz));
     }
     }
 }

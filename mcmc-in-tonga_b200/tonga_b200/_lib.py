@@ -69,6 +69,13 @@ SYMBOLS = {
     "tonga_chains_temper_swap": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_uint64]),
     "tonga_chains_temper_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
     "tonga_chains_scalar_ptrs": (C.c_int, [_P] + [c_vpp] * 3),
+    "tonga_chains_shard_init": (C.c_int, [_P, C.c_int32, C.c_int32, c_vpp, C.POINTER(C.c_uint64)]),
+    "tonga_chains_shard_connect": (C.c_int, [_P, c_vpp]),
+    "tonga_chains_shard_info": (C.c_int, [_P, c_ip, c_ip, c_ip, c_ip, c_lp, c_lp]),
+    "tonga_shard_range": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip]),
+    "tonga_ipc_export": (C.c_int, [_P, C.c_char_p]),
+    "tonga_ipc_open": (C.c_int, [C.c_int32, C.c_char_p, c_vpp]),
+    "tonga_ipc_close": (C.c_int, [C.c_int32, _P]),
     "tonga_chains_run": (C.c_int, [_P, C.c_int64, C.c_int32, _P, c_bp, c_dp, c_ip]),
     "tonga_chains_get_state": (C.c_int, [_P, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "tonga_chains_get_stats": (C.c_int, [_P, c_lp, c_lp]),

@@ -249,6 +249,26 @@ class Chains:
         check(self.lib.tonga_chains_scalar_ptrs(self._h, *[C.byref(q) for q in ptrs]))
         return {k: q.value for k, q in zip(("phi", "noise", "beta"), ptrs)}
 
+    # ---- ray sharding of a streamed batch (tonga_chains_shard_*; BASELINE config 3 on several GPUs)
+    def shard_init(self, rank: int, world: int):
+        """This rank's part of a ray-sharded batch: allocates the exchange block, returns (device pointer, bytes)."""
+        base, nbytes = C.c_void_p(), C.c_uint64()
+        check(self.lib.tonga_chains_shard_init(self._h, int(rank), int(world), C.byref(base), C.byref(nbytes)))
+        self.shard_rank, self.shard_world = int(rank), int(world)
+        return base.value, nbytes.value
+
+    def shard_connect(self, peer_bases):
+        """peer_bases[world]: device pointers (ints), valid on this rank's device, of every rank's exchange block."""
+        arr = (C.c_void_p * len(peer_bases))(*[C.c_void_p(int(b) if b else 0) for b in peer_bases])
+        check(self.lib.tonga_chains_shard_connect(self._h, arr))
+
+    def shard_info(self):
+        """dict(rank, world, ray0, ray1, point0, point1): the rank's own rays / points in the library's (length-sorted) order."""
+        r, w, r0, r1 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        p0, p1 = C.c_int64(), C.c_int64()
+        check(self.lib.tonga_chains_shard_info(self._h, C.byref(r), C.byref(w), C.byref(r0), C.byref(r1), C.byref(p0), C.byref(p1)))
+        return dict(rank=r.value, world=w.value, ray0=r0.value, ray1=r1.value, point0=p0.value, point1=p1.value)
+
     def run(self, n_iter: int, recs: np.ndarray | None = None, record: bool = False, trace: bool = False):
         """Generate mode (device Philox) unless `recs` ([n, n_iter] PROPOSAL_DTYPE) is given (replay).
         -> dict(recs (if record), accept, phi, K (if trace))."""

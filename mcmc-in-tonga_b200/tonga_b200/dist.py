@@ -140,3 +140,65 @@ def allreduce_sums(s1, s2, count, device=None, group=None):
     t = t.cpu().numpy()
     n = len(s1)
     return t[:n], t[n:2 * n], int(round(t[-1]))
+
+
+# ---------------------------------------------------------------------------------------------------- ray sharding (config 3)
+def shard_tiles(n_tiles: int, world: int, rank: int):
+    """Own tile range [t0, t1) of `rank` in a ray-sharded streamed batch (the library's tonga_shard_range: host arithmetic)."""
+    import ctypes as C
+    from . import _lib
+    t0, t1 = C.c_int32(), C.c_int32()
+    _lib.check(_lib.load().tonga_shard_range(int(n_tiles), int(rank), int(world), C.byref(t0), C.byref(t1)))
+    return t0.value, t1.value
+
+
+def exchange_handles(handle: bytes, group=None):
+    """All-gather one 64-byte CUDA IPC handle per rank -> list of `world` handles (works under gloo and NCCL)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    out = torch.empty(world * len(handle), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    flat = bytes(out.cpu().numpy().tobytes())
+    return [flat[i * len(handle):(i + 1) * len(handle)] for i in range(world)]
+
+
+def connect_ray_shards(chains, device: int, group=None):
+    """Turn `chains` (a STREAMED batch created identically on every rank of the process group) into this rank's part of a
+    ray-sharded batch: the ranks exchange the CUDA IPC handles of their exchange blocks (64 bytes each) and map each other's
+    blocks, so that the candidate pass can store its rays' (t*, misfit term) straight into every peer over NVLink."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    base, _ = chains.shard_init(rank, world)
+    h = C.create_string_buffer(64)
+    _lib.check(lib.tonga_ipc_export(C.c_void_p(base), h))
+    handles = exchange_handles(h.raw, group)
+    bases = []
+    for r in range(world):
+        if r == rank:
+            bases.append(base)
+            continue
+        q = C.c_void_p()
+        _lib.check(lib.tonga_ipc_open(int(device), handles[r], C.byref(q)))
+        bases.append(q.value)
+    chains.shard_connect(bases)
+    chains._shard_peer_maps = [(int(device), b) for r, b in enumerate(bases) if r != rank]  # closed by disconnect_ray_shards
+    dist.barrier(group)
+    return bases
+
+
+def disconnect_ray_shards(chains, group=None):
+    """Unmap the peers' exchange blocks (call on every rank before the batches are destroyed)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    dist.barrier(group)  # nobody is still storing into a block that is about to go away
+    for device, b in getattr(chains, "_shard_peer_maps", []):
+        _lib.check(lib.tonga_ipc_close(device, C.c_void_p(b)))
+    chains._shard_peer_maps = []

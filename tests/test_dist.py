@@ -117,3 +117,46 @@ def test_cross_rank_ladder_takes_the_single_rank_decisions():
     assert att == 3 * 128 + 3 * 127 and 0 < acc <= att
     for _rank, b, a, t in got:
         assert np.array_equal(b, beta) and (a, t) == (acc, att)
+
+
+# ---------------------------------------------------------------------------------------------------- ray sharding (config 3)
+def test_ray_shard_tile_ranges_partition_the_tiles():
+    """tonga_shard_range (host arithmetic of the C ABI): contiguous, disjoint, covering, sizes within one tile of each other."""
+    from tonga_b200.dist import shard_tiles
+    for n_tiles in (0, 1, 5, 17, 2441):
+        for w in (1, 2, 3, 8, 16):
+            rng = [shard_tiles(n_tiles, w, r) for r in range(w)]
+            assert rng[0][0] == 0 and rng[-1][1] == n_tiles
+            for (a0, a1), (b0, b1) in zip(rng, rng[1:]):
+                assert a1 == b0 and a0 <= a1
+            sizes = [b - a for a, b in rng]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _handle_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tonga_b200.dist import exchange_handles
+        mine = bytes((rank * 64 + i) % 251 for i in range(64))  # stands in for a cudaIpcMemHandle_t (64 opaque bytes)
+        q.put((rank, exchange_handles(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_over_gloo():
+    """connect_ray_shards' host half: every rank ends up with every rank's 64-byte handle, in rank order."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_handle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = [bytes((r * 64 + i) % 251 for i in range(64)) for r in range(world)]
+    for _rank, hs in got:
+        assert hs == want

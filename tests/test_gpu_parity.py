@@ -1082,3 +1082,99 @@ def test_long_runs_are_cut_into_launches_without_a_trace(tonga, monkeypatch):
     for k in ("K", "phi", "ptS", "iter", "action", "accept", "next_action"):
         assert np.array_equal(h0[k], h1[k]), k
     ctx.close()
+
+
+def _run_shards_in_threads(chs, n_iter, **kw):
+    """run() of every shard in its own host thread (the accept kernel of a shard waits for the other shards' candidate passes)."""
+    import threading
+    outs, errs = [None] * len(chs), [None] * len(chs)
+
+    def work(i):
+        try:
+            outs[i] = chs[i].run(n_iter, **kw)
+        except Exception as e:  # noqa: BLE001
+            errs[i] = e
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(chs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_ray_sharded_streamed_sampler_equals_unsharded(tonga, monkeypatch, world):
+    """BASELINE config 3's multi-GPU mode on one GPU: `world` ray shards of a STREAMED batch (own context and stream each, the
+    'peer' exchange blocks are plain device pointers here) run concurrently and exchange (t*, misfit term) of their rays per
+    proposal.  Every shard must reproduce the unsharded run bit for bit: proposals, decisions, phi, K, t*, history, counters;
+    the shards' own owners together are the unsharded owners."""
+    import copy
+    from tonga_b200.api import Chains, Context
+    monkeypatch.setenv("TONGA_STREAM_TILE", "1024")   # 381-ray Tonga: 17 tiles to share out
+    monkeypatch.setenv("TONGA_SHARD_TIMEOUT_MS", "20000")
+    ds, p0 = tonga
+    p = copy.copy(p0)
+    p.n_iter, p.burn_in, p.keep_each = 120.0, 40.0, 10.0
+    n = 6
+    ctx = Context(ds, p)
+    ref = Chains(ctx, n, chain_id0=3, seed=2024, sampler="streamed")
+    ref.build_starting()
+    o_ref = [ref.run(60, record=True, trace=True), ref.run(60, record=True, trace=True)]
+    s_ref, h_ref, t_ref = ref.state(want_owners=True), ref.history(), ref.stats()
+    assert ref.verify() == (0, 0.0, 0.0)
+    ctxs = [Context(ds, p) for _ in range(world)]
+    chs = [Chains(c, n, chain_id0=3, seed=2024, sampler="streamed") for c in ctxs]
+    bases = [ch.shard_init(r, world)[0] for r, ch in enumerate(chs)]
+    for ch in chs:
+        ch.shard_connect(bases)
+        ch.build_starting()
+    infos = [ch.shard_info() for ch in chs]
+    assert infos[0]["point0"] == 0 and infos[-1]["point1"] == ctx.P and all(a["point1"] == b["point0"] for a, b in zip(infos, infos[1:]))
+    o1 = _run_shards_in_threads(chs, 60, record=True, trace=True)
+    o2 = _run_shards_in_threads(chs, 60, record=True, trace=True)
+    owners = np.full_like(s_ref["owners"], -2)
+    for r, ch in enumerate(chs):
+        for o, orf in ((o1[r], o_ref[0]), (o2[r], o_ref[1])):
+            assert o["recs"].tobytes() == orf["recs"].tobytes() and np.array_equal(o["accept"], orf["accept"]) and np.array_equal(o["K"], orf["K"])
+            assert o["phi"].tobytes() == orf["phi"].tobytes(), "phi must be bit-identical: the terms of all rays are summed in the canonical order on every rank"
+        s, h, t = ch.state(want_owners=True), ch.history(), ch.stats()
+        assert np.array_equal(s["K"], s_ref["K"]) and s["phi"].tobytes() == s_ref["phi"].tobytes() and s["ptS"].tobytes() == s_ref["ptS"].tobytes()
+        assert s["cells"].tobytes() == s_ref["cells"].tobytes()
+        for key in ("n_hist", "K", "iter", "action", "accept", "next_action"):
+            assert np.array_equal(h[key], h_ref[key]), key
+        assert h["phi"].tobytes() == h_ref["phi"].tobytes() and h["ptS"].tobytes() == h_ref["ptS"].tobytes() and (h["n_hist"] == 8).all()
+        assert t[0] == t_ref[0] and np.array_equal(t[1], t_ref[1])
+        assert ch.verify() == (0, 0.0, 0.0)
+        mine = s["owners"] != -2
+        assert not (mine & (owners != -2)).any(), "every ray point belongs to exactly one shard"
+        owners[mine] = s["owners"][mine]
+    assert np.array_equal(owners, s_ref["owners"])
+    for ch in chs:
+        ch.close()
+    for c in ctxs:
+        c.close()
+    ref.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_ray_shard_peer_timeout_is_an_error_not_a_hang(tonga, monkeypatch):
+    """A shard whose peer never runs must come back with TONGA_ERR_PEER after the bounded wait."""
+    from tonga_b200._lib import TongaError
+    from tonga_b200.api import Chains, Context
+    monkeypatch.setenv("TONGA_SHARD_TIMEOUT_MS", "300")
+    ds, p = tonga
+    ctx = Context(ds, p)
+    a, b = Chains(ctx, 2, seed=1, sampler="streamed", hist_cap=0), Chains(ctx, 2, seed=1, sampler="streamed", hist_cap=0)
+    bases = [a.shard_init(0, 2)[0], b.shard_init(1, 2)[0]]
+    with pytest.raises(TongaError):
+        a.build_starting(); a.run(1)          # not connected yet
+    a.shard_connect(bases); b.shard_connect(bases)
+    a.build_starting()
+    with pytest.raises(TongaError) as e:
+        a.run(2)                              # b never publishes
+    assert e.value.code == -6
+    a.close(); b.close(); ctx.close()
