@@ -151,7 +151,7 @@ def algorithmic_work(counts, P, S, R):
 
 
 # ---------------------------------------------------------------------------------------------------- extra legs (B200 arm)
-def leg_config3(local_rank, peaks, fp64_peak, fp32_peak, R=100000, chains=64, iters=30):
+def leg_config3(local_rank, peaks, fp64_peak, fp32_peak, R=100000, chains=64, iters=30, world=1):
     """BASELINE config 3: synthetic 3-D model, 100k rays x ~200 points.  tS is synthesised on the GPU (forward model of a random
     200-nucleus model + noise); full evaluate at K = 100 / 500 / 2000; STREAMED sampler started at K = 1000."""
     import copy
@@ -209,7 +209,32 @@ def leg_config3(local_rank, peaks, fp64_peak, fp32_peak, R=100000, chains=64, it
                                     "note": "SURVEY 8(d) minimal bytes (2 B of owner state per point); the kernel's own 18 B/point layout moves "
                                             "%.0f GB/s" % (own_bytes / (ms * 1e-3) / 1e9)},
                        "verify": {"owner_mismatch": mm, "max_dphi": dphi, "max_dtstar": dts}}
+    st_un = ch.state(want_ptS=False)
     ch.close()
+    if world > 1:
+        # the SAME batch (same chains, seed, start models) ray-sharded over the ranks (SURVEY 8e alternative for config 3): every rank
+        # keeps the per-point state of its own ray tiles; (t*, misfit term) of its rays go to every rank's exchange block by P2P
+        # stores from inside the candidate pass (tonga_chains_shard_*; no NCCL on the data path).  Strong scaling of one batch.
+        import torch.distributed as dist
+        from tonga_b200.dist import connect_ray_shards, disconnect_ray_shards
+        chs = Chains(ctx, chains, seed=11, hist_cap=0, sampler="streamed")
+        connect_ray_shards(chs, local_rank)
+        chs.set_models(Kp, cp)
+        dist.barrier()
+        chs.run(3)
+        chs.reset()
+        dist.barrier()
+        chs.run(iters)
+        ms_s = chs.last_kernel_ms()
+        st_sh = chs.state(want_ptS=False)
+        mm, dphi, dts = chs.verify()
+        info = chs.shard_info()
+        out["ray_sharded"] = {"chains": chains, "iterations": iters, "ms_per_iteration_rank": ms_s / iters, "own_points": info["point1"] - info["point0"],
+                              "bit_identical_to_unsharded": bool(st_sh["phi"].tobytes() == st_un["phi"].tobytes() and np.array_equal(st_sh["K"], st_un["K"])
+                                                                 and st_sh["cells"].tobytes() == st_un["cells"].tobytes()),
+                              "verify_own_points": {"owner_mismatch": mm, "max_dphi": dphi, "max_dtstar": dts}}
+        disconnect_ray_shards(chs)
+        chs.close()
     ctx.close()
     return out
 
@@ -463,12 +488,21 @@ def main():
         fp64_peak, fp32_peak = ctx.peak_flops()
         c5 = leg_config5(ds, p, warm, local_rank, rank, world, iters=args.iters)
         c5_rate = float(n) * world * args.iters / (max_over_ranks(c5["ms"]) * 1e-3)
-        c3 = leg_config3(local_rank, peaks, fp64_peak, fp32_peak)
+        c3 = leg_config3(local_rank, peaks, fp64_peak, fp32_peak, world=world)
         c3_ms = max_over_ranks(c3["streamed"]["ms_per_iteration"])
+        if world > 1:
+            rs_ms = max_over_ranks(c3["ray_sharded"]["ms_per_iteration_rank"])
+            rs_ok = max_over_ranks(0.0 if c3["ray_sharded"]["bit_identical_to_unsharded"] else 1.0) == 0.0
         if rank == 0:
             c5["proposals_per_s"] = c5_rate
             c3["streamed"]["proposals_per_s_all_gpus"] = c3["streamed"]["chains"] * world / c3_ms * 1e3
             c3["streamed"]["parallelism"] = f"chain-sharded x{world} ({c3['streamed']['chains']} chains per GPU, ray set replicated)"
+            if world > 1:
+                rs = c3["ray_sharded"]
+                rs.update({"ms_per_iteration": rs_ms, "proposals_per_s": rs["chains"] / rs_ms * 1e3, "bit_identical_to_unsharded_all_ranks": rs_ok,
+                           "speedup_vs_one_gpu": c3["streamed"]["ms_per_iteration"] / rs_ms,
+                           "parallelism": f"ray-sharded x{world}: ONE batch of {rs['chains']} chains, per-point state split by ray tiles, "
+                                          "(t*, term) exchanged per proposal by P2P stores fused into the candidate pass"})
             out["config5"], out["config3"] = c5, c3
     if rank == 0:
         if not args.no_cpu_baseline:
