@@ -4,6 +4,9 @@ Bars (BASELINE.json north_star): cell indices bit-exact; t* and phi within 1e-9 
 decisions identical on replayed proposal streams.  The oracle sums t*/phi left to right, the device uses its
 canonical tree order, hence a tolerance on the sums (never on the indices).
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 
