@@ -31,6 +31,7 @@ constexpr int NW = TG_PHI_WARPS;  // warps per chain CTA
 
 #include "sampler_kernel.cuh"
 #include "wide_kernels.cuh"
+#include "stream_cull.cuh"
 
 namespace tg {
 
@@ -274,6 +275,16 @@ struct tonga_chains {
     size_t xch_bytes = 0, xch_hdr = 0;
     unsigned char *sh_peer[tg::TG_MAX_SHARDS] = {};
     unsigned long long sh_seq = 0;       // exchanges published so far
+    // streamed sampler with spatial culling (stream_cull.cuh)
+    bool culled = false;
+    int s2_maxn = 0;
+    size_t s2_smem = 0;
+    float4 *d_sub = nullptr;         // bounding spheres of the 32-point runs
+    int32_t *d_sub_off = nullptr;    // [R+1]
+    float *d_dmax = nullptr;         // [n][Rp]
+    double *d_term = nullptr;        // [n][Rp]
+    int32_t *d_cand = nullptr, *d_ncand = nullptr, *d_dirty = nullptr, *d_ndirty = nullptr, *d_work_off = nullptr;
+    uint8_t *d_cand_changed = nullptr;
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
@@ -409,6 +420,39 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
             TG_CUDA(cudaFuncSetAttribute(tg::tg_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
             TG_CUDA(cudaFuncSetAttribute(tg::tg_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
         }
+        // spatial culling (stream_cull.cuh): one warp per candidate ray; needs a ray's owners in the warp's shared memory
+        ch->s2_maxn = ((ctx->max_npts + 8 + 31) / 32) * 32;
+        ch->s2_smem = (size_t)tg::S2_WARPS * ((tg::s2_warp_smem(ch->s2_maxn) + 15) & ~(size_t)15);
+        const char *ce = std::getenv("TONGA_STREAM_CULL");
+        ch->culled = !(ce && ce[0] == '0') && ch->s2_smem <= std::min<size_t>(ctx->smem_optin, 56 * 1024);
+        if (ch->culled) {
+            const int R = ctx->R;
+            std::vector<int32_t> so(R + 1, 0);  // 32-point runs per (sorted) ray
+            for (int rs = 0; rs < R; rs++) {
+                const int npt = ctx->h_ray_off[ctx->h_ray_orig[rs] + 1] - ctx->h_ray_off[ctx->h_ray_orig[rs]];
+                so[rs + 1] = so[rs] + (npt + 31) / 32;
+            }
+            TG_ALLOC(ch->d_sub_off, 4 * (size_t)(R + 1));
+            TG_ALLOC(ch->d_sub, sizeof(float4) * (size_t)std::max(so[R], 1));
+            TG_CUDA(cudaMemcpyAsync(ch->d_sub_off, so.data(), 4 * (size_t)(R + 1), cudaMemcpyHostToDevice, ctx->stream));
+            tg::tg_sub_spheres_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(R, ctx->d_ray_off, ch->d_sub_off, ctx->d_px, ctx->d_py, ctx->d_pz, ch->d_sub);
+            TG_CUDA(cudaGetLastError());
+            TG_CUDA(cudaStreamSynchronize(ctx->stream));  // `so` is a local
+            TG_ALLOC(ch->d_dmax, 4 * n * Rp);
+            TG_ALLOC(ch->d_term, 8 * n * Rp);
+            TG_ALLOC(ch->d_cand, 4 * n * R);
+            TG_ALLOC(ch->d_dirty, 4 * n * R);
+            TG_ALLOC(ch->d_cand_changed, n * R);
+            TG_ALLOC(ch->d_ncand, 4 * n);
+            TG_ALLOC(ch->d_ndirty, 4 * n);
+            TG_ALLOC(ch->d_work_off, 4 * (n + 1));
+            TG_CUDA(cudaMemsetAsync(ch->d_ncand, 0, 4 * n, ctx->stream));
+            TG_CUDA(cudaMemsetAsync(ch->d_ndirty, 0, 4 * n, ctx->stream));
+            if (ch->s2_smem > 48 * 1024) {
+                TG_CUDA(cudaFuncSetAttribute(tg::tg_stream2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->s2_smem));
+                TG_CUDA(cudaFuncSetAttribute(tg::tg_stream2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->s2_smem));
+            }
+        }
     }
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
@@ -496,6 +540,8 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     }
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->d_xch) cudaFree(ch->d_xch);
+    void *cull[] = {ch->d_sub, ch->d_sub_off, ch->d_dmax, ch->d_term, ch->d_cand, ch->d_ncand, ch->d_dirty, ch->d_ndirty, ch->d_work_off, ch->d_cand_changed};
+    for (void *p : cull) cudaFree(p);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
     delete ch;
@@ -510,6 +556,12 @@ static int establish_state(tonga_chains *ch) {
     const size_t tot = (size_t)ch->n * ch->Rp;
     tg::tg_copy_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_ptS_tmp, ch->d_tstar);
     TG_CUDA(cudaGetLastError());
+    if (ch->culled) {  // culling state of the streamed sampler: dmax per ray, misfit terms; tstar_c = t*, term_c = term
+        tg::tg_stream_init_kernel<<<dim3((unsigned)((ctx->R + 7) / 8), (unsigned)ch->n), 256, 0, ctx->stream>>>(ctx->R, ch->Rp, ctx->Ppad, ctx->d_ray_off, ch->d_dcache, ch->d_tstar,
+                                                                                                      ctx->d_tS, ctx->d_sig, ch->d_noise, ch->d_dmax, ch->d_term,
+                                                                                                      ch->d_tstar_c, ch->d_term_c);
+        TG_CUDA(cudaGetLastError());
+    }
     ch->have_models = true;
     return TONGA_OK;
 }
@@ -702,6 +754,16 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             for (int g = 0; g < sh.world; g++) sh.peer_base[g] = ch->sh_peer[g];
             TG_CUDA(cudaMemsetAsync(sh.err, 0, 4, s));
         }
+        const bool culled = ch->streamed && ch->culled && !sharded;
+        tg::CullArgs ca{};
+        if (culled) {
+            ca.sub = ch->d_sub; ca.sub_off = ch->d_sub_off; ca.cells = ch->d_cells; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
+            ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.cand_changed = ch->d_cand_changed; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
+            ca.work_off = ch->d_work_off; ca.R = ctx->R; ca.ray0 = 0; ca.ray1 = ctx->R; ca.maxn = ch->s2_maxn; ca.p0 = 0; ca.p1 = ctx->Ppad;
+            w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;
+        }
+        const dim3 cgrid((unsigned)((ctx->R + tg::CULL_THREADS - 1) / tg::CULL_THREADS), (unsigned)ch->n);
+        const unsigned s2grid = (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 4u;
         const dim3 sgrid((unsigned)((size_t)(sh.tile1 - sh.tile0) * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;
         for (int64_t it = 0; it < nIter; it++) {
@@ -719,7 +781,12 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             w.sh = sh; sa.sh = sh;
             if (ch->streamed) TG_CUDA(cudaMemsetAsync(ch->d_active + ch->n, 0, 4, s));
             tg::tg_wide_propose_kernel<<<ch->n, tg::WIDE_PROPOSE_THREADS, 0, s>>>(w);
-            if (ch->streamed) {
+            if (culled) {
+                ca.s = sa;
+                tg::tg_cull_kernel<<<cgrid, tg::CULL_THREADS, 0, s>>>(ca);
+                tg::tg_cull_prefix_kernel<<<1, 1024, 0, s>>>(ch->d_active, ch->d_active + ch->n, ch->d_ncand, ch->d_work_off);
+                tg::tg_stream2_kernel<false><<<s2grid, tg::S2_THREADS, ch->s2_smem, s>>>(ca);
+            } else if (ch->streamed) {
                 if (sgrid.x > 0) tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
                 if (sharded) tg::tg_shard_signal_kernel<<<1, 32, 0, s>>>(sh);
             } else if (!ctx->prm.debug_prior) {
@@ -727,7 +794,10 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
                 if (rc != TONGA_OK) return rc;
             }
             tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
-            if (ch->streamed && sgrid.x > 0) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
+            if (culled) {
+                tg::tg_stream2_kernel<true><<<s2grid, tg::S2_THREADS, ch->s2_smem, s>>>(ca);
+                tg::tg_renumber_kernel<<<dim3(128, (unsigned)ch->n), 256, 0, s>>>(ca);
+            } else if (ch->streamed && sgrid.x > 0) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
         }
         TG_CUDA(cudaGetLastError());
     } else {
@@ -1076,6 +1146,12 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
                                               ch->d_owner16, own16_tmp, ch->d_tstar, ch->d_ptS_tmp,
                                               ch->d_phi, ch->d_phi_tmp, ch->d_dcache, dc_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
+    if (ch->culled && ch->sh_world <= 1) {  // the culling state must be consistent with the chain state (violations count as mismatches)
+        tg::tg_stream_check_kernel<<<dim3((unsigned)((ctx->R + 7) / 8), (unsigned)ch->n), 256, 0, s>>>(ctx->R, ch->Rp, ctx->Ppad, 0, ctx->R, ctx->d_ray_off, ch->d_dcache, ch->d_tstar,
+                                                                                             ctx->d_tS, ctx->d_sig, ch->d_noise, ch->d_dmax, ch->d_term, ch->d_tstar_c,
+                                                                                             ch->d_term_c, ch->d_mism);
+        TG_CUDA(cudaGetLastError());
+    }
     unsigned long long mm = 0;
     double md[2] = {0, 0};
     TG_CUDA(cudaMemcpyAsync(&mm, ch->d_mism, 8, cudaMemcpyDeviceToHost, s));

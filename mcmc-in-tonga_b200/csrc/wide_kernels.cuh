@@ -98,6 +98,11 @@ struct WideArgs {
     int32_t *n_active;      // [1], zeroed by the host before the propose kernel
     int32_t *accept_flag;   // [n]
     ShardArgs sh;           // ray sharding (streamed sampler): the accept kernel waits for every rank's candidate pass
+    // streamed sampler with culling (stream_cull.cuh): per-chain candidate / dirty ray lists, misfit terms of the current state
+    int culled;
+    int32_t *ncand, *ndirty;   // [n], zeroed by the propose kernel
+    const int32_t *dirty;      // [n][R]
+    double *term;              // [n][Rp]
     // streams / traces
     const tonga_proposal *recs_in;
     tonga_proposal *recs_out;
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
             }
             const int ps = a.pending_slot[chain];
             if (ps >= 0) { a.hist_next[(size_t)chain * a.hist_cap + ps] = pr.action; a.pending_slot[chain] = -1; }
+            if (a.culled) { a.ncand[chain] = 0; a.ndirty[chain] = 0; }
         }
     }
     __syncthreads();
@@ -231,6 +237,26 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
             if (act == 1) K += 1;
             else if (act == 2) K -= 1;
             else if (act == 5) noise = pr.zeta;
+        }
+        if (a.culled) {
+            // the candidate pass changed tstar_c / term_c for the DIRTY rays only: commit them to the chain's t* / term, or restore
+            // them (invariant between iterations: tstar_c == t*, term_c == term)
+            double *tsc_w = a.tstar_c + (size_t)chain * a.Rp, *trm_w = const_cast<double *>(a.term_c) + (size_t)chain * a.Rp;
+            double *trm_cur = a.term + (size_t)chain * a.Rp;
+            if (act != 5) {
+                const int nd = a.ndirty[chain];
+                const int32_t *dl = a.dirty + (size_t)chain * R;
+                for (int d = tid; d < nd; d += TG_PHI_LANES) {
+                    const int r = dl[d];
+                    if (accepted) { ts[r] = tsc_w[r]; trm_cur[r] = trm_w[r]; }
+                    else { tsc_w[r] = ts[r]; trm_w[r] = trm_cur[r]; }
+                }
+            } else if (accepted) {  // the noise level changed: every term does
+                for (int r = tid; r < R; r += TG_PHI_LANES) {
+                    const double v = misfit_term(ts[r], a.tS[r], a.sig[r], noise);
+                    trm_cur[r] = v; trm_w[r] = v;
+                }
+            }
         }
     }
     // bookkeeping, traces, thinning (:275-281) -- as step G of the resident sampler
