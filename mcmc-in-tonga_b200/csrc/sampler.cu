@@ -757,7 +757,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         const bool culled = ch->streamed && ch->culled && !sharded;
         tg::CullArgs ca{};
         if (culled) {
-            ca.sub = ch->d_sub; ca.sub_off = ch->d_sub_off; ca.cells = ch->d_cells; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
+            ca.sub = ch->d_sub; ca.sub_off = ch->d_sub_off; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
             ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.cand_changed = ch->d_cand_changed; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
             ca.work_off = ch->d_work_off; ca.R = ctx->R; ca.ray0 = 0; ca.ray1 = ctx->R; ca.maxn = ch->s2_maxn; ca.p0 = 0; ca.p1 = ctx->Ppad;
             w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;

@@ -27,7 +27,6 @@ struct CullArgs {
     StreamArgs s;            // geometry, candidate models, chain state (tiles unused)
     const float4 *sub;       // bounding sphere (centre, radius) of every 32-point run, rays in sorted order
     const int32_t *sub_off;  // [R+1]
-    const double *cells;     // current models [n][4][KC] (position of nucleus idx for death / change / the old position of a move)
     float *dmax;             // [n][Rp]
     double *term;            // [n][Rp] misfit term of the chain's current t* (what term_c is restored to)
     int32_t *cand;           // [n][R] candidate rays of this proposal
@@ -44,8 +43,9 @@ struct CullArgs {
 constexpr int CULL_THREADS = 256;
 constexpr int S2_THREADS = 256;
 constexpr int S2_WARPS = S2_THREADS / 32;
-__host__ __device__ inline size_t s2_warp_smem(int maxn) {  // owner16[maxn] | queue16[maxn] | chg32[maxn/32 + 1] | cnt[2]
-    return (size_t)maxn * 4 + (size_t)(maxn / 32 + 1) * 4 + 8;
+constexpr int S2_LIST = 256;  // nuclei near the killed / moved nucleus that an orphan is rescanned against (else: all)
+__host__ __device__ inline size_t s2_warp_smem(int maxn) {  // owner16[maxn] | queue16[maxn] | list16[S2_LIST] | chg32[maxn/32 + 1] | cnt[2]
+    return (size_t)maxn * 4 + (size_t)S2_LIST * 2 + (size_t)(maxn / 32 + 1) * 4 + 8;
 }
 
 // ---- static geometry: bounding spheres of the 32-point runs (one thread per ray) ---------------------------------------------
@@ -116,11 +116,7 @@ __global__ void __launch_bounds__(CULL_THREADS) tg_cull_kernel(const CullArgs a)
     if (r < a.ray1) {
         const bool has_new = (act == 1 || act == 4), has_old = (act == 2 || act == 3 || act == 4);
         const float nx = (float)pr.x, ny = (float)pr.y, nz = (float)pr.z;
-        float ox = 0.f, oy = 0.f, oz = 0.f;
-        if (has_old) {
-            const double *cur = a.cells + (size_t)chain * 4 * a.s.KC;
-            ox = (float)cur[pr.idx]; oy = (float)cur[a.s.KC + pr.idx]; oz = (float)cur[2 * a.s.KC + pr.idx];
-        }
+        const float ox = (float)pr.ox, oy = (float)pr.oy, oz = (float)pr.oz;  // killed / changed nucleus, old position of a moved one
         const float dm = a.dmax[(size_t)chain * a.s.Rp + r] * 1.0001f;
         for (int s = a.sub_off[r]; s < a.sub_off[r + 1] && !cand; s++) {
             const float4 sp = __ldg(a.sub + s);
@@ -180,7 +176,8 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
     unsigned char *wbase = smem_raw + (size_t)warp * ((s2_warp_smem(ca.maxn) + 15) & ~(size_t)15);
     uint16_t *s_owner = reinterpret_cast<uint16_t *>(wbase);
     uint16_t *s_queue = s_owner + ca.maxn;
-    uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_queue + ca.maxn);
+    uint16_t *s_list = s_queue + ca.maxn;
+    uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_list + S2_LIST);
     int *s_cnt = reinterpret_cast<int *>(s_chg + ca.maxn / 32 + 1);
     const float ta = a.tol_alpha, tb = a.tol_beta2;
 
@@ -307,71 +304,82 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
         else if (act == 2) phase1(std::integral_constant<int, 2>{});
         else phase1(std::integral_constant<int, 3>{});
         __syncwarp();
-        // ---- orphans (death / move): nearest nucleus of the candidate model; the lanes split the nuclei
+        // ---- orphans (death / move): nearest nucleus of the candidate model, ONE LANE PER ORPHAN.  The new owner of a point of
+        // the killed / moved nucleus k is a Voronoi neighbour of k: with r = |p - k| <= sqrt(dmax of the ray) and delta = distance
+        // from k to its nearest other nucleus j0, |p - j*| <= |p - j0| <= r + delta, hence |k - j*| <= 2 r + delta.  The warp lists
+        // the nuclei inside that radius (grown by 0.1 % + 1 km, far more than the screening band) once per ray -- ascending, so the
+        // lowest index still wins exact ties -- and every orphan scans the list only; a moved nucleus is always listed.
         const int nq = s_cnt[0];
-        for (int e = 0; e < nq; e++) {
-            const int j = s_queue[e];
-            const long long p = p0a + j;
-            int bi = -2;
-            float dbest = 1e9f;
-            if (!a.exact_only) {
-                const float x = a.pxf[p], y = a.pyf[p], z = a.pzf[p];
-                float d1 = 1e9f, d2 = 1e9f;
-                int i1 = -1;
-                for (int i = 4 * lane; i < Kn; i += 128) {
-                    const float4 fx = __ldg(reinterpret_cast<const float4 *>(cf + i)), fy = __ldg(reinterpret_cast<const float4 *>(cf + a.KC + i)),
-                                 fz = __ldg(reinterpret_cast<const float4 *>(cf + 2 * a.KC + i));
-                    const float d[4] = {dist2_f32(fx.x, fy.x, fz.x, x, y, z), dist2_f32(fx.y, fy.y, fz.y, x, y, z), dist2_f32(fx.z, fy.z, fz.z, x, y, z),
-                                        dist2_f32(fx.w, fy.w, fz.w, x, y, z)};
+        if (nq > 0) {
+            const float kx = (float)pr.ox, ky = (float)pr.oy, kz = (float)pr.oz;  // k before the proposal (the commit pass runs after the model was committed)
+            const float rmax = sqrtf(ca.dmax[(size_t)chain * a.Rp + r] * 1.0001f);
+            float dl2 = 3.0e38f;
+            for (int j = lane; j < Kn; j += 32) {
+                const float d = dist2_f32(cf[j], cf[a.KC + j], cf[2 * a.KC + j], kx, ky, kz);
+                if (!(act == 4 && j == idx)) dl2 = fminf(dl2, d);
+            }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const bool lt = d[u] < d1;
-                        d2 = lt ? d1 : fminf(d2, d[u]);
-                        i1 = lt ? i + u : i1;
-                        d1 = lt ? d[u] : d1;
+            for (int o = 16; o > 0; o >>= 1) dl2 = fminf(dl2, __shfl_xor_sync(FULL, dl2, o));
+            const float rho = (2.0f * rmax + sqrtf(dl2)) * 1.001f + 1.0f, rho2 = rho * rho;
+            int nl = 0;
+            for (int j0 = 0; j0 < Kn && nl <= S2_LIST; j0 += 32) {
+                const int j = j0 + lane;
+                const bool in = j < Kn && ((act == 4 && j == idx) || !(dist2_f32(cf[j], cf[a.KC + j], cf[2 * a.KC + j], kx, ky, kz) > rho2));
+                const uint32_t m = __ballot_sync(FULL, in);
+                const int pos = nl + __popc(m & ((1u << lane) - 1u));
+                if (in && pos < S2_LIST) s_list[pos] = (uint16_t)j;
+                nl += __popc(m);
+            }
+            const bool all = nl > S2_LIST || !(rho2 < 3.0e38f);  // too many (or no bound): scan every nucleus
+            const int nn = all ? Kn : nl;
+            __syncwarp();
+            for (int e0 = 0; e0 < nq; e0 += 32) {
+                const int e = e0 + lane;
+                const bool on = e < nq;
+                const int j = on ? (int)s_queue[e] : 0;
+                const long long p = p0a + j;
+                int bi = -2;
+                float dbest = 1e9f;
+                if (on && !a.exact_only) {
+                    const float x = a.pxf[p], y = a.pyf[p], z = a.pzf[p];
+                    float d1 = 1e9f, d2 = 1e9f;
+                    int i1 = -1;
+                    for (int i = 0; i < nn; i++) {
+                        const int jj = all ? i : (int)s_list[i];
+                        const float d = dist2_f32(__ldg(cf + jj), __ldg(cf + a.KC + jj), __ldg(cf + 2 * a.KC + jj), x, y, z);
+                        const bool lt = d < d1;
+                        d2 = lt ? d1 : fminf(d2, d);
+                        i1 = lt ? jj : i1;
+                        d1 = lt ? d : d1;
+                    }
+                    dbest = d1;
+                    const float tol = fmaf(ta, d1 + d2, tb);
+                    if (d2 - d1 > tol) bi = i1;
+                }
+                if (on && bi == -2) {  // exact FP64; ascending indices, strict <: the lowest index wins ties (MCsub.jl:255)
+                    const double x = a.px[p], y = a.py[p], z = a.pz[p];
+                    double best = 1e9;
+                    int b = -1;
+                    for (int i = 0; i < nn; i++) {
+                        const int jj = all ? i : (int)s_list[i];
+                        const double d = dist2_exact(cc[jj], cc[a.KC + jj], cc[2 * a.KC + jj], x, y, z);
+                        if (d < best) { best = d; b = jj; }
+                    }
+                    bi = b;
+                    dbest = (float)best;
+                }
+                if (on) {
+                    if (COMMIT) {
+                        dmx = fmaxf(dmx, bi < 0 ? 1e9f : dbest);
+                        // a death's owners stay in the OLD numbering here: tg_renumber_kernel shifts every owner above the killed index afterwards
+                        const int bo = (act == 2 && bi >= idx) ? bi + 1 : bi;
+                        own[p] = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bo;
+                        dc[p] = bi < 0 ? 1e9f : dbest;
+                    } else {
+                        s_owner[j] = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bi;
+                        if (act == 2 || bi != idx) atomicOr(&s_chg[j >> 5], 1u << (j & 31));  // a point that stays with the moved nucleus keeps its zeta
                     }
                 }
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) {
-                    const float e1 = __shfl_xor_sync(FULL, d1, m), e2 = __shfl_xor_sync(FULL, d2, m);
-                    const int ei = __shfl_xor_sync(FULL, i1, m);
-                    const bool lt = e1 < d1;
-                    d2 = fminf(fminf(d2, e2), lt ? d1 : e1);
-                    i1 = lt ? ei : i1;
-                    d1 = lt ? e1 : d1;
-                }
-                dbest = d1;
-                const float tol = fmaf(ta, d1 + d2, tb);
-                if (d2 - d1 > tol) bi = i1;
-            }
-            if (bi == -2) {  // exact FP64, lowest index wins ties (MCsub.jl:255)
-                const double x = a.px[p], y = a.py[p], z = a.pz[p];
-                double best = 1e9;
-                int b = 0x7fffffff;
-                for (int i = lane; i < Kn; i += 32) {
-                    const double d = dist2_exact(cc[i], cc[a.KC + i], cc[2 * a.KC + i], x, y, z);
-                    if (d < best) { best = d; b = i; }
-                }
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) {
-                    const double ob = __shfl_xor_sync(FULL, best, m);
-                    const int oi = __shfl_xor_sync(FULL, b, m);
-                    if (ob < best || (ob == best && oi < b)) { best = ob; b = oi; }
-                }
-                bi = (b == 0x7fffffff) ? -1 : b;
-                dbest = (float)best;
-            }
-            if (COMMIT) {
-                dmx = fmaxf(dmx, bi < 0 ? 1e9f : dbest);
-                if (lane == 0) {
-                    // a death's owners stay in the OLD numbering here: tg_renumber_kernel shifts every owner above the killed index afterwards
-                    const int bo = (act == 2 && bi >= idx) ? bi + 1 : bi;
-                    own[p] = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bo;
-                    dc[p] = bi < 0 ? 1e9f : dbest;
-                }
-            } else if (lane == 0) {
-                s_owner[j] = bi < 0 ? (uint16_t)TG_NONE16S : (uint16_t)bi;
-                if (act == 2 || bi != idx) atomicOr(&s_chg[j >> 5], 1u << (j & 31));  // a point that stays with the moved nucleus keeps its zeta
             }
         }
         __syncwarp();

@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
                       (unsigned long long)(a.chain_id0 + chain), cur, cur + KC, cur + 2 * KC, cur + 3 * KC, K, a.noise[chain], a.prm,
                          a.prm.zeta_scale * a.prm.sig / 100, lane);
         if (lane == 0) {
+            if (pr.do_eval && (pr.action == 2 || pr.action == 3)) {  // position of the killed / changed nucleus (a move carries its old position already):
+                pr.ox = cur[pr.idx]; pr.oy = cur[KC + pr.idx]; pr.oz = cur[2 * KC + pr.idx];  // the culled point pass needs it after the model was committed
+            }
             s_prop = pr;
             a.props[chain] = pr;
             if (a.mode == 0 && a.recs_out) {
