@@ -275,6 +275,8 @@ struct tonga_chains {
     size_t xch_bytes = 0, xch_hdr = 0;
     unsigned char *sh_peer[tg::TG_MAX_SHARDS] = {};
     unsigned long long sh_seq = 0;       // exchanges published so far
+    int mb_cap = 0;
+    size_t mb_cnt_bytes = 0, mb_sec = 0;
     // streamed sampler with spatial culling (stream_cull.cuh)
     bool culled = false;
     int s2_maxn = 0;
@@ -753,23 +755,33 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             sh.timeout_ns = (unsigned long long)(tmo * 1e6);
             for (int g = 0; g < sh.world; g++) sh.peer_base[g] = ch->sh_peer[g];
             TG_CUDA(cudaMemsetAsync(sh.err, 0, 4, s));
+            if (ch->culled) {
+                sh.mb = 1; sh.mb_cap = ch->mb_cap; sh.mb_n = ch->n; sh.ndirty = ch->d_ndirty;
+                sh.mb_hdr = ch->xch_hdr; sh.mb_sec = ch->mb_sec; sh.mb_cnt_bytes = ch->mb_cnt_bytes;
+            }
         }
-        const bool culled = ch->streamed && ch->culled && !sharded;
+        const bool culled = ch->streamed && ch->culled;
         tg::CullArgs ca{};
         if (culled) {
             ca.sub = ch->d_sub; ca.sub_off = ch->d_sub_off; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
             ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.cand_changed = ch->d_cand_changed; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
             ca.work_off = ch->d_work_off; ca.R = ctx->R; ca.ray0 = 0; ca.ray1 = ctx->R; ca.maxn = ch->s2_maxn; ca.p0 = 0; ca.p1 = ctx->Ppad;
+            if (sharded) {
+                int32_t r0 = 0, r1 = 0;
+                int64_t q0 = 0, q1 = 0;
+                tonga_chains_shard_info(ch, nullptr, nullptr, &r0, &r1, &q0, &q1);
+                ca.ray0 = r0; ca.ray1 = r1; ca.p0 = q0; ca.p1 = q1;
+            }
             w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;
         }
-        const dim3 cgrid((unsigned)((ctx->R + tg::CULL_THREADS - 1) / tg::CULL_THREADS), (unsigned)ch->n);
+        const dim3 cgrid((unsigned)std::max(1, (ca.ray1 - ca.ray0 + tg::CULL_THREADS - 1) / tg::CULL_THREADS), (unsigned)ch->n);
         const unsigned s2grid = (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 4u;
         const dim3 sgrid((unsigned)((size_t)(sh.tile1 - sh.tile0) * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;
         for (int64_t it = 0; it < nIter; it++) {
             w.it = it; w.iter = ch->iter_done + 1 + it;
-            if (sharded) {  // this iteration's exchange: sequence number, parity buffers in every rank's block
-                sh.seq = ++ch->sh_seq;
+            if (sharded) sh.seq = ++ch->sh_seq;  // this iteration's exchange
+            if (sharded && !culled) {  // tile kernels: parity buffers of (t*, term) for ALL rays in every rank's block
                 const size_t par = (size_t)(sh.seq & 1ull);
                 for (int g = 0; g < sh.world; g++) {
                     sh.peer_term[g] = (double *)(ch->sh_peer[g] + ch->xch_hdr + par * xbuf);
@@ -786,6 +798,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
                 tg::tg_cull_kernel<<<cgrid, tg::CULL_THREADS, 0, s>>>(ca);
                 tg::tg_cull_prefix_kernel<<<1, 1024, 0, s>>>(ch->d_active, ch->d_active + ch->n, ch->d_ncand, ch->d_work_off);
                 tg::tg_stream2_kernel<false><<<s2grid, tg::S2_THREADS, ch->s2_smem, s>>>(ca);
+                if (sharded) tg::tg_shard_signal_kernel<<<1, 256, 0, s>>>(sh);
             } else if (ch->streamed) {
                 if (sgrid.x > 0) tg::tg_stream_kernel<false><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);
                 if (sharded) tg::tg_shard_signal_kernel<<<1, 32, 0, s>>>(sh);
@@ -872,6 +885,19 @@ extern "C" int tonga_chains_shard_init(tonga_chains *ch, int32_t rank, int32_t w
     ch->sh_rank = rank; ch->sh_world = world; ch->sh_tile0 = t0; ch->sh_tile1 = t1;
     ch->xch_hdr = (128 * (size_t)(world + 1) + 255) & ~(size_t)255;
     ch->xch_bytes = ch->xch_hdr + 4 * 8 * (size_t)ch->n * (size_t)ch->Rp;
+    if (ch->culled) {  // mailbox protocol: only the dirty rays travel; capacity = the largest own ray count of any rank
+        int cap = 1;
+        for (int g = 0; g < world; g++) {
+            int a0 = 0, a1 = 0;
+            tonga_shard_range(ch->n_stiles, g, world, &a0, &a1);
+            if (a1 > a0) cap = std::max(cap, ch->h_stiles[a1 - 1].r1 - ch->h_stiles[a0].r0);
+        }
+        ch->mb_cap = cap;
+        ch->mb_cnt_bytes = (4 * (size_t)ch->n + 255) & ~(size_t)255;
+        ch->mb_sec = ch->mb_cnt_bytes + 20 * (size_t)ch->n * (size_t)cap;
+        ch->mb_sec = (ch->mb_sec + 255) & ~(size_t)255;
+        ch->xch_bytes = ch->xch_hdr + 2 * (size_t)world * ch->mb_sec;
+    }
     TG_CUDA(cudaMalloc((void **)&ch->d_xch, ch->xch_bytes));
     TG_CUDA(cudaMemset(ch->d_xch, 0, ch->xch_bytes));
     ch->sh_peer[rank] = ch->d_xch;
@@ -1146,8 +1172,10 @@ extern "C" int tonga_chains_verify(tonga_chains *ch, int64_t *owner_mismatch, do
                                               ch->d_owner16, own16_tmp, ch->d_tstar, ch->d_ptS_tmp,
                                               ch->d_phi, ch->d_phi_tmp, ch->d_dcache, dc_tmp, ctx->tol_alpha, ctx->tol_beta2, ch->d_mism, ch->d_maxd);
     TG_CUDA(cudaGetLastError());
-    if (ch->culled && ch->sh_world <= 1) {  // the culling state must be consistent with the chain state (violations count as mismatches)
-        tg::tg_stream_check_kernel<<<dim3((unsigned)((ctx->R + 7) / 8), (unsigned)ch->n), 256, 0, s>>>(ctx->R, ch->Rp, ctx->Ppad, 0, ctx->R, ctx->d_ray_off, ch->d_dcache, ch->d_tstar,
+    if (ch->culled) {  // the culling state must be consistent with the chain state (violations count as mismatches)
+        int32_t vr0 = 0, vr1 = ctx->R;
+        if (ch->sh_world > 1) tonga_chains_shard_info(ch, nullptr, nullptr, &vr0, &vr1, nullptr, nullptr);
+        tg::tg_stream_check_kernel<<<dim3((unsigned)((ctx->R + 7) / 8), (unsigned)ch->n), 256, 0, s>>>(ctx->R, ch->Rp, ctx->Ppad, vr0, vr1, ctx->d_ray_off, ch->d_dcache, ch->d_tstar,
                                                                                              ctx->d_tS, ctx->d_sig, ch->d_noise, ch->d_dmax, ch->d_term, ch->d_tstar_c,
                                                                                              ch->d_term_c, ch->d_mism);
         TG_CUDA(cudaGetLastError());

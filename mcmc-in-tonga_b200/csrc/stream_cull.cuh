@@ -409,7 +409,14 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
             const size_t i = (size_t)chain * a.Rp + r;
             const double term = misfit_term(t, a.tS[r], a.sig[r], a.noise[chain]);
             a.tstar_c[i] = t; a.term_c[i] = term;
-            ca.dirty[(size_t)chain * ca.R + atomicAdd(ca.ndirty + chain, 1)] = r;
+            const int di = atomicAdd(ca.ndirty + chain, 1);
+            ca.dirty[(size_t)chain * ca.R + di] = r;
+            for (int w = 0; w < a.sh.world; w++) {  // ray-sharded: the record goes into this rank's section of every other block (P2P stores)
+                if (w == a.sh.rank) continue;
+                unsigned char *sec = mb_section(a.sh, w, a.sh.rank);
+                const size_t k = (size_t)chain * a.sh.mb_cap + di;
+                mb_ray(a.sh, sec)[k] = r; mb_t(a.sh, sec)[k] = t; mb_term(a.sh, sec)[k] = term;
+            }
         }
     }
 }

@@ -38,7 +38,24 @@ struct ShardArgs {
     unsigned char *peer_base[TG_MAX_SHARDS];  // exchange blocks of all ranks (peer_base[rank] = own)
     double *peer_tsc[TG_MAX_SHARDS];          // [n][Rp] candidate t* buffer of this parity in rank w's block
     double *peer_term[TG_MAX_SHARDS];         // [n][Rp] candidate misfit terms, same
+    // culled point pass (stream_cull.cuh): only the DIRTY rays travel.  Block layout behind the header: for parity 0, 1 and source
+    // rank 0..world-1 one section {cnt[n] | ray[n][cap] | t*[n][cap] | term[n][cap]}; a rank writes its own section of every block.
+    int mb;                   // 1: mailbox protocol
+    int mb_cap, mb_n;         // records per chain and section (>= own rays of any rank); chains
+    const int32_t *ndirty;    // this rank's dirty counts (published by the signal kernel)
+    unsigned long long mb_hdr, mb_sec, mb_cnt_bytes;
 };
+__device__ __forceinline__ unsigned char *mb_section(const ShardArgs &sh, int block_of, int src) {
+    return sh.peer_base[block_of] + sh.mb_hdr + ((sh.seq & 1ull) * (unsigned long long)sh.world + (unsigned long long)src) * sh.mb_sec;
+}
+__device__ __forceinline__ int32_t *mb_cnt(unsigned char *sec) { return reinterpret_cast<int32_t *>(sec); }
+__device__ __forceinline__ int32_t *mb_ray(const ShardArgs &sh, unsigned char *sec) { return reinterpret_cast<int32_t *>(sec + sh.mb_cnt_bytes); }
+__device__ __forceinline__ double *mb_t(const ShardArgs &sh, unsigned char *sec) {
+    return reinterpret_cast<double *>(sec + sh.mb_cnt_bytes + 4ull * sh.mb_n * sh.mb_cap);
+}
+__device__ __forceinline__ double *mb_term(const ShardArgs &sh, unsigned char *sec) {
+    return reinterpret_cast<double *>(sec + sh.mb_cnt_bytes + 12ull * sh.mb_n * sh.mb_cap);
+}
 __device__ __forceinline__ unsigned long long tg_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -47,6 +64,14 @@ __device__ __forceinline__ unsigned long long tg_globaltimer() {
 // every rank's flag in every rank's block: "my stores of exchange `seq` are performed" (stream order puts this kernel after the
 // candidate pass; the system-scope fence + release store make the pass's peer stores visible before the flag)
 __global__ void tg_shard_signal_kernel(const ShardArgs sh) {
+    if (sh.mb) {  // mailbox protocol: how many records this rank has left in every block
+        for (int w = 0; w < sh.world; w++) {
+            if (w == sh.rank) continue;
+            int32_t *c = mb_cnt(mb_section(sh, w, sh.rank));
+            for (int i = threadIdx.x; i < sh.mb_n; i += blockDim.x) c[i] = sh.ndirty[i];
+        }
+        __syncthreads();
+    }
     __threadfence_system();
     const int w = threadIdx.x;
     if (w < sh.world) {
@@ -189,6 +214,21 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
     const double *tsc = a.tstar_c + (size_t)chain * a.Rp;  // streamed: candidate t*, sorted ray order
     int accepted = 0;
     shard_wait(a.sh, tid);  // ray-sharded: (t*, term) of the other ranks' rays have arrived in this rank's exchange block
+    if (a.sh.world > 1 && a.sh.mb && do_eval && act != 5) {  // culled point pass: the other ranks' dirty rays -> tstar_c / term_c
+        double *tsc_w = a.tstar_c + (size_t)chain * a.Rp, *trm_w = const_cast<double *>(a.term_c) + (size_t)chain * a.Rp;
+        for (int w = 0; w < a.sh.world; w++) {
+            if (w == a.sh.rank) continue;
+            unsigned char *sec = mb_section(a.sh, a.sh.rank, w);
+            const int cnt = __ldcg(mb_cnt(sec) + chain);
+            const int32_t *rr = mb_ray(a.sh, sec) + (size_t)chain * a.sh.mb_cap;
+            const double *tt = mb_t(a.sh, sec) + (size_t)chain * a.sh.mb_cap, *mm = mb_term(a.sh, sec) + (size_t)chain * a.sh.mb_cap;
+            for (int d = tid; d < cnt; d += TG_PHI_LANES) {
+                const int r = __ldcg(rr + d);
+                tsc_w[r] = __ldcg(tt + d); trm_w[r] = __ldcg(mm + d);
+            }
+        }
+        __syncthreads();
+    }
     if (do_eval) {
         double phin;
         if (pm.debug_prior) {
@@ -233,7 +273,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 for (int i = tid; i < 4 * KC; i += TG_PHI_LANES) cur[i] = cand[i];
                 if (!a.streamed && !pm.debug_prior)  // streamed: the commit pass copies t* tile by tile
                     for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = tc[a.ray_orig[r]];
-                if (a.streamed && a.sh.world > 1)  // ray-sharded: t* is replicated, the commit pass only sees this rank's tiles
+                if (a.streamed && a.sh.world > 1 && !a.sh.mb)  // ray-sharded: t* is replicated, the commit pass only sees this rank's tiles
                     for (int r = tid; r < R; r += TG_PHI_LANES) ts[r] = __ldcg(tsc + r);
             }
             phi = phin;
@@ -253,6 +293,19 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                     const int r = dl[d];
                     if (accepted) { ts[r] = tsc_w[r]; trm_cur[r] = trm_w[r]; }
                     else { tsc_w[r] = ts[r]; trm_w[r] = trm_cur[r]; }
+                }
+                if (a.sh.world > 1 && a.sh.mb) {  // ... and the other ranks' dirty rays (t*, term are replicated)
+                    for (int w = 0; w < a.sh.world; w++) {
+                        if (w == a.sh.rank) continue;
+                        unsigned char *sec = mb_section(a.sh, a.sh.rank, w);
+                        const int cnt = __ldcg(mb_cnt(sec) + chain);
+                        const int32_t *rr = mb_ray(a.sh, sec) + (size_t)chain * a.sh.mb_cap;
+                        for (int d = tid; d < cnt; d += TG_PHI_LANES) {
+                            const int r = __ldcg(rr + d);
+                            if (accepted) { ts[r] = tsc_w[r]; trm_cur[r] = trm_w[r]; }
+                            else { tsc_w[r] = ts[r]; trm_w[r] = trm_cur[r]; }
+                        }
+                    }
                 }
             } else if (accepted) {  // the noise level changed: every term does
                 for (int r = tid; r < R; r += TG_PHI_LANES) {
