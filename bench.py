@@ -300,16 +300,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        ref_chains = 8 * ncores  # a bounded sample of the workload per step: 8 chains per host thread, the B200 arm's per-chain work
         for _ in range(max(args.warmup, 0)):
             cpu_reference_arm(ds, p, warm, max(args.iters // 10, 50), ncores)
         tot_props, tot_t = 0.0, 0.0
         for _ in range(args.steps):
-            rate, dt, chains = cpu_reference_arm(ds, p, warm, args.iters, ncores)
+            rate, dt, chains = cpu_reference_arm(ds, p, warm, args.iters, ncores, chains=ref_chains)
             tot_props += chains * args.iters
             tot_t += dt
         val = tot_props / tot_t
         rate_fresh, _, _ = cpu_reference_arm(ds, p, warm, args.iters, ncores, fresh=True)
-        sample = (f"{ncores} chains (warm start models 0..{ncores - 1}) x {args.iters} iterations per step on {ncores} host threads "
+        sample = (f"{ref_chains} chains (warm start models 0..{ref_chains - 1}) x {args.iters} iterations per step on {ncores} host threads "
                   "(one chain per thread, as pmap does); the per-chain work is the B200 arm's: same start models, same iteration count")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -452,12 +453,13 @@ def main():
         hb = {"achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": frac_hbm, "peak_source": f"MEASURED_PEAKS.json ({peaks_src})"}
         top = fp if frac_fp >= frac_hbm else hb  # report both, name the larger as the bound
         roof = {"bound": "fp64" if top is fp else "hbm", "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                "traffic": None, "traffic_ncu_capture": traffic_ncu, "peak_source": top["peak_source"],
+                "traffic": (traffic_ncu["dram_bytes_read_per_launch"] + traffic_ncu["dram_bytes_write_per_launch"]) if traffic_ncu else None,
+                "traffic_ncu_capture": traffic_ncu, "peak_source": top["peak_source"],
                 "kernel": "tg_sampler_kernel", "launch_ms": dev_ms / args.steps,
                 "algorithmic_bytes_per_proposal": bytes_ / props_rank, "algorithmic_flop_per_proposal": flops / props_rank,
                 "fp64": fp, "hbm": hb, "fp32_peak_tflops": fp32_peak,
                 "note": "contraction depth 3: no tensor cores; the chain state (owners) is shared-memory resident by design, so the HBM figure is "
-                        "algorithmic bytes / time and `traffic` (DRAM bytes of this run) is not measured here -- see traffic_ncu_capture"}
+                        "algorithmic bytes / time; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 chains x 1000 iterations, without history writes) from the committed ncu --set full capture (traffic_ncu_capture), not measured in this run"}
         acc_rate = (c[1, :4] / np.maximum(c[0, :4], 1)).round(4).tolist()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -506,8 +508,8 @@ def main():
             out["config5"], out["config3"] = c5, c3
     if rank == 0:
         if not args.no_cpu_baseline:
-            rate, dt, chains = cpu_reference_arm(ds, p, warm, args.iters, ncores, chains=2 * ncores)
-            rate1, dt1, _ = cpu_reference_arm(ds, p, warm, args.iters, 1, chains=2)
+            rate, dt, chains = cpu_reference_arm(ds, p, warm, args.iters, ncores, chains=48 * ncores)   # ~10 s of host work
+            rate1, dt1, _ = cpu_reference_arm(ds, p, warm, args.iters, 1, chains=16)
             ratef, _, _ = cpu_reference_arm(ds, p, warm, args.iters, ncores, fresh=True)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": ncores, "kind": "port",
                                    "sample": f"{chains} chains (warm start models 0..{chains - 1}) x {args.iters} iterations on {ncores} threads ({dt:.1f} s); "

@@ -282,6 +282,7 @@ struct tonga_chains {
     int s2_maxn = 0;
     size_t s2_smem = 0;
     float4 *d_sub = nullptr;         // bounding spheres of the 32-point runs
+    float4 *d_raysph = nullptr;      // [R] bounding spheres of the rays
     int32_t *d_sub_off = nullptr;    // [R+1]
     float *d_dmax = nullptr;         // [n][Rp]
     double *d_term = nullptr;        // [n][Rp]
@@ -436,8 +437,9 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
             }
             TG_ALLOC(ch->d_sub_off, 4 * (size_t)(R + 1));
             TG_ALLOC(ch->d_sub, sizeof(float4) * (size_t)std::max(so[R], 1));
+            TG_ALLOC(ch->d_raysph, sizeof(float4) * (size_t)R);
             TG_CUDA(cudaMemcpyAsync(ch->d_sub_off, so.data(), 4 * (size_t)(R + 1), cudaMemcpyHostToDevice, ctx->stream));
-            tg::tg_sub_spheres_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(R, ctx->d_ray_off, ch->d_sub_off, ctx->d_px, ctx->d_py, ctx->d_pz, ch->d_sub);
+            tg::tg_sub_spheres_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(R, ctx->d_ray_off, ch->d_sub_off, ctx->d_px, ctx->d_py, ctx->d_pz, ch->d_sub, ch->d_raysph);
             TG_CUDA(cudaGetLastError());
             TG_CUDA(cudaStreamSynchronize(ctx->stream));  // `so` is a local
             TG_ALLOC(ch->d_dmax, 4 * n * Rp);
@@ -542,7 +544,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     }
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->d_xch) cudaFree(ch->d_xch);
-    void *cull[] = {ch->d_sub, ch->d_sub_off, ch->d_dmax, ch->d_term, ch->d_cand, ch->d_ncand, ch->d_dirty, ch->d_ndirty, ch->d_work_off, ch->d_cand_changed};
+    void *cull[] = {ch->d_raysph, ch->d_sub, ch->d_sub_off, ch->d_dmax, ch->d_term, ch->d_cand, ch->d_ncand, ch->d_dirty, ch->d_ndirty, ch->d_work_off, ch->d_cand_changed};
     for (void *p : cull) cudaFree(p);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
@@ -763,7 +765,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         const bool culled = ch->streamed && ch->culled;
         tg::CullArgs ca{};
         if (culled) {
-            ca.sub = ch->d_sub; ca.sub_off = ch->d_sub_off; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
+            ca.sub = ch->d_sub; ca.raysph = ch->d_raysph; ca.sub_off = ch->d_sub_off; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
             ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.cand_changed = ch->d_cand_changed; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
             ca.work_off = ch->d_work_off; ca.R = ctx->R; ca.ray0 = 0; ca.ray1 = ctx->R; ca.maxn = ch->s2_maxn; ca.p0 = 0; ca.p1 = ctx->Ppad;
             if (sharded) {

@@ -26,6 +26,7 @@ namespace tg {
 struct CullArgs {
     StreamArgs s;            // geometry, candidate models, chain state (tiles unused)
     const float4 *sub;       // bounding sphere (centre, radius) of every 32-point run, rays in sorted order
+    const float4 *raysph;    // [R] bounding sphere of the whole ray (first, coarse test)
     const int32_t *sub_off;  // [R+1]
     float *dmax;             // [n][Rp]
     double *term;            // [n][Rp] misfit term of the chain's current t* (what term_c is restored to)
@@ -50,12 +51,14 @@ __host__ __device__ inline size_t s2_warp_smem(int maxn) {  // owner16[maxn] | q
 
 // ---- static geometry: bounding spheres of the 32-point runs (one thread per ray) ---------------------------------------------
 __global__ void tg_sub_spheres_kernel(int R, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ sub_off, const double *__restrict__ px,
-                                      const double *__restrict__ py, const double *__restrict__ pz, float4 *__restrict__ sub) {
+                                      const double *__restrict__ py, const double *__restrict__ pz, float4 *__restrict__ sub, float4 *__restrict__ raysph) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const int q0 = ray_off[r], n = ray_off[r + 1] - q0;
-    for (int s0 = 0, s = sub_off[r]; s0 < n; s0 += 32, s++) {
-        const int m = min(32, n - s0);
+    for (int s0 = -1, s = sub_off[r]; s0 < n; s0 += 32) {  // first round (s0 = -1): the whole ray
+        const bool whole = s0 < 0;
+        if (whole) s0 = 0;
+        const int m = whole ? n : min(32, n - s0);
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (int j = 0; j < m; j++) {
             const double v[3] = {px[q0 + s0 + j], py[q0 + s0 + j], pz[q0 + s0 + j]};
@@ -70,7 +73,9 @@ __global__ void tg_sub_spheres_kernel(int R, const int32_t *__restrict__ ray_off
         // rounded outwards: the fl32 centre is off by <= 1 ulp of the largest coordinate, the radius by 1 ulp
         const double cm = fmax(fmax(fabs(c[0]), fabs(c[1])), fabs(c[2]));
         const float radf = (float)(sqrt(rad2) * (1.0 + 1e-6) + 4e-7 * cm + 1e-30);
-        sub[s] = make_float4((float)c[0], (float)c[1], (float)c[2], radf);
+        const float4 sp = make_float4((float)c[0], (float)c[1], (float)c[2], radf);
+        if (whole) { raysph[r] = sp; s0 = -32; }
+        else sub[s++] = sp;
     }
 }
 
@@ -118,9 +123,13 @@ __global__ void __launch_bounds__(CULL_THREADS) tg_cull_kernel(const CullArgs a)
         const float nx = (float)pr.x, ny = (float)pr.y, nz = (float)pr.z;
         const float ox = (float)pr.ox, oy = (float)pr.oy, oz = (float)pr.oz;  // killed / changed nucleus, old position of a moved one
         const float dm = a.dmax[(size_t)chain * a.s.Rp + r] * 1.0001f;
-        for (int s = a.sub_off[r]; s < a.sub_off[r + 1] && !cand; s++) {
-            const float4 sp = __ldg(a.sub + s);
-            cand = (has_new && sphere_near(sp, nx, ny, nz, dm)) || (has_old && sphere_near(sp, ox, oy, oz, dm));
+        const float4 rs = __ldg(a.raysph + r);
+        const bool near_new = has_new && sphere_near(rs, nx, ny, nz, dm), near_old = has_old && sphere_near(rs, ox, oy, oz, dm);
+        if (near_new || near_old) {
+            for (int s = a.sub_off[r]; s < a.sub_off[r + 1] && !cand; s++) {
+                const float4 sp = __ldg(a.sub + s);
+                cand = (near_new && sphere_near(sp, nx, ny, nz, dm)) || (near_old && sphere_near(sp, ox, oy, oz, dm));
+            }
         }
     }
     const uint32_t m = __ballot_sync(0xffffffffu, cand);
@@ -181,22 +190,35 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
     int *s_cnt = reinterpret_cast<int *>(s_chg + ca.maxn / 32 + 1);
     const float ta = a.tol_alpha, tb = a.tol_beta2;
 
-    for (int item = blockIdx.x * S2_WARPS + warp; item < total; item += gridDim.x * S2_WARPS) {
-        // item -> (active slot, index in the chain's candidate list): largest slot with work_off[slot] <= item
-        int lo_s = 0, hi_s = n_active;
-        while (hi_s - lo_s > 1) {
-            const int mid = (lo_s + hi_s) >> 1;
-            if (ca.work_off[mid] <= item) lo_s = mid; else hi_s = mid;
+    constexpr int CH = 8;  // items per chunk: lanes 0..7 fetch the chunk's metadata (slot, ray, offsets) side by side
+    for (int c0 = (blockIdx.x * S2_WARPS + warp) * CH; c0 < total; c0 += gridDim.x * S2_WARPS * CH) {
+        int m_chain = 0, m_ci = 0, m_r = 0, m_q0 = 0, m_n = 0;
+        {
+            const int item = c0 + (lane & (CH - 1));
+            if (item < total) {
+                // item -> (active slot, index in the chain's candidate list): largest slot with work_off[slot] <= item
+                int lo_s = 0, hi_s = n_active;
+                while (hi_s - lo_s > 1) {
+                    const int mid = (lo_s + hi_s) >> 1;
+                    if (__ldg(ca.work_off + mid) <= item) lo_s = mid; else hi_s = mid;
+                }
+                m_chain = a.active[lo_s];
+                m_ci = item - __ldg(ca.work_off + lo_s);
+                m_r = ca.cand[(size_t)m_chain * ca.R + m_ci];
+                m_q0 = a.ray_off[m_r];
+                m_n = a.ray_off[m_r + 1] - m_q0;
+            }
         }
-        const int chain = a.active[lo_s];
-        const int ci = item - ca.work_off[lo_s];
+#pragma unroll 1
+    for (int ii = 0; ii < CH && c0 + ii < total; ii++) {
+        const int chain = __shfl_sync(FULL, m_chain, ii), ci = __shfl_sync(FULL, m_ci, ii), r = __shfl_sync(FULL, m_r, ii);
+        const int q0 = __shfl_sync(FULL, m_q0, ii), n = __shfl_sync(FULL, m_n, ii);
         const Prop pr = a.props[chain];
         const int act = pr.action;
         if (COMMIT) {
             if (!a.accept_flag[chain] || act == 3) continue;  // change: no owner moves
             if (!ca.cand_changed[(size_t)chain * ca.R + ci]) continue;
         }
-        const int r = ca.cand[(size_t)chain * ca.R + ci];
         const int Kn = a.Kc[chain];
         const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
         const float *cf = a.cells_cf + (size_t)chain * 3 * a.KC;
@@ -206,7 +228,6 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
         const double cx = pr.x, cy = pr.y, cz = pr.z;
         const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
         const int newo = (act == 1) ? Kn - 1 : idx;
-        const int q0 = a.ray_off[r], n = a.ray_off[r + 1] - q0;
         const long long p0a = (long long)(q0 & ~3);
         const int lo = (int)(q0 - p0a), hi = lo + n;  // valid relative range [lo, hi)
         const int ngroups = (hi + 3) >> 2;
@@ -418,6 +439,7 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
                 mb_ray(a.sh, sec)[k] = r; mb_t(a.sh, sec)[k] = t; mb_term(a.sh, sec)[k] = term;
             }
         }
+    }
     }
 }
 
