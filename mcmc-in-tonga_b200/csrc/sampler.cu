@@ -777,7 +777,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;
         }
         const dim3 cgrid((unsigned)std::max(1, (ca.ray1 - ca.ray0 + tg::CULL_THREADS - 1) / tg::CULL_THREADS), (unsigned)ch->n);
-        const unsigned s2grid = (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 4u;
+        const unsigned s2grid = (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148) * (unsigned)S2_MIN_CTAS;
         const dim3 sgrid((unsigned)((size_t)(sh.tile1 - sh.tile0) * (size_t)((ch->n + tg::STREAM_GROUP - 1) / tg::STREAM_GROUP)));
         const int exact = (ch->exact_only || ctx->exact_only) ? 1 : 0;
         for (int64_t it = 0; it < nIter; it++) {

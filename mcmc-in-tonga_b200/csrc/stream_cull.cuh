@@ -44,9 +44,12 @@ struct CullArgs {
 constexpr int CULL_THREADS = 256;
 constexpr int S2_THREADS = 256;
 constexpr int S2_WARPS = S2_THREADS / 32;
+#ifndef S2_MIN_CTAS
+#define S2_MIN_CTAS 4
+#endif
 constexpr int S2_LIST = 256;  // nuclei near the killed / moved nucleus that an orphan is rescanned against (else: all)
-__host__ __device__ inline size_t s2_warp_smem(int maxn) {  // owner16[maxn] | queue16[maxn] | list16[S2_LIST] | chg32[maxn/32 + 1] | cnt[2]
-    return (size_t)maxn * 4 + (size_t)S2_LIST * 2 + (size_t)(maxn / 32 + 1) * 4 + 8;
+__host__ __device__ inline size_t s2_warp_smem(int maxn) {  // term64[maxn] | owner16[maxn] | queue16[maxn] | list16[S2_LIST] | chg32[maxn/32 + 1] | cnt[2]
+    return (size_t)maxn * 12 + (size_t)S2_LIST * 2 + (size_t)(maxn / 32 + 1) * 4 + 8;
 }
 
 // ---- static geometry: bounding spheres of the 32-point runs (one thread per ray) ---------------------------------------------
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(1024) tg_cull_prefix_kernel(const int32_t *__r
 
 // ---- one warp per candidate ray -------------------------------------------------------------------------------------------
 template <bool COMMIT>
-__global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArgs ca) {
+__global__ void __launch_bounds__(S2_THREADS, S2_MIN_CTAS) tg_stream2_kernel(const CullArgs ca) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StreamArgs &a = ca.s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -183,7 +186,8 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
     const int n_active = *a.n_active;
     const int total = ca.work_off[n_active];
     unsigned char *wbase = smem_raw + (size_t)warp * ((s2_warp_smem(ca.maxn) + 15) & ~(size_t)15);
-    uint16_t *s_owner = reinterpret_cast<uint16_t *>(wbase);
+    double *s_term = reinterpret_cast<double *>(wbase);
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_term + ca.maxn);
     uint16_t *s_queue = s_owner + ca.maxn;
     uint16_t *s_list = s_queue + ca.maxn;
     uint32_t *s_chg = reinterpret_cast<uint32_t *>(s_list + S2_LIST);
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
 
     constexpr int CH = 8;  // items per chunk: lanes 0..7 fetch the chunk's metadata (slot, ray, offsets) side by side
     for (int c0 = (blockIdx.x * S2_WARPS + warp) * CH; c0 < total; c0 += gridDim.x * S2_WARPS * CH) {
-        int m_chain = 0, m_ci = 0, m_r = 0, m_q0 = 0, m_n = 0;
+        int m_chain = 0, m_ci = 0, m_r = 0, m_q0 = 0, m_n = 0, m_skip = 0;
         {
             const int item = c0 + (lane & (CH - 1));
             if (item < total) {
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
                 }
                 m_chain = a.active[lo_s];
                 m_ci = item - __ldg(ca.work_off + lo_s);
+                if (COMMIT) m_skip = !a.accept_flag[m_chain] || !ca.cand_changed[(size_t)m_chain * ca.R + m_ci];
                 m_r = ca.cand[(size_t)m_chain * ca.R + m_ci];
                 m_q0 = a.ray_off[m_r];
                 m_n = a.ray_off[m_r + 1] - m_q0;
@@ -213,12 +218,10 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
     for (int ii = 0; ii < CH && c0 + ii < total; ii++) {
         const int chain = __shfl_sync(FULL, m_chain, ii), ci = __shfl_sync(FULL, m_ci, ii), r = __shfl_sync(FULL, m_r, ii);
         const int q0 = __shfl_sync(FULL, m_q0, ii), n = __shfl_sync(FULL, m_n, ii);
+        if (COMMIT && __shfl_sync(FULL, m_skip, ii)) continue;  // rejected, or nothing to commit in this ray
         const Prop pr = a.props[chain];
         const int act = pr.action;
-        if (COMMIT) {
-            if (!a.accept_flag[chain] || act == 3) continue;  // change: no owner moves
-            if (!ca.cand_changed[(size_t)chain * ca.R + ci]) continue;
-        }
+        if (COMMIT && act == 3) continue;  // change: no owner moves
         const int Kn = a.Kc[chain];
         const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
         const float *cf = a.cells_cf + (size_t)chain * 3 * a.KC;
@@ -422,10 +425,14 @@ __global__ void __launch_bounds__(S2_THREADS, 4) tg_stream2_kernel(const CullArg
         const bool on = lane < 8;
         const int trip = (nseg + 7) >> 3;
         const uint16_t *ow = s_owner + lo;
-        const double t = tstar_g8(on ? nseg : 0, trip, lane & 7, [&](int j) {
+        // the segment terms by ALL lanes (loads of several rounds in flight), then the ordered canonical sum from shared memory
+#pragma unroll 4
+        for (int j = lane; j < nseg; j += 32) {
             const uint16_t oa = ow[j], ob = ow[j + 1];
-            return seg_term(a.dt[q0 + j], oa == TG_NONE16S ? 0.0 : zc[oa], ob == TG_NONE16S ? 0.0 : zc[ob]);
-        });
+            s_term[j] = seg_term(__ldg(a.dt + q0 + j), oa == TG_NONE16S ? 0.0 : __ldg(zc + oa), ob == TG_NONE16S ? 0.0 : __ldg(zc + ob));
+        }
+        __syncwarp();
+        const double t = tstar_g8(on ? nseg : 0, trip, lane & 7, [&](int j) { return s_term[j]; });
         if (lane == 0) {
             const size_t i = (size_t)chain * a.Rp + r;
             const double term = misfit_term(t, a.tS[r], a.sig[r], a.noise[chain]);

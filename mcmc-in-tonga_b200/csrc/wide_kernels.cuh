@@ -239,12 +239,12 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
                 const double *trm = a.term_c + (size_t)chain * a.Rp;
                 double acc = 0.0;
                 int c = 0;
-                for (; (c + 8) * TG_PHI_LANES <= R; c += 8) {  // 8 loads in flight, then the ordered adds (canonical phi order, phi_ray)
-                    double v[8];
+                for (; (c + 16) * TG_PHI_LANES <= R; c += 16) {  // 16 loads in flight, then the ordered adds (canonical phi order, phi_ray)
+                    double v[16];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = __ldcg(trm + phi_ray(c + u, tid));  // L2: peers write these rows
+                    for (int u = 0; u < 16; u++) v[u] = __ldcg(trm + phi_ray(c + u, tid));  // L2: peers write these rows
 #pragma unroll
-                    for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+                    for (int u = 0; u < 16; u++) acc = __dadd_rn(acc, v[u]);
                 }
                 for (; c * TG_PHI_LANES < R; c++) {
                     const int r = phi_ray(c, tid);
