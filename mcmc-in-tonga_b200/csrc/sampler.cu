@@ -287,7 +287,7 @@ struct tonga_chains {
     float *d_dmax = nullptr;         // [n][Rp]
     double *d_term = nullptr;        // [n][Rp]
     int32_t *d_cand = nullptr, *d_ncand = nullptr, *d_dirty = nullptr, *d_ndirty = nullptr, *d_work_off = nullptr;
-    uint8_t *d_cand_changed = nullptr;
+    int32_t *d_clist = nullptr, *d_nclist = nullptr, *d_ncommit = nullptr, *d_work_off2 = nullptr;
     // scratch
     double *d_ptS_tmp = nullptr;  // [n][R]  (wide sampler: t* of the candidates)
     double *d_phi_tmp = nullptr;
@@ -446,7 +446,12 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
             TG_ALLOC(ch->d_term, 8 * n * Rp);
             TG_ALLOC(ch->d_cand, 4 * n * R);
             TG_ALLOC(ch->d_dirty, 4 * n * R);
-            TG_ALLOC(ch->d_cand_changed, n * R);
+            TG_ALLOC(ch->d_clist, 4 * n * R);
+            TG_ALLOC(ch->d_nclist, 4 * n);
+            TG_ALLOC(ch->d_ncommit, 4 * n);
+            TG_ALLOC(ch->d_work_off2, 4 * (n + 1));
+            TG_CUDA(cudaMemsetAsync(ch->d_nclist, 0, 4 * n, ctx->stream));
+            TG_CUDA(cudaMemsetAsync(ch->d_ncommit, 0, 4 * n, ctx->stream));
             TG_ALLOC(ch->d_ncand, 4 * n);
             TG_ALLOC(ch->d_ndirty, 4 * n);
             TG_ALLOC(ch->d_work_off, 4 * (n + 1));
@@ -544,7 +549,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     }
     if (ch->d_prof) cudaFree(ch->d_prof);
     if (ch->d_xch) cudaFree(ch->d_xch);
-    void *cull[] = {ch->d_raysph, ch->d_sub, ch->d_sub_off, ch->d_dmax, ch->d_term, ch->d_cand, ch->d_ncand, ch->d_dirty, ch->d_ndirty, ch->d_work_off, ch->d_cand_changed};
+    void *cull[] = {ch->d_raysph, ch->d_sub, ch->d_sub_off, ch->d_dmax, ch->d_term, ch->d_cand, ch->d_ncand, ch->d_dirty, ch->d_ndirty, ch->d_work_off, ch->d_clist, ch->d_nclist, ch->d_ncommit, ch->d_work_off2};
     for (void *p : cull) cudaFree(p);
     if (ch->ev0) cudaEventDestroy(ch->ev0);
     if (ch->ev1) cudaEventDestroy(ch->ev1);
@@ -766,7 +771,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
         tg::CullArgs ca{};
         if (culled) {
             ca.sub = ch->d_sub; ca.raysph = ch->d_raysph; ca.sub_off = ch->d_sub_off; ca.dmax = ch->d_dmax; ca.term = ch->d_term;
-            ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.cand_changed = ch->d_cand_changed; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
+            ca.cand = ch->d_cand; ca.ncand = ch->d_ncand; ca.clist = ch->d_clist; ca.nclist = ch->d_nclist; ca.ncommit = ch->d_ncommit; ca.work_off2 = ch->d_work_off2; ca.dirty = ch->d_dirty; ca.ndirty = ch->d_ndirty;
             ca.work_off = ch->d_work_off; ca.R = ctx->R; ca.ray0 = 0; ca.ray1 = ctx->R; ca.maxn = ch->s2_maxn; ca.p0 = 0; ca.p1 = ctx->Ppad;
             if (sharded) {
                 int32_t r0 = 0, r1 = 0;
@@ -774,7 +779,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
                 tonga_chains_shard_info(ch, nullptr, nullptr, &r0, &r1, &q0, &q1);
                 ca.ray0 = r0; ca.ray1 = r1; ca.p0 = q0; ca.p1 = q1;
             }
-            w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;
+            w.nclist = ch->d_nclist; w.ncommit = ch->d_ncommit; w.culled = 1; w.ncand = ch->d_ncand; w.ndirty = ch->d_ndirty; w.dirty = ch->d_dirty; w.term = ch->d_term;
         }
         const dim3 cgrid((unsigned)std::max(1, (ca.ray1 - ca.ray0 + tg::CULL_THREADS - 1) / tg::CULL_THREADS), (unsigned)ch->n);
         const unsigned s2grid = (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148) * (unsigned)S2_MIN_CTAS;
@@ -810,6 +815,7 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             }
             tg::tg_wide_accept_kernel<<<ch->n, TG_PHI_LANES, 0, s>>>(w);
             if (culled) {
+                tg::tg_cull_prefix_kernel<<<1, 1024, 0, s>>>(ch->d_active, ch->d_active + ch->n, ch->d_ncommit, ch->d_work_off2);
                 tg::tg_stream2_kernel<true><<<s2grid, tg::S2_THREADS, ch->s2_smem, s>>>(ca);
                 tg::tg_renumber_kernel<<<dim3(128, (unsigned)ch->n), 256, 0, s>>>(ca);
             } else if (ch->streamed && sgrid.x > 0) tg::tg_stream_kernel<true><<<sgrid, tg::STREAM_THREADS, ch->stream_smem, s>>>(sa);

@@ -32,7 +32,10 @@ struct CullArgs {
     double *term;            // [n][Rp] misfit term of the chain's current t* (what term_c is restored to)
     int32_t *cand;           // [n][R] candidate rays of this proposal
     int32_t *ncand;          // [n]
-    uint8_t *cand_changed;   // [n][R] parallel to cand: the candidate pass found something to commit in this ray
+    int32_t *clist;          // [n][R] rays in which the candidate pass found something to commit (the commit pass's work list)
+    int32_t *nclist;         // [n] its length; the accept kernel turns it into ncommit (0 for rejected chains / a change)
+    int32_t *ncommit;        // [n]
+    int32_t *work_off2;      // [n+1] prefix of ncommit over the active list
     int32_t *dirty;          // [n][R] rays whose t* differs under the candidate model
     int32_t *ndirty;         // [n]
     int32_t *work_off;       // [n+1] prefix of ncand over the active list
@@ -184,7 +187,9 @@ __global__ void __launch_bounds__(S2_THREADS, S2_MIN_CTAS) tg_stream2_kernel(con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t FULL = 0xffffffffu;
     const int n_active = *a.n_active;
-    const int total = ca.work_off[n_active];
+    const int32_t *woff = COMMIT ? ca.work_off2 : ca.work_off;
+    const int32_t *wlist = COMMIT ? ca.clist : ca.cand;
+    const int total = woff[n_active];
     unsigned char *wbase = smem_raw + (size_t)warp * ((s2_warp_smem(ca.maxn) + 15) & ~(size_t)15);
     double *s_term = reinterpret_cast<double *>(wbase);
     uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_term + ca.maxn);
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(S2_THREADS, S2_MIN_CTAS) tg_stream2_kernel(con
 
     constexpr int CH = 8;  // items per chunk: lanes 0..7 fetch the chunk's metadata (slot, ray, offsets) side by side
     for (int c0 = (blockIdx.x * S2_WARPS + warp) * CH; c0 < total; c0 += gridDim.x * S2_WARPS * CH) {
-        int m_chain = 0, m_ci = 0, m_r = 0, m_q0 = 0, m_n = 0, m_skip = 0;
+        int m_chain = 0, m_ci = 0, m_r = 0, m_q0 = 0, m_n = 0;
         {
             const int item = c0 + (lane & (CH - 1));
             if (item < total) {
@@ -204,24 +209,21 @@ __global__ void __launch_bounds__(S2_THREADS, S2_MIN_CTAS) tg_stream2_kernel(con
                 int lo_s = 0, hi_s = n_active;
                 while (hi_s - lo_s > 1) {
                     const int mid = (lo_s + hi_s) >> 1;
-                    if (__ldg(ca.work_off + mid) <= item) lo_s = mid; else hi_s = mid;
+                    if (__ldg(woff + mid) <= item) lo_s = mid; else hi_s = mid;
                 }
                 m_chain = a.active[lo_s];
-                m_ci = item - __ldg(ca.work_off + lo_s);
-                if (COMMIT) m_skip = !a.accept_flag[m_chain] || !ca.cand_changed[(size_t)m_chain * ca.R + m_ci];
-                m_r = ca.cand[(size_t)m_chain * ca.R + m_ci];
+                m_ci = item - __ldg(woff + lo_s);
+                m_r = wlist[(size_t)m_chain * ca.R + m_ci];
                 m_q0 = a.ray_off[m_r];
                 m_n = a.ray_off[m_r + 1] - m_q0;
             }
         }
 #pragma unroll 1
     for (int ii = 0; ii < CH && c0 + ii < total; ii++) {
-        const int chain = __shfl_sync(FULL, m_chain, ii), ci = __shfl_sync(FULL, m_ci, ii), r = __shfl_sync(FULL, m_r, ii);
+        const int chain = __shfl_sync(FULL, m_chain, ii), r = __shfl_sync(FULL, m_r, ii);
         const int q0 = __shfl_sync(FULL, m_q0, ii), n = __shfl_sync(FULL, m_n, ii);
-        if (COMMIT && __shfl_sync(FULL, m_skip, ii)) continue;  // rejected, or nothing to commit in this ray
         const Prop pr = a.props[chain];
-        const int act = pr.action;
-        if (COMMIT && act == 3) continue;  // change: no owner moves
+        const int act = pr.action;  // (COMMIT: the work list holds accepted births / deaths / moves only)
         const int Kn = a.Kc[chain];
         const double *cc = a.cells_c + (size_t)chain * 4 * a.KC;
         const float *cf = a.cells_cf + (size_t)chain * 3 * a.KC;
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(S2_THREADS, S2_MIN_CTAS) tg_stream2_kernel(con
         bool anyc = false;
         for (int i = lane; i < (hi >> 5) + 1; i += 32) anyc |= (s_chg[i] != 0u);
         const bool dirty = __any_sync(FULL, anyc);
-        if (lane == 0) ca.cand_changed[(size_t)chain * ca.R + ci] = (uint8_t)((dirty || nq > 0) ? 1 : 0);
+        if (lane == 0 && act != 3 && (dirty || nq > 0)) ca.clist[(size_t)chain * ca.R + atomicAdd(ca.nclist + chain, 1)] = r;
         if (!dirty) continue;
         // ---- t* of the ray under the candidate model (canonical order: lanes 0..7)
         const double *zc = cc + 3 * (size_t)a.KC;

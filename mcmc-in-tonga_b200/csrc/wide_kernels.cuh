@@ -126,6 +126,7 @@ struct WideArgs {
     // streamed sampler with culling (stream_cull.cuh): per-chain candidate / dirty ray lists, misfit terms of the current state
     int culled;
     int32_t *ncand, *ndirty;   // [n], zeroed by the propose kernel
+    int32_t *nclist, *ncommit; // [n] rays with something to commit (candidate pass) -> the commit pass's count (accept kernel)
     const int32_t *dirty;      // [n][R]
     double *term;              // [n][Rp]
     // streams / traces
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(WIDE_PROPOSE_THREADS) tg_wide_propose_kernel(c
             }
             const int ps = a.pending_slot[chain];
             if (ps >= 0) { a.hist_next[(size_t)chain * a.hist_cap + ps] = pr.action; a.pending_slot[chain] = -1; }
-            if (a.culled) { a.ncand[chain] = 0; a.ndirty[chain] = 0; }
+            if (a.culled) { a.ncand[chain] = 0; a.ndirty[chain] = 0; a.nclist[chain] = 0; a.ncommit[chain] = 0; }
         }
     }
     __syncthreads();
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(TG_PHI_LANES) tg_wide_accept_kernel(const Wide
         a.K[chain] = K; a.phi[chain] = phi; a.noise[chain] = noise;
         a.n_hist[chain] = n_hist; a.model_num[chain] = model_num;
         if (a.accept_flag) a.accept_flag[chain] = accepted;
+        if (a.culled) a.ncommit[chain] = (accepted && do_eval && act != 5 && act != 3) ? a.nclist[chain] : 0;
     }
 }
 
