@@ -206,8 +206,10 @@ def leg_config3(local_rank, peaks, fp64_peak, fp32_peak, R=100000, chains=64, it
     out["streamed"] = {"chains": chains, "K_start": 1000, "iterations": iters, "ms_per_iteration": ms / iters, "proposals_per_s": chains * iters / ms * 1e3,
                        "roofline": {"bound": "hbm", "achieved": minimal_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": minimal_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                    "note": "SURVEY 8(d) minimal bytes (2 B of owner state per point); the kernel's own 18 B/point layout moves "
-                                            "%.0f GB/s" % (own_bytes / (ms * 1e-3) / 1e9)},
+                                    "note": "SURVEY 8(d) minimal bytes (2 B of owner state per point and evaluated / accepted proposal) / time.  The culled point "
+                                            "pass (stream_cull.cuh) reads only the rays near the proposal's nucleus (18 B per point of a candidate ray): "
+                                            "an unculled pass over the same proposals would move %.0f GB per iteration, the ncu launch list "
+                                            "(profiles/r02_stream_cull_launches.md) shows 1.7 GB" % (own_bytes / iters / 1e9)},
                        "verify": {"owner_mismatch": mm, "max_dphi": dphi, "max_dtstar": dts}}
     st_un = ch.state(want_ptS=False)
     ch.close()
@@ -503,8 +505,9 @@ def main():
                 rs = c3["ray_sharded"]
                 rs.update({"ms_per_iteration": rs_ms, "proposals_per_s": rs["chains"] / rs_ms * 1e3, "bit_identical_to_unsharded_all_ranks": rs_ok,
                            "speedup_vs_one_gpu": c3["streamed"]["ms_per_iteration"] / rs_ms,
-                           "parallelism": f"ray-sharded x{world}: ONE batch of {rs['chains']} chains, per-point state split by ray tiles, "
-                                          "(t*, term) exchanged per proposal by P2P stores fused into the candidate pass"})
+                           "parallelism": f"ray-sharded x{world}: ONE batch of {rs['chains']} chains, per-point state split by ray tiles; per proposal the "
+                                          "candidate pass stores (ray, t*, misfit term) of its dirty rays into every rank's exchange block (P2P stores over "
+                                          "NVLink, CUDA IPC mappings), sequence flags + bounded wait in the accept kernel; no NCCL on the data path"})
             out["config5"], out["config3"] = c5, c3
     if rank == 0:
         if not args.no_cpu_baseline:
