@@ -48,14 +48,14 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     const Tile tile = tiles[blockIdx.x];
     const int K = Ks[model];
     if (K < 0) return;  // wide sampler: this chain has no candidate to evaluate in this iteration
-    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier, counters | float4 coefficients [Kcap + 2] | owner16[tile_pts] | queue16[tile_pts]
+    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier, counters | float4 coefficients [Kcap + 8] | owner16[tile_pts] | queue16[tile_pts]
     double *s_nx = reinterpret_cast<double *>(smem_raw);
     double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zeta + Kcap);
     int *s_nq = reinterpret_cast<int *>(s_bar + 1);
     float *s_red = reinterpret_cast<float *>(s_nq + 2);  // [3][8] per-warp maxima
     float4 *s_cf = reinterpret_cast<float4 *>(s_red + 24);
-    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_cf + Kcap + 2);
+    uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_cf + Kcap + 8);
     uint16_t *s_queue = s_owner + tile_pts;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -102,12 +102,12 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
         d_off = 1.5f * B;     // added to every |n'|^2: the computed distances stay >= 0 (non-negative floats order like their bits)
         tol_beta = 2.5f * B + 6.0f * 5.9604644775390625e-08f * d_off;
     }
-    for (int i = tid; i < K + 2; i += EVAL_THREADS) {
+    for (int i = tid; i < K + 8; i += EVAL_THREADS) {
         if (i < K) {
             const double nx = s_nx[i] - cenx, ny = s_ny[i] - ceny, nz = s_nz[i] - cenz;
             s_cf[i] = make_float4((float)(-2.0 * nx), (float)(-2.0 * ny), (float)(-2.0 * nz), (float)(nx * nx + ny * ny + nz * nz + (double)d_off));
         } else {
-            s_cf[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));  // padding nuclei (the loop visits pairs): +inf, never win
+            s_cf[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));  // padding nuclei (the loop visits blocks of 8): +inf, never win
         }
     }
     __syncthreads();
@@ -137,47 +137,60 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
             const float2 Y01 = make_float2(ys[0] - fcy, ys[1] - fcy), Y23 = make_float2(ys[2] - fcy, ys[3] - fcy);
             const float2 Z01 = make_float2(zs[0] - fcz, zs[1] - fcz), Z23 = make_float2(zs[2] - fcz, zs[3] - fcz);
             const float2 Q01 = __ffma2_rn(Z01, Z01, __ffma2_rn(Y01, Y01, __fmul2_rn(X01, X01))), Q23 = __ffma2_rn(Z23, Z23, __ffma2_rn(Y23, Y23, __fmul2_rn(X23, X23)));
-#pragma unroll 1
-            for (int cb = 0; cb < K; cb += 128) {  // chunks of 128 nuclei: 7 index bits
-                const int kend = min(128, (K - cb + 1) & ~1);
-                uint32_t c1[EVAL_PPT], c2[EVAL_PPT];
+            // Blocks of 8 nuclei.  Inside a block only the block minimum is kept (one 3-input min per two pairs); across blocks
+            // best / second best of the block minima and the id of the best block (5 ALU instructions per block): ~1.1 ALU
+            // instructions per pair instead of 3.5 with per-pair (best, second best, index) tracking -- the FMA pipe (2 per pair) is
+            // the limiter again.  The winning block is recomputed afterwards (identical arithmetic) for the index and the
+            // in-block runner-up.
+            float B1[EVAL_PPT], B2[EVAL_PPT];
+            int BK[EVAL_PPT];
 #pragma unroll
-                for (int q = 0; q < EVAL_PPT; q++) { c1[q] = INF_PACK; c2[q] = INF_PACK; }
-                const float4 *cf = s_cf + cb;
+            for (int q = 0; q < EVAL_PPT; q++) { B1[q] = __int_as_float(0x7f800000); B2[q] = __int_as_float(0x7f800000); BK[q] = 0; }
+            const int nblk = (K + 7) >> 3;
 #pragma unroll 1
-                for (int i = 0; i < kend; i += 2) {  // two nuclei per step: the ALU pipe (min / max, rt 2) is the limiter, see below
+            for (int b = 0; b < nblk; b++) {
+                const float4 *cf = s_cf + 8 * b;
+                float bm[EVAL_PPT];
+#pragma unroll
+                for (int q = 0; q < EVAL_PPT; q++) bm[q] = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
                     const float4 cA = cf[i], cB = cf[i + 1];
-                    float dA[EVAL_PPT], dB[EVAL_PPT];
-                    {
-                        const float2 ca = make_float2(cA.x, cA.x), cbv = make_float2(cA.y, cA.y), cc = make_float2(cA.z, cA.z), ce = make_float2(cA.w, cA.w);
-                        const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
-                        const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
-                        dA[0] = da.x; dA[1] = da.y; dA[2] = db.x; dA[3] = db.y;
-                    }
-                    {
-                        const float2 ca = make_float2(cB.x, cB.x), cbv = make_float2(cB.y, cB.y), cc = make_float2(cB.z, cB.z), ce = make_float2(cB.w, cB.w);
-                        const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
-                        const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
-                        dB[0] = da.x; dB[1] = da.y; dB[2] = db.x; dB[3] = db.y;
-                    }
-#pragma unroll
-                    for (int q = 0; q < EVAL_PPT; q++) {
-                        // (best, second best) of {c1, c2, a, b} in 5 min / max operations for TWO pairs: 3.5 ALU instructions per pair
-                        // with the two packs.  The distances are >= 0 by construction (offset in the coefficients, see above).
-                        const uint32_t a_ = (__float_as_uint(dA[q]) & 0xFFFFFF80u) | (uint32_t)i, b_ = (__float_as_uint(dB[q]) & 0xFFFFFF80u) | (uint32_t)(i + 1);
-                        const uint32_t m = min(a_, b_), M = max(a_, b_);
-                        c2[q] = __vimin3_u32(c2[q], max(c1[q], m), M);
-                        c1[q] = min(c1[q], m);
-                    }
+                    const float2 ca = make_float2(cA.x, cA.x), cbv = make_float2(cA.y, cA.y), cc = make_float2(cA.z, cA.z), ce = make_float2(cA.w, cA.w);
+                    const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
+                    const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
+                    const float2 ga = make_float2(cB.x, cB.x), gb = make_float2(cB.y, cB.y), gc = make_float2(cB.z, cB.z), ge = make_float2(cB.w, cB.w);
+                    const float2 ea = __fadd2_rn(__ffma2_rn(X01, ga, __ffma2_rn(Y01, gb, __ffma2_rn(Z01, gc, ge))), Q01);
+                    const float2 eb = __fadd2_rn(__ffma2_rn(X23, ga, __ffma2_rn(Y23, gb, __ffma2_rn(Z23, gc, ge))), Q23);
+                    bm[0] = fminf(fminf(bm[0], da.x), ea.x); bm[1] = fminf(fminf(bm[1], da.y), ea.y);
+                    bm[2] = fminf(fminf(bm[2], db.x), eb.x); bm[3] = fminf(fminf(bm[3], db.y), eb.y);
                 }
 #pragma unroll
-                for (int q = 0; q < EVAL_PPT; q++) {  // merge the chunk's (best, second best) into the running ones
-                    const float f1 = __uint_as_float(c1[q] & 0xFFFFFF80u), f2 = __uint_as_float(c2[q] & 0xFFFFFF80u);
-                    const bool lt = f1 < D1[q];
-                    D2[q] = lt ? fminf(D1[q], f2) : fminf(D2[q], f1);
-                    I1[q] = lt ? cb + (int)(c1[q] & 0x7Fu) : I1[q];
-                    D1[q] = lt ? f1 : D1[q];
+                for (int q = 0; q < EVAL_PPT; q++) {
+                    const bool lt = bm[q] < B1[q];
+                    B2[q] = fminf(B2[q], fmaxf(B1[q], bm[q]));
+                    BK[q] = lt ? b : BK[q];
+                    B1[q] = fminf(B1[q], bm[q]);
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < EVAL_PPT; q++) {  // the winning block again: index of the best, runner-up inside the block
+                const float X = (q < 2) ? (q == 0 ? X01.x : X01.y) : (q == 2 ? X23.x : X23.y), Y = (q < 2) ? (q == 0 ? Y01.x : Y01.y) : (q == 2 ? Y23.x : Y23.y),
+                            Z = (q < 2) ? (q == 0 ? Z01.x : Z01.y) : (q == 2 ? Z23.x : Z23.y), Q = (q < 2) ? (q == 0 ? Q01.x : Q01.y) : (q == 2 ? Q23.x : Q23.y);
+                const float4 *cf = s_cf + 8 * BK[q];
+                float d1 = __int_as_float(0x7f800000), d2 = __int_as_float(0x7f800000);
+                int i1 = -1;
+#pragma unroll 2
+                for (int i = 0; i < 8; i++) {
+                    const float4 c = cf[i];
+                    const float d = __fadd_rn(__fmaf_rn(X, c.x, __fmaf_rn(Y, c.y, __fmaf_rn(Z, c.z, c.w))), Q);
+                    const bool lt = d < d1;
+                    d2 = lt ? d1 : fminf(d2, d);
+                    i1 = lt ? i : i1;
+                    d1 = lt ? d : d1;
+                }
+                // (d1 == B1 bit for bit: same operations; were it not, d1 / d2 below are still the block's true best / second best)
+                if (i1 >= 0 && d1 < 1e9f) { D1[q] = d1; D2[q] = fminf(fminf(B2[q], d2), 1e9f); I1[q] = 8 * BK[q] + i1; }
             }
 #pragma unroll
             for (int q = 0; q < EVAL_PPT; q++) {
@@ -268,7 +281,7 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
-        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + 8 + 96 + 16 * ((size_t)Kcap + 2) + 2 * sizeof(uint16_t) * (size_t)ctx->tile_pts;
+        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + 8 + 96 + 16 * ((size_t)Kcap + 8) + 2 * sizeof(uint16_t) * (size_t)ctx->tile_pts;
         if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ctx->n_tiles, nModels);
