@@ -34,7 +34,10 @@ constexpr int EVAL_PPT = 4;  // points per thread per pass
 //     d2 - d1 > alpha (d1 + d2) + beta,   alpha = 2^-16 + 2^-19,  beta = 2.5 B
 // (2 B for the two values, 25 % margin); anything else -- also a best within the band of the 1e9 "no nucleus" threshold --
 // goes to a per-tile queue and is re-scanned in exact FP64 by the whole CTA after the pass (no divergent rescans inside it).
-__global__ void __launch_bounds__(EVAL_THREADS)
+#ifndef EVAL_MIN_CTAS
+#define EVAL_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_CTAS)
 tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restrict__ Ks, const double *__restrict__ cells,
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, double cenx, double ceny,
