@@ -152,6 +152,35 @@ end
 
 TD_inversion_function(TD_parameters, dataStruct1, chain::Int64) = run_chains(TD_parameters, dataStruct1, chain:chain)[1]
 
+# ---- one batch over several GPUs (one Julia process per GPU): ray sharding of a STREAMED batch ---------------------------------
+# Call on every rank after tonga_chains_create_ex(..., sampler = 3) with the same arguments; `allgather64(bytes)` is the host-side
+# exchange of one 64-byte CUDA IPC handle per rank (e.g. MPI.Allgather) returning a Vector of W handles in rank order.
+# Returns the mapped peer pointers (close them with shard_disconnect before destroying the batch).
+function shard_connect(ch::Ptr{Cvoid}, rank::Integer, world::Integer, device::Integer, allgather64)
+    base = Ref{Ptr{Cvoid}}(C_NULL); nbytes = Ref{UInt64}(0)
+    check(ccall((:tonga_chains_shard_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{Ptr{Cvoid}}, Ref{UInt64}), ch, rank, world, base, nbytes))
+    handle = Vector{UInt8}(undef, 64)
+    check(ccall((:tonga_ipc_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), base[], handle))
+    handles = allgather64(handle)
+    peers = Vector{Ptr{Cvoid}}(undef, world)
+    for w in 0:world-1
+        if w == rank
+            peers[w+1] = base[]
+        else
+            q = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:tonga_ipc_open, LIB), Cint, (Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}), device, handles[w+1], q))
+            peers[w+1] = q[]
+        end
+    end
+    check(ccall((:tonga_chains_shard_connect, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), ch, peers))
+    return peers
+end
+function shard_disconnect(peers::Vector{Ptr{Cvoid}}, rank::Integer, device::Integer)
+    for w in 0:length(peers)-1
+        w == rank || check(ccall((:tonga_ipc_close, LIB), Cint, (Int32, Ptr{Cvoid}), device, peers[w+1]))
+    end
+end
+
 end # module
 
 # Method overwrite: make the reference's global names forward to the GPU path.
