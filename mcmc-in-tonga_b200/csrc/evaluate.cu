@@ -23,8 +23,8 @@ constexpr int EVAL_PPT = 4;  // points per thread per pass
 // with c = centre of the nucleus box, p' = p - c, n' = n - c,
 //     |p - n|^2 = |p'|^2 + ( |n'|^2 - 2 p'.n' )
 // so a nucleus is four fl32 coefficients (-2 n'x, -2 n'y, -2 n'z, |n'|^2) -- ONE 128-bit shared-memory broadcast -- and a
-// (point, nucleus) pair costs 3 FMAs + 1 add, issued as packed FFMA2 / FADD2 over point pairs: 2 instructions per pair
-// instead of 3 for (dx^2 + dy^2 + dz^2).  Best and second best are kept as INTEGER min / max of the distance bits with the
+// (point, nucleus) pair costs 3 FMAs, issued as packed FFMA2 over point pairs (1.5 instructions per pair instead of 3 for
+// dx^2 + dy^2 + dz^2); |p'|^2 does not depend on the nucleus and is added once, after the selection.  Best and second best are kept as INTEGER min / max of the distance bits with the
 // nucleus index (mod 128) in the 7 low mantissa bits (non-negative floats order like their bits; nuclei are visited in
 // chunks of 128): 4 ALU instructions per pair instead of a compare and three selects.
 // Error band (u = 2^-24; per axis a: A_a = max |p'_a|, |n'_a| over the tile's model, M_a = max |p_a|): every one of the five
@@ -160,11 +160,11 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                 for (int i = 0; i < 8; i += 2) {
                     const float4 cA = cf[i], cB = cf[i + 1];
                     const float2 ca = make_float2(cA.x, cA.x), cbv = make_float2(cA.y, cA.y), cc = make_float2(cA.z, cA.z), ce = make_float2(cA.w, cA.w);
-                    const float2 da = __fadd2_rn(__ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce))), Q01);
-                    const float2 db = __fadd2_rn(__ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce))), Q23);
+                    const float2 da = __ffma2_rn(X01, ca, __ffma2_rn(Y01, cbv, __ffma2_rn(Z01, cc, ce)));
+                    const float2 db = __ffma2_rn(X23, ca, __ffma2_rn(Y23, cbv, __ffma2_rn(Z23, cc, ce)));
                     const float2 ga = make_float2(cB.x, cB.x), gb = make_float2(cB.y, cB.y), gc = make_float2(cB.z, cB.z), ge = make_float2(cB.w, cB.w);
-                    const float2 ea = __fadd2_rn(__ffma2_rn(X01, ga, __ffma2_rn(Y01, gb, __ffma2_rn(Z01, gc, ge))), Q01);
-                    const float2 eb = __fadd2_rn(__ffma2_rn(X23, ga, __ffma2_rn(Y23, gb, __ffma2_rn(Z23, gc, ge))), Q23);
+                    const float2 ea = __ffma2_rn(X01, ga, __ffma2_rn(Y01, gb, __ffma2_rn(Z01, gc, ge)));
+                    const float2 eb = __ffma2_rn(X23, ga, __ffma2_rn(Y23, gb, __ffma2_rn(Z23, gc, ge)));
                     bm[0] = fminf(fminf(bm[0], da.x), ea.x); bm[1] = fminf(fminf(bm[1], da.y), ea.y);
                     bm[2] = fminf(fminf(bm[2], db.x), eb.x); bm[3] = fminf(fminf(bm[3], db.y), eb.y);
                 }
@@ -186,14 +186,17 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
 #pragma unroll 2
                 for (int i = 0; i < 8; i++) {
                     const float4 c = cf[i];
-                    const float d = __fadd_rn(__fmaf_rn(X, c.x, __fmaf_rn(Y, c.y, __fmaf_rn(Z, c.z, c.w))), Q);
+                    const float d = __fmaf_rn(X, c.x, __fmaf_rn(Y, c.y, __fmaf_rn(Z, c.z, c.w)));
                     const bool lt = d < d1;
                     d2 = lt ? d1 : fminf(d2, d);
                     i1 = lt ? i : i1;
                     d1 = lt ? d : d1;
                 }
                 // (d1 == B1 bit for bit: same operations; were it not, d1 / d2 below are still the block's true best / second best)
-                if (i1 >= 0 && d1 < 1e9f) { D1[q] = d1; D2[q] = fminf(fminf(B2[q], d2), 1e9f); I1[q] = 8 * BK[q] + i1; }
+                // |p'|^2 joins after the selection: x -> fl(x + Q) is monotone, so best / second best of the sums are the sums of the
+                // best / second best (values that only tie after the rounding are inside the band anyway -> exact re-scan)
+                const float s1 = __fadd_rn(d1, Q), s2 = __fadd_rn(fminf(B2[q], d2), Q);
+                if (i1 >= 0 && s1 < 1e9f) { D1[q] = s1; D2[q] = fminf(s2, 1e9f); I1[q] = 8 * BK[q] + i1; }
             }
 #pragma unroll
             for (int q = 0; q < EVAL_PPT; q++) {
