@@ -42,7 +42,7 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
                const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
                const float *__restrict__ pxf, const float *__restrict__ pyf, const float *__restrict__ pzf, double cenx, double ceny,
                double cenz, float mpx, float mpy, float mpz /* max |p'| per axis over the ray set */, float mux, float muy,
-               float muz /* max |p| per axis */, int exact_only, const double *__restrict__ dt, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
+               float muz /* max |p| per axis */, int exact_only, int stage_xyz, const double *__restrict__ dt, const int32_t *__restrict__ ray_off, const int32_t *__restrict__ ray_orig,
                const int32_t *__restrict__ point_orig, int R, int64_t P, int64_t Ppad, int tile_pts,
                double *__restrict__ ptS, int32_t *__restrict__ owners32, uint8_t *__restrict__ owners8, float *__restrict__ dmin32,
                uint16_t *__restrict__ owners16) {
@@ -51,9 +51,14 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     const Tile tile = tiles[blockIdx.x];
     const int K = Ks[model];
     if (K < 0) return;  // wide sampler: this chain has no candidate to evaluate in this iteration
-    // shared layout: nx[Kcap] ny[Kcap] nz[Kcap] nzeta[Kcap] | mbarrier, counters | float4 coefficients [Kcap + 8] | owner16[tile_pts] | queue16[tile_pts]
-    double *s_nx = reinterpret_cast<double *>(smem_raw);
-    double *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap, *s_zeta = s_nz + Kcap;
+    // shared layout: [nx[Kcap] ny[Kcap] nz[Kcap]] nzeta[Kcap] | mbarrier, counters | float4 coefficients [Kcap + 8] | owner16[tile_pts] | queue16[tile_pts]
+    // The FP64 coordinates are only read by the prologue and the (rare) exact re-scan: for large models (stage_xyz == 0) they stay in
+    // global memory (L2-resident, uniform addresses) and the CTA keeps 48 KB less at K = 2000 -- 3 instead of 2 CTAs per SM.
+    const double *mc = cells + (size_t)model * 4 * Kcap;
+    double *s_stage = reinterpret_cast<double *>(smem_raw);
+    const int nrows = stage_xyz ? 4 : 1;
+    double *s_zeta = s_stage + (nrows - 1) * Kcap;
+    const double *s_nx = stage_xyz ? s_stage : mc, *s_ny = s_nx + Kcap, *s_nz = s_ny + Kcap;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zeta + Kcap);
     int *s_nq = reinterpret_cast<int *>(s_bar + 1);
     float *s_red = reinterpret_cast<float *>(s_nq + 2);  // [3][8] per-warp maxima
@@ -62,10 +67,10 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     uint16_t *s_queue = s_owner + tile_pts;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    const double *mc = cells + (size_t)model * 4 * Kcap;
-    const uint32_t nbytes = (uint32_t)(4 * Kcap * sizeof(double));
-    const bool use_bulk = (nbytes >= 2048u) && ((nbytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(mc) & 15u) == 0);
-    if (use_bulk) {  // one TMA bulk copy of the whole [4][Kcap] block
+    const double *src = mc + (4 - nrows) * Kcap;
+    const uint32_t nbytes = (uint32_t)(nrows * Kcap * sizeof(double));
+    const bool use_bulk = (nbytes >= 2048u) && ((nbytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    if (use_bulk) {  // one TMA bulk copy of the whole [4][Kcap] block (or of its zeta row)
         if (tid == 0) {
             mbar_init(s_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -73,11 +78,11 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(s_bar, nbytes);
-            bulk_g2s(s_nx, mc, nbytes, s_bar);
+            bulk_g2s(s_stage, src, nbytes, s_bar);
         }
         mbar_wait(s_bar, 0);
     } else {
-        for (int i = tid; i < 4 * Kcap; i += EVAL_THREADS) s_nx[i] = mc[i];
+        for (int i = tid; i < nrows * Kcap; i += EVAL_THREADS) s_stage[i] = src[i];
         __syncthreads();
     }
     // the model's coordinate bound (for the band), then the fl32 coefficients of the nuclei
@@ -287,14 +292,16 @@ int launch_evaluate(tonga_ctx *ctx, int nModels, int Kcap, const int32_t *K_dev,
     if (nModels <= 0) return TONGA_OK;
     if (nModels > 65535) return fail(TONGA_ERR_CAPACITY, "evaluate: at most 65535 models per call");
     if ((!ctx->prm.debug_prior || force_geometry) && ctx->n_tiles > 0) {
-        const size_t smem = sizeof(double) * 4 * (size_t)Kcap + 8 + 8 + 96 + 16 * ((size_t)Kcap + 8) + 2 * sizeof(uint16_t) * (size_t)ctx->tile_pts;
+        const int ex = exact_only < 0 ? ctx->exact_only : exact_only;
+        const int stage_xyz = (ex || Kcap <= 1024) ? 1 : 0;  // large models: FP64 coordinates stay in global memory (3 CTAs per SM at K = 2000)
+        const size_t smem = sizeof(double) * (stage_xyz ? 4 : 1) * (size_t)Kcap + 8 + 8 + 96 + 16 * ((size_t)Kcap + 8) + 2 * sizeof(uint16_t) * (size_t)ctx->tile_pts;
         if (smem > ctx->smem_optin) return fail(TONGA_ERR_CAPACITY, "evaluate: Kcap too large for shared memory");
         TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ctx->n_tiles, nModels);
         tg_eval_kernel<<<grid, EVAL_THREADS, smem, ctx->stream>>>(ctx->d_tiles, Kcap, K_dev, cells_dev, ctx->d_px, ctx->d_py,
                                                                   ctx->d_pz, ctx->d_pxf, ctx->d_pyf, ctx->d_pzf, ctx->cen[0], ctx->cen[1], ctx->cen[2],
                                                                   ctx->mp_cen[0], ctx->mp_cen[1], ctx->mp_cen[2], ctx->mp_abs[0], ctx->mp_abs[1], ctx->mp_abs[2],
-                                                                  exact_only < 0 ? ctx->exact_only : exact_only, ctx->d_dt, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
+                                                                  ex, stage_xyz, ctx->d_dt, ctx->d_ray_off, ctx->d_ray_orig, ctx->d_point_orig,
                                                                   ctx->R, ctx->P, ctx->Ppad, ctx->tile_pts, ptS_dev,
                                                                   owners32_dev, owners8_dev, dmin32_dev, owners16_dev);
         TG_CUDA(cudaGetLastError());
