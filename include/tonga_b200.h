@@ -99,6 +99,11 @@ int tonga_set_exact_only(tonga_ctx *ctx, int32_t exact_only);
 int tonga_evaluate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z, const double *zeta,
                    double noise, double *ptS_out, double *phi_out, double *like_out, double *loglik_out);
 
+/* The misfit alone, MCsub.jl:169-173: phi[i] = sum_k ((ptS[i][k] - tS[k])^2 * 1.0) / (noise[i] * allSig[k])^2 for nModels given t*
+ * vectors ptS[nModels][R] (caller's ray order; noise may be NULL = 1.0), computed by the kernel every evaluate / proposal uses
+ * (tg_phi_kernel, canonical summation order).  Lets the reference's own stored (ptS, phi) pairs (model.jld) be checked directly. */
+int tonga_misfit(tonga_ctx *ctx, int32_t nModels, const double *ptS, const double *noise, double *phi);
+
 /* Batched evaluate over nModels independent models (replaces nModels calls of MCsub.jl:123-185).
  * K[nModels]; cells[nModels][4][Kcap]; noise[nModels] or NULL; outputs (any may be NULL): ptS[nModels][R],
  * phi[nModels], owners[nModels][P] (0-based nearest nucleus per flat point, -1 if none within sqrt(1e9)). */

@@ -384,6 +384,28 @@ extern "C" int tonga_evaluate_batch(tonga_ctx *ctx, int32_t nModels, int32_t Kca
     return TONGA_OK;
 }
 
+extern "C" int tonga_misfit(tonga_ctx *ctx, int32_t nModels, const double *ptS, const double *noise, double *phi) {
+    if (!ctx || nModels < 0 || !ptS || !phi) return tg::fail(TONGA_ERR_ARG, "tonga_misfit: bad argument");
+    if (nModels == 0) return TONGA_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const size_t R = (size_t)ctx->R, n = (size_t)nModels;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_pts = 0, o_noise = o_pts + al(8 * n * (R ? R : 1)), o_phi = o_noise + al(8 * n), total = o_phi + al(8 * n);
+    int rc = tg::ensure_scratch(ctx, total);
+    if (rc != TONGA_OK) return rc;
+    char *d = (char *)ctx->d_scratch;
+    cudaStream_t s = ctx->stream;
+    if (R) TG_CUDA(cudaMemcpyAsync(d + o_pts, ptS, 8 * n * R, cudaMemcpyHostToDevice, s));
+    if (noise) TG_CUDA(cudaMemcpyAsync(d + o_noise, noise, 8 * n, cudaMemcpyHostToDevice, s));
+    tg::tg_phi_kernel<<<nModels, TG_PHI_LANES, 0, s>>>(ctx->R, (const double *)(d + o_pts), ctx->d_ray_orig, ctx->d_tS, ctx->d_sig,
+                                                       noise ? (const double *)(d + o_noise) : nullptr, (double *)(d + o_phi), ctx->prm.debug_prior);
+    TG_CUDA(cudaGetLastError());
+    TG_CUDA(cudaMemcpyAsync(phi, d + o_phi, 8 * n, cudaMemcpyDeviceToHost, s));
+    TG_CUDA(cudaStreamSynchronize(s));
+    return TONGA_OK;
+}
+
 extern "C" int tonga_evaluate(tonga_ctx *ctx, int32_t K, const double *x, const double *y, const double *z,
                               const double *zeta, double noise, double *ptS_out, double *phi_out, double *like_out,
                               double *loglik_out) {

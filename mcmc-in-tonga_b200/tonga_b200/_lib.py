@@ -53,6 +53,7 @@ SYMBOLS = {
     "tonga_set_exact_only": (C.c_int, [_P, C.c_int32]),
     "tonga_evaluate": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp, c_dp, c_dp]),
     "tonga_evaluate_batch": (C.c_int, [_P, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),
+    "tonga_misfit": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp]),
     "tonga_evaluate_batch_dev": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "tonga_interpolate": (C.c_int, [_P, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp, C.c_int32, c_dp, C.c_int32, c_dp,
                                     c_dp, c_ip, c_ip]),

@@ -143,6 +143,15 @@ class Context:
         check(self.lib.tonga_evaluate_batch(self._h, n, Kcap, ip(K), dp(cells), dp(noise), dp(ptS), dp(phi), ip(owners)))
         return dict(phi=phi, ptS=ptS, owners=owners)
 
+    def misfit(self, ptS, noise=None):
+        """phi of given t* vectors ptS[n, R] against this context's tS / allSig (MCsub.jl:169-173), by the device kernel."""
+        ptS = np.ascontiguousarray(np.atleast_2d(ptS), dtype=np.float64)
+        assert ptS.shape[1] == self.R
+        noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        phi = np.zeros(len(ptS))
+        check(self.lib.tonga_misfit(self._h, len(ptS), dp(ptS), dp(noise), dp(phi)))
+        return phi
+
     def evaluate_batch_dev(self, n, Kcap, K_ptr, cells_ptr, noise_ptr, ptS_ptr, phi_ptr, owners_ptr=None):
         """Device-pointer variant (ints from torch .data_ptr()); asynchronous on the context's stream."""
         check(self.lib.tonga_evaluate_batch_dev(self._h, n, Kcap, K_ptr, cells_ptr, noise_ptr, ptS_ptr, phi_ptr, owners_ptr))

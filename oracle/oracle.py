@@ -66,6 +66,8 @@ def lib():
         L.orc_interpolation.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_ip]
         L.orc_evaluate.restype = C.c_int
         L.orc_evaluate.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcData), C.POINTER(OrcModel), c_ip, c_dp]
+        L.orc_misfit.restype = None
+        L.orc_misfit.argtypes = [C.c_int, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp, c_dp]
         L.orc_build_starting.restype = C.c_int
         L.orc_build_starting.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcData), C.POINTER(OrcRng), C.POINTER(OrcModel)]
         L.orc_chain_run.restype = C.c_int
@@ -162,6 +164,14 @@ def interpolation(mx, my, mz, mv, X, Y, Z):
     n = lib().orc_interpolation(len(mx), _dp(mx), _dp(my), _dp(mz), _dp(mv), len(X), _dp(X), len(Y), _dp(Y), len(Z), _dp(Z),
                                 _dp(out), _ip(idx))
     return out[:n].copy(), idx[:n].copy()
+
+
+def misfit(ptS, tS, allSig, noise=1.0):
+    """MCsub.jl:169-182 -> (phi, likelihood, loglik_gauss); the C function orc_evaluate itself calls."""
+    ptS, tS, allSig = (np.ascontiguousarray(a, np.float64) for a in (ptS, tS, allSig))
+    out = np.zeros(3)
+    lib().orc_misfit(len(tS), _dp(ptS), _dp(tS), _dp(allSig), float(noise), _dp(out[0:1]), _dp(out[1:2]), _dp(out[2:3]))
+    return float(out[0]), float(out[1]), float(out[2])
 
 
 def evaluate(p: OrcParams, d: Data, x, y, z, zeta, noise=1.0, want_owners=False):

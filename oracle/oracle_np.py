@@ -55,6 +55,19 @@ def interpolation(mx, my, mz, mv, X, Y, Z):
     return nearest_many(X[:npoints], Y[:npoints], Z[:npoints], np.asarray(mx), np.asarray(my), np.asarray(mz), np.asarray(mv))
 
 
+def misfit(ptS, tS, allSig, noise=1.0):
+    """MCsub.jl:169-182 -> (phi, likelihood).  Pinned bit for bit by the reference's own model.jld (tests/test_oracle.py)."""
+    n = len(tS)
+    C = 0.0
+    lk = 0.0
+    for k in range(n):  # :169-172
+        sg = noise * allSig[k]
+        df = (ptS - tS)[k]
+        C += df * df * 1.0 / (sg * sg)
+        lk += -math.log(sg * math.sqrt(2 * math.pi)) * n  # :179 (the second line, :180, is discarded: SURVEY F5)
+    return C, lk
+
+
 def evaluate(rayX, rayY, rayZ, rayL, rayU, tS, allSig, mx, my, mz, mv, noise=1.0, debug_prior=0):
     """MCsub.jl:123-185 -> dict(ptS, phi, likelihood, owners[m,R])."""
     m, n = rayX.shape  # :138
@@ -76,13 +89,7 @@ def evaluate(rayX, rayY, rayZ, rayL, rayU, tS, allSig, mx, my, mz, mv, noise=1.0
         for t in terms:  # left-to-right (Julia's own order is unspecified; see tonga_oracle.h)
             s += t
         ptS[i] = s
-    C = 0.0
-    lk = 0.0
-    for k in range(n):  # :169-172
-        sg = noise * allSig[k]
-        df = (ptS - tS)[k]
-        C += df * df * 1.0 / (sg * sg)
-        lk += -math.log(sg * math.sqrt(2 * math.pi)) * n  # :179 (the second line, :180, is discarded: SURVEY F5)
+    C, lk = misfit(ptS, tS, allSig, noise)
     return dict(ptS=ptS, phi=C, likelihood=lk, owners=owners)
 
 

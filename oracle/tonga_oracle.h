@@ -93,6 +93,10 @@ int orc_interpolation(int K, const double *mx, const double *my, const double *m
                       int nX, const double *X, int nY, const double *Y, int nZ, const double *Z,
                       double *zeta_out, int32_t *idx_out);
 
+/* misfit phi + the constant "likelihood" (+ the Gaussian log-likelihood evidently intended), MCsub.jl:169-182; outputs may be NULL */
+void orc_misfit(int n, const double *ptS, const double *tS, const double *allSig, double noise, double *phi,
+                double *likelihood, double *loglik_gauss);
+
 int orc_evaluate(const orc_params *p, const orc_data *d, orc_model *mdl, int32_t *owners /* m*R or NULL */,
                  double *loglik_gauss /* or NULL */);
 

@@ -23,7 +23,7 @@ def tonga():
     return load_tonga381(p=p), p
 
 
-def random_ragged(seed, R=23, m=17, box=(100.0, 80.0, 60.0), full_some=True):
+def random_ragged(seed, R=23, m=17, box=(100.0, 80.0, 60.0), full_some=True, tS=None, sig=None):
     """Small random ragged ray set in the reference layout (m x R, NaN tail padding)."""
     from tonga_b200.data import make_datastruct
     from tonga_b200.structs import StepRangeLen, parameters
@@ -43,7 +43,7 @@ def random_ragged(seed, R=23, m=17, box=(100.0, 80.0, 60.0), full_some=True):
     U = np.where(np.isnan(z), np.nan, 0.1 + 0.001 * np.nan_to_num(z))
     p = parameters()
     bx = (StepRangeLen(-10.0, 5.0, box[0] + 10), StepRangeLen(-10.0, 5.0, box[1] + 10), StepRangeLen(0.0, 5.0, box[2]))
-    ds = make_datastruct(x, y, z, U, rng.uniform(0.1, 1.0, R), rng.uniform(0.05, 0.5, R), p, box=bx)
+    ds = make_datastruct(x, y, z, U, rng.uniform(0.1, 1.0, R) if tS is None else tS, rng.uniform(0.05, 0.5, R) if sig is None else sig, p, box=bx)
     return ds, p
 
 

@@ -10,7 +10,9 @@ Outputs
                  and the ak135 velocity table (Data/ak135f.txt) used to synthesise the slowness the
                  shipped raypaths file lacks.
   tests/golden/model_jld.npz  the 100 stored models of the reference's only shipped *output*, model.jld (2 chains x 50),
-                 used for invariant tests only: it belongs to an unshipped 487-ray data set.
+                 It belongs to an unshipped 487-ray data set, so the forward model cannot be replayed on it,
+                 but (ptS, tS) -> phi and the constant "likelihood" (MCsub.jl:169-182) can: with allSig = 0.2 the stored phi
+                 of all 100 models and the likelihood are reproduced bit for bit (tests/test_oracle.py).
 
 These are DATA (inputs/outputs of the reference), not reference source.
 """
@@ -103,7 +105,7 @@ def model_jld():
         accept=np.array([r["accept"] for r in recs], np.int64),
         zeta_xz=np.array([r["zeta_xz"] for r in recs]),
         zeta_xy=np.array([r["zeta_xy"] for r in recs]),
-        ptS=np.stack([r["ptS"] for r in recs]).astype(np.float32),  # float32: invariants only, keeps it small
+        ptS=np.stack([r["ptS"] for r in recs]),  # float64: (ptS, tS) -> phi is a reference-produced known answer (allSig = 0.2)
         tS=recs[0]["tS"],
         tS_identical=np.array(all((r["tS"] == recs[0]["tS"]).all() for r in recs)),
         sha256=np.array(sha(mp)),

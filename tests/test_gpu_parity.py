@@ -60,6 +60,25 @@ def test_evaluate_tonga381(tonga_ctx, K):
     assert _close(got["loglik_gauss"], ref["loglik_gauss"])
 
 
+def test_misfit_kernel_against_reference_output():
+    """Reference-PRODUCED known answers (not the oracle): model.jld, the reference's own output of a 487-ray run, stores ptS, tS and
+    phi of 100 models (allSig = 0.2, see tests/test_oracle.py).  The device misfit (tg_phi_kernel through tonga_misfit -- the kernel
+    every evaluate and every proposal ends in) must reproduce the stored phi to 1e-12 (its canonical summation order differs from
+    the reference's left-to-right loop; the contract is 1e-9), and evaluate's model-independent "likelihood" (MCsub.jl:179, F5)
+    must equal the stored constant."""
+    from tonga_b200.api import Context
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_jld.npz"))
+    ds, p = random_ragged(3, R=487, m=12, tS=m["tS"].copy(), sig=np.full(487, 0.2))
+    ctx = Context(ds, p)
+    phi = ctx.misfit(m["ptS"])
+    assert phi.shape == (100,) and np.all(np.abs(phi - m["phi"]) <= 1e-12 * m["phi"]), np.abs(phi / m["phi"] - 1).max()
+    assert ctx.misfit(m["ptS"][:1], noise=[2.0])[0] == pytest.approx(m["phi"][0] / 4, rel=1e-12)  # hierarchical noise scales allSig
+    rng = np.random.default_rng(0)
+    got = ctx.evaluate(*random_model(rng, 7, box_of(ds)))
+    assert abs(got["likelihood"] - m["likelihood"][0]) <= 1e-12 * m["likelihood"][0]
+    ctx.close()
+
+
 def test_evaluate_batch_many_models(tonga_ctx):
     import oracle as O
     ctx, ds, p = tonga_ctx

@@ -1,8 +1,10 @@
 """CPU tests of the oracle itself (no GPU): the C restatement against its independent NumPy twin, the KATs of
-v_nearest / Interpolation, and the invariants the reference's only shipped output (model.jld) pins.
+v_nearest / Interpolation, and what the reference's only shipped output (model.jld) pins.
 
-PARITY UNPINNED: the reference has no golden vectors for this path and cannot run here; these
-tests are what pins the oracle instead."""
+PARITY PARTLY PINNED: the reference cannot run here and has no golden vectors for the forward model (owners, t*), so those are
+pinned by the twin + KATs only.  The misfit phi and the constant "likelihood" (MCsub.jl:169-182) ARE pinned by
+reference-produced values: model.jld stores (ptS, tS, phi, likelihood) of 100 models, and the oracle reproduces every phi and
+the likelihood to 1e-13 (test_misfit_and_likelihood_pinned_by_reference_output)."""
 import os
 
 import numpy as np
@@ -202,3 +204,27 @@ def test_model_jld_invariants():
     # the constant equals sum_k(-log(sig_k*sqrt(2pi))) * n  =>  its per-datum mean gives a plausible sigma
     sig_gm = np.exp(-m["likelihood"][0] / 487 / 487) / np.sqrt(2 * np.pi)
     assert 0.05 < sig_gm < 1.0
+
+
+def test_misfit_and_likelihood_pinned_by_reference_output():
+    """Reference-produced known answers for MCsub.jl:169-182.  model.jld (the reference's own output of a 487-ray run) stores ptS,
+    tS, phi and likelihood of 100 models; phi / sum((ptS - tS)^2) = 25 for all of them, i.e. allSig = 0.2 for every ray.  With
+    that, the oracle's misfit -- the function orc_evaluate itself calls, and its NumPy twin -- reproduces all 100 stored phi
+    BIT FOR BIT -- operation order ((d*d)*1.0)/(sig*sig) and the left-to-right loop over the rays (:170-172) are the reference's
+    -- and the likelihood constant to 1e-13 (the discarded second line, SURVEY F5, confirmed by a reference-produced value)."""
+    import oracle as O
+    import oracle_np as ON
+    m = np.load(os.path.join(GOLDEN, "model_jld.npz"))
+    assert m["ptS"].dtype == np.float64 and m["ptS"].shape == (100, 487)
+    tS, sig = m["tS"], np.full(487, 0.2)
+    for i in range(100):
+        phi_c, like_c, lg = O.misfit(m["ptS"][i], tS, sig)
+        assert phi_c == m["phi"][i], (i, phi_c, m["phi"][i])            # bit for bit
+        # the likelihood is a Julia `sum(...)` (:179) whose SIMD order is unspecified: 487 equal terms, so any order agrees to a few ulp
+        assert abs(like_c - m["likelihood"][i]) <= 1e-13 * like_c, (like_c, m["likelihood"][i])
+        assert abs(lg - (like_c / 487 - 0.5 * phi_c)) < 1e-9 * abs(lg)
+        if i % 10 == 0:
+            phi_n, like_n = ON.misfit(m["ptS"][i], tS, sig)
+            assert phi_n == m["phi"][i] and like_n == like_c
+    # sigma is identified by the data, not assumed: a 1-ulp different sigma already breaks the equality
+    assert O.misfit(m["ptS"][0], tS, np.full(487, np.nextafter(0.2, 1.0)))[0] != m["phi"][0]
