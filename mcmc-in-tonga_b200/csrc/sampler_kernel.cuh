@@ -90,6 +90,16 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 #endif
 constexpr int SQ_CAP = 64;    // orphan-word queue entries per warp
 constexpr int ZLUT_TAG = 128; // entries 128..255 of the zeta look-up table: tagged bytes (all hold the implicit new owner's value)
+// Visits a warp's blocks b = warp + NW * bi whose bit is set in `mask` (bi < 32), then every bi >= 32 (not covered by the mask).
+struct BlockIter {
+    uint32_t rem;
+    int hi;
+    __device__ __forceinline__ explicit BlockIter(uint32_t mask) : rem(mask), hi(32) {}
+    __device__ __forceinline__ int next() {
+        if (rem) { const int b = __ffs((int)rem) - 1; rem &= rem - 1u; return b; }
+        return hi++;
+    }
+};
 struct WarpProp {  // the proposal's scalars that are only needed again at the acceptance / commit: one copy per warp (same values)
     double u, aux, zeta, ox, oy, oz, zold, cx, cy, cz;
 };
@@ -348,11 +358,13 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
     const float ta2 = h.ta2, tb = h.tb;
     const bool exact_only = h.exact_only != 0;
     const int Kr = (K + 1) & ~1;  // nuclei are visited in pairs; slot K (if any) holds +inf
-    int qn = 0, bi = 0, blk = warp;
+    int qn = 0;
+    BlockIter iter(blkmask);  // only the blocks that hold orphans
 #pragma unroll 1
     for (;;) {
+        const int blk = warp + NW * iter.next();
         const bool last = blk >= nBlocks;
-        if (!last && (bi >= 32 || ((blkmask >> bi) & 1u))) {
+        if (!last) {
             const int w = blk * 32 + lane;
             const bool has = ((s_mask[w >> 3] >> (sub * 4)) & 0xFu) != 0u;
             const uint32_t m = __ballot_sync(FULL, has);
@@ -428,7 +440,6 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
             __syncwarp();
         }
         if (last) break;
-        blk += NW; bi++;
     }
 }
 
@@ -594,10 +605,9 @@ static __device__ __noinline__ void phase_f_mask(const int accepted, const int p
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(tg_smem + h.o_mask);
     const float *s_fx = reinterpret_cast<const float *>(tg_smem + h.o_nucf), *s_fy = s_fx + h.KC, *s_fz = s_fy + h.KC;
     const int nBlocks = h.nBlocks;
-    int bi = 0;
+    BlockIter iter(blkmask);
 #pragma unroll 1
-    for (int blk = warp; blk < nBlocks; blk += NW, bi++) {
-        if (bi < 32 && !((blkmask >> bi) & 1u)) continue;
+    for (int blk = warp + NW * iter.next(); blk < nBlocks; blk = warp + NW * iter.next()) {
         const int w = blk * 32 + lane;
         const uint32_t mb = (s_mask[w >> 3] >> (sub * 4)) & 0xFu;
         __syncwarp();
@@ -628,10 +638,9 @@ static __device__ __noinline__ void phase_f_tags(const int accepted, const uint3
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *s_own32 = reinterpret_cast<uint32_t *>(tg_smem + h.o_owner);
     const int nBlocks = h.nBlocks;
-    int bi = 0;
+    BlockIter iter(tagmask);
 #pragma unroll 1
-    for (int blk = warp; blk < nBlocks; blk += NW, bi++) {
-        if (bi < 32 && !((tagmask >> bi) & 1u)) continue;
+    for (int blk = warp + NW * iter.next(); blk < nBlocks; blk = warp + NW * iter.next()) {
         const int w = blk * 32 + lane;
         const uint32_t ow = s_own32[w], t = ow & 0x80808080u;
         if (t) {
