@@ -67,27 +67,9 @@ struct SamplerArgs {
     int32_t *hist_action, *hist_accept, *hist_next;
 };
 
-#ifndef TG_B1_PINGPONG
-#define TG_B1_PINGPONG 0
-#endif
-#ifndef TG_C_EXACT
-#define TG_C_EXACT 0
-#endif
-#ifndef TG_B1_PREFETCH
-#define TG_B1_PREFETCH 0
-#endif
-#ifndef TG_C_XPF
-#define TG_C_XPF 0
-#endif
-#if TG_B1_PREFETCH
-// the owner-distance cache goes through L1 (plain loads / stores: a chain lives on one SM) so that prefetch.global.L1 can bring the next block in
-#define TG_DC_LOAD(p) (*(p))
-#define TG_DC_STORE(p, v) (*(p) = (v))
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#else
+// the owner-distance cache is read and written past L1 (ld.cg / st.cg): 67 KB per chain, streamed once per birth / move
 #define TG_DC_LOAD(p) __ldcg(p)
 #define TG_DC_STORE(p, v) __stcg(p, v)
-#endif
 constexpr int SQ_CAP = 64;    // orphan-word queue entries per warp
 constexpr int ZLUT_TAG = 128; // entries 128..255 of the zeta look-up table: tagged bytes (all hold the implicit new owner's value)
 // Visits a warp's blocks b = warp + NW * bi whose bit is set in `mask` (bi < 32), then every bi >= 32 (not covered by the mask).
@@ -282,30 +264,13 @@ static __device__ __noinline__ uint2 phase_b1_switch(const int pidx, const float
     };
     const float4 *gx = reinterpret_cast<const float4 *>(h.pxf) + lane, *gy = reinterpret_cast<const float4 *>(h.pyf) + lane,
                  *gz = reinterpret_cast<const float4 *>(h.pzf) + lane, *gd = reinterpret_cast<const float4 *>(h.dcache) + lane;
-    if (TG_B1_PINGPONG == 1 || (TG_B1_PINGPONG == 2 && ACT == 1)) {  // compile-time
-        // two register sets: the loads of block b + NW are in flight while block b is screened (the loads are unconditional: the
-        // arrays carry TG_PT_SLACK elements of slack)
-        float4 ax = __ldg(gx + warp * 32), ay = __ldg(gy + warp * 32), az = __ldg(gz + warp * 32), ad = TG_DC_LOAD(gd + warp * 32);
-        int bi = 0;
+    // One block per step; the other warps of the SM (7 chains x 4 warps) hide the L2 latency.  Measured and rejected (profiles/README.md,
+    // round 2): a two-register-set ping-pong (birth only: 26.9, both actions: 24.2 against 27.4 M/s -- the second set costs spills)
+    // and prefetch.global.L1 of the next block (27.3 / 26.9 M/s with the cache going through L1).
+    int bi = 0;
 #pragma unroll 1
-        for (int blk = warp; blk < nBlocks; blk += 2 * NW, bi += 2) {
-            const float4 bx = __ldg(gx + (blk + NW) * 32), by = __ldg(gy + (blk + NW) * 32), bz = __ldg(gz + (blk + NW) * 32), bd = TG_DC_LOAD(gd + (blk + NW) * 32);
-            body(blk, bi, ax, ay, az, ad);
-            ax = __ldg(gx + (blk + 2 * NW) * 32); ay = __ldg(gy + (blk + 2 * NW) * 32); az = __ldg(gz + (blk + 2 * NW) * 32); ad = TG_DC_LOAD(gd + (blk + 2 * NW) * 32);
-            if (blk + NW < nBlocks) body(blk + NW, bi + 1, bx, by, bz, bd);
-        }
-    } else {
-        // one block per step; the other warps of the SM (7 chains x 4 warps) hide the L2 latency
-        int bi = 0;
-#pragma unroll 1
-        for (int blk = warp; blk < nBlocks; blk += NW, bi++) {
-#if TG_B1_PREFETCH
-            const int nb = (blk + TG_B1_PREFETCH * NW) * 32;  // (TG_PT_SLACK covers the run past the end)
-            prefetch_l1(gx + nb); prefetch_l1(gy + nb); prefetch_l1(gz + nb); prefetch_l1(gd + nb);
-#endif
-            body(blk, bi, __ldg(gx + blk * 32), __ldg(gy + blk * 32), __ldg(gz + blk * 32), TG_DC_LOAD(gd + blk * 32));
-        }
-    }
+    for (int blk = warp; blk < nBlocks; blk += NW, bi++)
+        body(blk, bi, __ldg(gx + blk * 32), __ldg(gy + blk * 32), __ldg(gz + blk * 32), TG_DC_LOAD(gd + blk * 32));
     return make_uint2(tagmask, blkmask);
 }
 
@@ -473,63 +438,6 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
     if (dirty) s_perm[rank] = (uint8_t)lane;
     __syncwarp();
     double tnv = 0.0;
-#if TG_C_XPF
-    // The first round's dt of group t+1 (the only global loads of the loop: one L2 round trip) is requested while group t is summed.
-    uint32_t inf_n = 0u;
-    double pn[4] = {0.0, 0.0, 0.0, 0.0};
-    if (cnt > 0) {
-        inf_n = __shfl_sync(FULL, info, grp < cnt ? (int)s_perm[grp] : 0);
-        const double *p0 = h.dt + (inf_n & 0x3FFFFu) + sub;
-#pragma unroll
-        for (int u = 0; u < 4; u++) pn[u] = __ldg(p0 + 8 * u);
-    }
-#pragma unroll 1
-    for (int t = 0; 4 * t < cnt; t++) {  // 4 touched rays at a time, 8 lanes each
-        const bool on = 4 * t + grp < cnt;
-        const uint32_t inf = inf_n;
-        const int tq0 = (int)(inf & 0x3FFFFu), tnp = on ? (int)(inf >> 18) : 0;
-        const int nseg = tnp > 1 ? tnp - 1 : 0;
-        const int trip = __reduce_max_sync(FULL, (nseg + 7) >> 3);
-        const uint8_t *ow = s_owner + tq0 + sub;
-        const double *dtp = h.dt + tq0 + sub;
-        const int nl = nseg - sub;  // this lane's segments: j = sub + 8 k < nseg  <=>  8 k < nl
-        double acc = 0.0;
-        double dn[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) dn[u] = pn[u];
-        if (4 * (t + 1) < cnt) {  // warp-uniform
-            const int e1 = 4 * (t + 1) + grp;
-            inf_n = __shfl_sync(FULL, info, e1 < cnt ? (int)s_perm[e1] : 0);
-            const double *p1 = h.dt + (inf_n & 0x3FFFFu) + sub;
-#pragma unroll
-            for (int u = 0; u < 4; u++) pn[u] = __ldg(p1 + 8 * u);
-        }
-#pragma unroll 1
-        for (int k0 = 0; k0 < trip; k0 += 4, ow += 32) {
-            double d[4], za[4], zb[4];
-            uint32_t oa[4], ob[4];
-            dtp += 32;
-#pragma unroll
-            for (int u = 0; u < 4; u++) { d[u] = dn[u]; oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
-            if (k0 + 4 < trip) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const double term = __dmul_rn(d[u], div1000_exact(__dadd_rn(za[u], zb[u])));
-                if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
-            }
-        }
-        acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
-        acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
-        acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
-        const double v = __shfl_sync(FULL, acc, (rank & 3) << 3);
-        if (dirty && (rank >> 2) == t) tnv = v;
-    }
-#else
 #pragma unroll 1
     for (int t = 0; 4 * t < cnt; t++) {  // 4 touched rays at a time, 8 lanes each
         const int e = 4 * t + grp;
@@ -546,6 +454,9 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         const double *dtp = h.dt + tq0 + sub;
         const int nl = nseg - sub;  // this lane's segments: j = sub + 8 k < nseg  <=>  8 k < nl
         double acc = 0.0;
+        // Measured and rejected (profiles/README.md, round 2): skipping the passes beyond `trip` by warp-uniform branches (Tonga's rays
+        // need 2, 3, 5, 9 or 17 passes; -20 % of this loop's instructions, 27.2 against 27.4 M/s) and requesting the first round's dt
+        // of the NEXT group of rays while this one is summed (phase C 22.1 k -> 19.7 k cycles, the other phases grow by as much).
         double dn[4];  // dt of the next round: the only global (L2) loads of the loop, requested one round ahead
 #pragma unroll
         for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
@@ -560,26 +471,11 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
             for (int u = 0; u < 4; u++) { d[u] = dn[u]; dn[u] = __ldg(dtp + 8 * u); oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
 #pragma unroll
             for (int u = 0; u < 4; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
-#if TG_C_EXACT
-            // the passes beyond `trip` are skipped by warp-uniform branches (Tonga: rays of 2, 3, 5, 9, 17 passes)
-            const int np = trip - k0;
-#define TG_C_PASS(u) { const double term = __dmul_rn(d[u], div1000_exact(__dadd_rn(za[u], zb[u]))); if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term); }
-            TG_C_PASS(0)
-            if (np > 1) {
-                TG_C_PASS(1)
-                if (np > 2) {
-                    TG_C_PASS(2)
-                    if (np > 3) TG_C_PASS(3)
-                }
-            }
-#undef TG_C_PASS
-#else
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const double term = __dmul_rn(d[u], div1000_exact(__dadd_rn(za[u], zb[u])));
                 if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
             }
-#endif
         }
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
         acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
@@ -587,7 +483,6 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         const double v = __shfl_sync(FULL, acc, (rank & 3) << 3);
         if (dirty && (rank >> 2) == t) tnv = v;
     }
-#endif
     __syncwarp();
     CRes r;
     r.tn = tnv; r.dm = dm;
