@@ -343,7 +343,7 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
                 const int w = (int)s_queue[qn - cnt + lane];
                 const uint32_t mb = (s_mask[w >> 3] >> ((w & 7) * 4)) & 0xFu;
                 const uint32_t ow = s_own32[w];
-                uint32_t nb[4] = {TG_OWNER_NONE, TG_OWNER_NONE, TG_OWNER_NONE, TG_OWNER_NONE};
+                uint32_t nbw = TG_OWNER_NONE * 0x01010101u;  // the 4 new owners, one byte each (a register, not an indexed array: no local memory)
                 uint32_t need = exact_only ? mb : 0u;
                 if (!exact_only) {
                     const float4 X = __ldg(reinterpret_cast<const float4 *>(h.pxf) + w), Y = __ldg(reinterpret_cast<const float4 *>(h.pyf) + w),
@@ -378,7 +378,7 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
                     for (int q = 0; q < 4; q++) {
                         const float f1 = __uint_as_float(d1[q] & 0xFFFFFF80u), f2 = __uint_as_float(d2[q] & 0xFFFFFF80u);
                         const float tol = fmaf(ta2, f1 + f2, tb);
-                        nb[q] = d1[q] & 0x7Fu;
+                        nbw = (nbw & ~(0xFFu << (8 * q))) | ((d1[q] & 0x7Fu) << (8 * q));
                         if (!(f2 - f1 > tol)) need |= 1u << q;  // ambiguous (also: nothing within the 1e9 threshold, NaN coordinates)
                     }
                     need &= mb;
@@ -389,15 +389,15 @@ static __device__ __noinline__ void phase_b2(const int act, const int pidx, cons
                     const double *s_nx = reinterpret_cast<const double *>(tg_smem + h.o_nuc), *s_ny = s_nx + h.KC, *s_nz = s_ny + h.KC;
 #pragma unroll 1
                     for (int q = 0; q < 4; q++)
-                        if ((need >> q) & 1u) nb[q] = (uint32_t)rescan_point(h.px, h.py, h.pz, s_nx, s_ny, s_nz, K, skip, mvi, cx, cy, cz, 4 * w + q);
+                        if ((need >> q) & 1u) {
+                            const uint32_t r = (uint32_t)rescan_point(h.px, h.py, h.pz, s_nx, s_ny, s_nz, K, skip, mvi, cx, cy, cz, 4 * w + q);
+                            nbw = (nbw & ~(0xFFu << (8 * q))) | (r << (8 * q));
+                        }
                 }
-                uint32_t nw = ow, chg = 0u;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if ((mb >> q) & 1u) {
-                        nw = (nw & ~(0xFFu << (8 * q))) | (nb[q] << (8 * q));  // death: old numbering, renumbered on accept
-                        chg |= (act == 2 || (int)nb[q] != pidx) ? 1u : 0u;   // a point that stays with the moved nucleus keeps its zeta
-                    }
+                const uint32_t m8 = ((mb & 1u) * 0xFFu) | ((mb & 2u) * (0xFF00u >> 1)) | ((mb & 4u) * (0xFF0000u >> 2)) | ((mb & 8u) * (0xFF000000u >> 3));
+                const uint32_t nw = (ow & ~m8) | (nbw & m8);  // death: old numbering, renumbered on accept
+                // a point that stays with the moved nucleus keeps its zeta
+                const bool chg = (act == 2) ? true : (((nbw ^ ((uint32_t)pidx * 0x01010101u)) & m8) != 0u);
                 s_own32[w] = nw;
                 if (chg) atomicOr(&s_dirtyw[w >> 5], 1u << (w & 31));
             }
@@ -454,9 +454,13 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         const double *dtp = h.dt + tq0 + sub;
         const int nl = nseg - sub;  // this lane's segments: j = sub + 8 k < nseg  <=>  8 k < nl
         double acc = 0.0;
-        // Measured and rejected (profiles/README.md, round 2): skipping the passes beyond `trip` by warp-uniform branches (Tonga's rays
-        // need 2, 3, 5, 9 or 17 passes; -20 % of this loop's instructions, 27.2 against 27.4 M/s) and requesting the first round's dt
-        // of the NEXT group of rays while this one is summed (phase C 22.1 k -> 19.7 k cycles, the other phases grow by as much).
+        // This loop issues 60 % of the kernel's shared-memory wavefronts and global L1 requests (ncu source page, tools/ncu_lsu.py), and
+        // the L1 / LSU data pipe is the busiest unit of the SM (66 %): loads that are not issued count for more than the arithmetic
+        // they feed.  Measured and rejected (profiles/README.md, round 2): skipping the ARITHMETIC of the passes beyond `trip`
+        // (-20 % of the loop's instructions, no gain); guarding their shared-memory loads by warp-uniform branches (the staging
+        // breaks up: 27.2 against 28.4 M/s); separate code for the last 1..3 passes (phase C 22.0 k -> 18.5 k cycles, but the build
+        // falls into the slow regime: 22.5 M/s); the first round's dt of the NEXT group requested while this one is summed (phase C
+        // -11 %, the other phases grow by as much).
         double dn[4];  // dt of the next round: the only global (L2) loads of the loop, requested one round ahead
 #pragma unroll
         for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
@@ -468,7 +472,11 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
             uint32_t oa[4], ob[4];
             dtp += 32;
 #pragma unroll
-            for (int u = 0; u < 4; u++) { d[u] = dn[u]; dn[u] = __ldg(dtp + 8 * u); oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
+            for (int u = 0; u < 4; u++) { d[u] = dn[u]; oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
+            if (k0 + 4 < trip) {  // warp-uniform: the next round's dt only if there is a next round (phase C issues 60 % of the kernel's global L1 requests)
+#pragma unroll
+                for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
 #pragma unroll
