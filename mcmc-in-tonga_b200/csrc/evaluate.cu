@@ -124,7 +124,6 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
 
     // ---- phase 1: owners of the tile's points (v_nearest, MCsub.jl:247-263)
     const int npts = tile.p1 - tile.p0;
-    const uint32_t INF_PACK = 0x7f800000u | 0x7Fu;
     for (int base = 0; base < npts; base += EVAL_THREADS * EVAL_PPT) {
         int pidx[EVAL_PPT];
         bool in[EVAL_PPT];
@@ -226,7 +225,37 @@ tg_eval_kernel(const Tile *__restrict__ tiles, int Kcap, const int32_t *__restri
     }
     __syncthreads();
     // ---- the queue: exact FP64 re-scan (MCsub.jl:252-259: strict <, lowest index wins ties, 1e9 start value)
+    // A short queue (the screened mode: a handful of near ties per tile) is re-scanned ONE WARP PER POINT -- lane l takes the nuclei
+    // l, l + 32, ..., then the warp picks the smallest distance, lowest index on exact ties -- so that a few points do not keep the
+    // whole CTA waiting at the barrier below for one thread's K-long serial loop; a long queue (exact-only mode) one thread per point.
     const int nq = s_nq[0];
+    if (nq < 2 * EVAL_THREADS) {
+        for (int qi = warp; qi < nq; qi += EVAL_THREADS / 32) {
+            const int j = s_queue[qi];
+            const int64_t p = tile.p0 + j;
+            const double x = px[p], y = py[p], z = pz[p];
+            double best = 1e9;  // mdist = 1e9, MCsub.jl:250
+            int b = 0x7fffffff;
+            for (int i = lane; i < K; i += 32) {
+                const double d = dist2_exact(s_nx[i], s_ny[i], s_nz[i], x, y, z);
+                if (d < best) { best = d; b = i; }  // ascending i within the lane: strict < keeps the lowest index
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, b, off);
+                if (ob < best || (ob == best && oi < b)) { best = ob; b = oi; }
+            }
+            if (b == 0x7fffffff) b = -1;  // nothing within the 1e9 threshold
+            if (lane == 0) {
+                s_owner[j] = b < 0 ? (uint16_t)TG_NONE16 : (uint16_t)b;
+                if (owners32) owners32[(size_t)model * P + point_orig[p]] = b;
+                if (owners8) owners8[(size_t)model * Ppad + p] = b < 0 ? (uint8_t)TG_OWNER_NONE : (uint8_t)b;
+                if (owners16) owners16[(size_t)model * Ppad + p] = s_owner[j];
+                if (dmin32) dmin32[(size_t)model * Ppad + p] = b < 0 ? 1e9f : (float)best;
+            }
+        }
+    } else
     for (int qi = tid; qi < nq; qi += EVAL_THREADS) {
         const int j = s_queue[qi];
         const int64_t p = tile.p0 + j;
