@@ -92,6 +92,21 @@ function evaluate(model, dataStruct, TD_parameters)
     return model, dataStruct, 1
 end
 
+# ---- the misfit alone, MCsub.jl:169-173: phi of given t* vectors (columns of ptS, one per model) against dataStruct.tS / allSig,
+# computed by the device kernel every evaluate / proposal ends in.  With the models of a stored reference run (`model.jld`) this
+# checks the library against numbers the reference itself produced: misfit(hcat((m.ptS for m in models)...), ds, p) ≈ [m.phi ...].
+function misfit(ptS::AbstractMatrix{Float64}, dataStruct, TD_parameters)
+    ctx = context(dataStruct, TD_parameters)
+    size(ptS, 1) == length(dataStruct.tS) || error("misfit: ptS must have one row per datum")
+    pts = Matrix{Float64}(ptS)                 # column-major R x n == the library's [n][R]
+    phi = Vector{Float64}(undef, size(pts, 2))
+    GC.@preserve pts phi begin
+        check(ccall((:tonga_misfit, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx, Int32(size(pts, 2)), pts, C_NULL, phi))
+    end
+    return phi
+end
+
 # ---- Interpolation / v_nearest, MCsub.jl:306-336, 247-263 -----------------------------------------------------------
 function interpolate(mx, my, mz, mv, X, Y, Z)
     Xv = collect(Float64, X); Yv = collect(Float64, Y); Zv = collect(Float64, Z)
