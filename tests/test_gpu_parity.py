@@ -603,6 +603,12 @@ def test_abi_error_paths_and_helpers(tonga):
     with pytest.raises(_lib.TongaError) as e:
         ctx.evaluate_batch(np.array([9], np.int32), np.zeros((1, 4, 4)))
     assert e.value.code == -1
+    # misfit: NULL arrays -> TONGA_ERR_ARG; nothing to do for 0 models; the misfit of the model's own t* is its phi
+    lib = _lib.load()
+    assert lib.tonga_misfit(ctx._h, 1, None, None, None) == -1 and b"tonga_misfit" in lib.tonga_last_error()
+    assert lib.tonga_misfit(ctx._h, 0, C.cast(1, C.POINTER(C.c_double)), None, C.cast(1, C.POINTER(C.c_double))) == 0
+    g = ctx.evaluate_batch(np.array([3], np.int32), np.array([[[10.0, 200.0, 400.0], [5.0, 100.0, 300.0], [50.0, 150.0, 400.0], [5.0, 20.0, 40.0]]]))
+    assert ctx.misfit(g["ptS"])[0] == g["phi"][0]
     # chains: run before start models -> TONGA_ERR_STATE; K above capacity -> TONGA_ERR_CAPACITY
     ch = api.Chains(ctx, 2, hist_cap=0)
     with pytest.raises(_lib.TongaError) as e:
