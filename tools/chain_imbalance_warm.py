@@ -20,3 +20,11 @@ print("all chains", {n: int(v) for n, v in zip(names, cyc[:, :9].mean(0) / 1000)
 for lab, sel in (("fastest 10%", o[:102]), ("middle 10%", o[460:562]), ("slowest 10%", o[-102:])):
     print(lab, "K mean %.1f" % K[sel].mean(), {n: int(v) for n, v in zip(names, cyc[sel, :9].mean(0) / 1000)}, "total/iter %d" % (tot[sel].mean() / 1000))
 print("launch length in cycles / slowest chain:", ms * 1e-3 * 1.965e9 / tot.max())
+b, sm = cyc[:, 14].astype(int), cyc[:, 15].astype(int)
+o = np.argsort(b)
+print("SM of CTA 0..15:", sm[o][:16], " CTA 148..163:", sm[o][148:164], " CTA 296..311:", sm[o][296:312])
+print("chains per SM: min %d max %d; SMs used %d" % (np.bincount(sm).min(), np.bincount(sm).max(), len(np.unique(sm))))
+same = np.mean([sm[o][i] == sm[o][i + 148] for i in range(1024 - 148)]); print("fraction of CTAs i, i+148 on the same SM: %.3f" % same)
+# per-SM load and finish
+tot_sm = np.bincount(sm, weights=tot); mx_sm = np.array([tot[sm == s].max() if (sm == s).any() else 0 for s in range(sm.max() + 1)])
+print("per-SM sum of chain cycles: max/mean %.3f ; per-SM slowest chain: max/mean %.3f" % (tot_sm.max() / tot_sm[tot_sm > 0].mean(), mx_sm.max() / mx_sm[mx_sm > 0].mean()))
