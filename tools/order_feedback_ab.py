@@ -11,15 +11,14 @@ ctx = Context(ds, p)
 K0, c0 = warm["K"][:1024].astype(np.int32), warm["cells"][:1024]
 res = {}
 for rep in range(2):
-    for fb, lead in (("0", "0"), ("1", "0")) + tuple(("1", l) for l in os.environ.get("PACE_LEADS", "").split(",") if l):
+    for fb in ("0", "1"):
         os.environ["TONGA_ORDER_FEEDBACK"] = fb
-        os.environ["TONGA_PACE_LEAD"] = lead
         ch = Chains(ctx, 1024, seed=20260000)
         ms = []
         for step in range(6):
             ch.reset(); ch.set_models(K0, c0); ch.run(1000); ms.append(ch.last_kernel_ms())
         st = ch.state(want_ptS=False)
         res[fb] = (st["K"].copy(), st["phi"].copy())
-        print("feedback", fb, "pace lead", lead, ["%.2f" % m for m in ms], "-> %.2f M/s (median of the last 4)" % (1024 * 1000 / np.median(ms[2:]) / 1e3), "verify", ch.verify())
+        print("feedback", fb, ["%.2f" % m for m in ms], "-> %.2f M/s (median of the last 4)" % (1024 * 1000 / np.median(ms[2:]) / 1e3), "verify", ch.verify())
         ch.close()
 print("final states identical with / without feedback:", bool((res["0"][0] == res["1"][0]).all() and (res["0"][1] == res["1"][1]).all()))
