@@ -257,6 +257,23 @@ __global__ void tg_copy_tstar_kernel(int n, int R, int Rp, const int32_t *ray_or
     }
 }
 
+// chain state -> the caller's layout, packed on the device so that tonga_chains_get_state is a few straight device-to-host copies:
+// cells [n][4][KC] -> [n][4][Kcap] with zeros behind the K valid nuclei; t* rows (sorted ray order, padded) -> [n][R] in the caller's order
+__global__ void tg_pack_cells_kernel(int n, int KC, int Kcap, const int32_t *K, const double *src, double *dst) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < (size_t)n * 4 * Kcap) {
+        const size_t row = i / Kcap, k = i % Kcap;  // row = chain * 4 + axis
+        dst[i] = ((int)k < K[row >> 2] && (int)k < KC) ? src[row * KC + k] : 0.0;
+    }
+}
+__global__ void tg_unsort_tstar_kernel(int n, int R, int Rp, const int32_t *ray_orig, const double *src /* [n][Rp] */, double *dst /* [n][R] */) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < (size_t)n * R) {
+        const size_t c = i / R, rs = i % R;
+        dst[c * R + ray_orig[rs]] = src[c * Rp + rs];
+    }
+}
+
 }  // namespace tg
 
 // ================================================================================================== host side
@@ -1064,27 +1081,39 @@ extern "C" int tonga_chains_get_state(tonga_chains *ch, int32_t Kcap, int32_t *K
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
     TG_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t n = (size_t)ch->n, KC = (size_t)ch->KC, R = (size_t)ctx->R, Rp = (size_t)ch->Rp, P = (size_t)ctx->P, Pp = (size_t)ctx->Ppad;
+    const size_t n = (size_t)ch->n, R = (size_t)ctx->R, P = (size_t)ctx->P, Pp = (size_t)ctx->Ppad;
+    // cells and t* are brought into the caller's layout on the device (scratch), then everything is copied straight into the caller's
+    // buffers on the stream -- at PCIe speed when they are page-locked (tonga_host_alloc) -- with one synchronisation at the end
+    cudaStream_t s = ctx->stream;
     std::vector<int32_t> hK(n);
-    TG_CUDA(cudaMemcpy(hK.data(), ch->d_K, 4 * n, cudaMemcpyDeviceToHost));
-    if (K) std::memcpy(K, hK.data(), 4 * n);
+    TG_CUDA(cudaMemcpyAsync(hK.data(), ch->d_K, 4 * n, cudaMemcpyDeviceToHost, s));
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_c = 0, o_t = o_c + (cells ? al(8 * n * 4 * (size_t)(Kcap > 0 ? Kcap : 1)) : 0), total = o_t + (ptS ? al(8 * n * (R ? R : 1)) : 0);
+    if (cells && Kcap < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_get_state: Kcap < 1");
+    if (total) {
+        int rc = tg::ensure_scratch(ctx, total);
+        if (rc != TONGA_OK) return rc;
+    }
+    char *sc = (char *)ctx->d_scratch;
     if (cells) {
-        if (Kcap < 1) return tg::fail(TONGA_ERR_ARG, "tonga_chains_get_state: Kcap < 1");
-        std::vector<double> hc(n * 4 * KC);
-        TG_CUDA(cudaMemcpy(hc.data(), ch->d_cells, 8 * n * 4 * KC, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; i++) {
-            if (hK[i] > Kcap) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_get_state: Kcap smaller than a chain's nCells");
-            for (int a = 0; a < 4; a++) std::memcpy(cells + (i * 4 + a) * (size_t)Kcap, &hc[(i * 4 + a) * KC], 8 * (size_t)hK[i]);
-        }
+        const size_t tot = n * 4 * (size_t)Kcap;
+        tg::tg_pack_cells_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ch->n, ch->KC, Kcap, ch->d_K, ch->d_cells, (double *)(sc + o_c));
+        TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaMemcpyAsync(cells, sc + o_c, 8 * tot, cudaMemcpyDeviceToHost, s));
     }
-    if (phi) TG_CUDA(cudaMemcpy(phi, ch->d_phi, 8 * n, cudaMemcpyDeviceToHost));
-    if (noise) TG_CUDA(cudaMemcpy(noise, ch->d_noise, 8 * n, cudaMemcpyDeviceToHost));
-    if (ptS) {  // device rows are in sorted ray order
-        std::vector<double> ht(n * Rp);
-        TG_CUDA(cudaMemcpy(ht.data(), ch->d_tstar, 8 * n * Rp, cudaMemcpyDeviceToHost));
+    if (phi) TG_CUDA(cudaMemcpyAsync(phi, ch->d_phi, 8 * n, cudaMemcpyDeviceToHost, s));
+    if (noise) TG_CUDA(cudaMemcpyAsync(noise, ch->d_noise, 8 * n, cudaMemcpyDeviceToHost, s));
+    if (ptS && R) {  // device rows are in sorted ray order
+        const size_t tot = n * R;
+        tg::tg_unsort_tstar_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ch->n, ctx->R, ch->Rp, ctx->d_ray_orig, ch->d_tstar, (double *)(sc + o_t));
+        TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaMemcpyAsync(ptS, sc + o_t, 8 * tot, cudaMemcpyDeviceToHost, s));
+    }
+    TG_CUDA(cudaStreamSynchronize(s));
+    if (K) std::memcpy(K, hK.data(), 4 * n);
+    if (cells)
         for (size_t i = 0; i < n; i++)
-            for (size_t rs = 0; rs < R; rs++) ptS[i * R + (size_t)ctx->h_ray_orig[rs]] = ht[i * Rp + rs];
-    }
+            if (hK[i] > Kcap) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_get_state: Kcap smaller than a chain's nCells");
     if (owners && ch->streamed) {
         std::vector<uint16_t> ho(n * Pp);
         TG_CUDA(cudaMemcpy(ho.data(), ch->d_owner16, 2 * n * Pp, cudaMemcpyDeviceToHost));
