@@ -258,12 +258,12 @@ __global__ void tg_copy_tstar_kernel(int n, int R, int Rp, const int32_t *ray_or
 }
 
 // chain state -> the caller's layout, packed on the device so that tonga_chains_get_state is a few straight device-to-host copies:
-// cells [n][4][KC] -> [n][4][Kcap] with zeros behind the K valid nuclei; t* rows (sorted ray order, padded) -> [n][R] in the caller's order
-__global__ void tg_pack_cells_kernel(int n, int KC, int Kcap, const int32_t *K, const double *src, double *dst) {
+// cells [n][4][KCsrc] -> [n][4][KCdst] with zeros behind the K valid nuclei (both directions: get_state and set_models); t* rows (sorted ray order, padded) -> [n][R] in the caller's order
+__global__ void tg_pack_cells_kernel(int n, int KCsrc, int KCdst, const int32_t *K, const double *src, double *dst) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < (size_t)n * 4 * Kcap) {
-        const size_t row = i / Kcap, k = i % Kcap;  // row = chain * 4 + axis
-        dst[i] = ((int)k < K[row >> 2] && (int)k < KC) ? src[row * KC + k] : 0.0;
+    if (i < (size_t)n * 4 * KCdst) {
+        const size_t row = i / KCdst, k = i % KCdst;  // row = chain * 4 + axis
+        dst[i] = ((int)k < K[row >> 2] && (int)k < KCsrc) ? src[row * KCsrc + k] : 0.0;
     }
 }
 __global__ void tg_unsort_tstar_kernel(int n, int R, int Rp, const int32_t *ray_orig, const double *src /* [n][Rp] */, double *dst /* [n][R] */) {
@@ -662,12 +662,21 @@ extern "C" int tonga_chains_set_models(tonga_chains *ch, int32_t Kcap, const int
             return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_set_models: K[i] outside [1, min(Kcap, " + std::to_string(KC) + ")]");
     std::lock_guard<std::mutex> lk(ctx->mu);
     TG_CUDA(cudaSetDevice(ctx->device));
-    std::vector<double> packed(n * 4 * KC, 0.0);
-    for (size_t i = 0; i < n; i++)
-        for (int a = 0; a < 4; a++) std::memcpy(&packed[(i * 4 + a) * KC], cells + (i * 4 + a) * (size_t)Kcap, 8 * (size_t)K[i]);
+    // the caller's [n][4][Kcap] block goes to the device as it is (at PCIe speed from page-locked memory) and is brought into the chains'
+    // [n][4][KC] layout there, zeros behind the K valid nuclei
     cudaStream_t s = ctx->stream;
+    TG_CUDA(cudaStreamSynchronize(s));  // (the scratch buffer may still be read by an earlier call)
+    {
+        int rc0 = tg::ensure_scratch(ctx, 8 * n * 4 * (size_t)Kcap);
+        if (rc0 != TONGA_OK) return rc0;
+    }
     TG_CUDA(cudaMemcpyAsync(ch->d_K, K, 4 * n, cudaMemcpyHostToDevice, s));
-    TG_CUDA(cudaMemcpyAsync(ch->d_cells, packed.data(), 8 * n * 4 * KC, cudaMemcpyHostToDevice, s));
+    TG_CUDA(cudaMemcpyAsync(ctx->d_scratch, cells, 8 * n * 4 * (size_t)Kcap, cudaMemcpyHostToDevice, s));
+    {
+        const size_t tot = n * 4 * KC;
+        tg::tg_pack_cells_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ch->n, Kcap, ch->KC, ch->d_K, (const double *)ctx->d_scratch, ch->d_cells);
+        TG_CUDA(cudaGetLastError());
+    }
     std::vector<double> nz(n, 1.0);
     if (noise) std::memcpy(nz.data(), noise, 8 * n);
     TG_CUDA(cudaMemcpyAsync(ch->d_noise, nz.data(), 8 * n, cudaMemcpyHostToDevice, s));
