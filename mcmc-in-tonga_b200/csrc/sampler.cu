@@ -13,9 +13,6 @@
 // The same canonical t* / phi reductions are used by evaluate.cu, so incremental state == full evaluate bit for bit
 // (tonga_chains_verify checks that on the device).
 #include <algorithm>
-#include <functional>
-#include <queue>
-#include <utility>
 #include <vector>
 #include <cmath>
 #include <cstdlib>
@@ -85,39 +82,9 @@ __global__ void tg_build_starting_kernel(int n, int KC, tonga_params pm, unsigne
 // CTA -> chain order of the resident sampler.  A chain's cost per iteration falls with its nCells (fewer, larger cells: more
 // points change owner, more rays are re-integrated), and the launch lasts as long as its slowest SM.  CTAs are dealt to the
 // SMs round-robin in launch order, so launching the chains sorted by K gives every SM one chain of every cost tier.
-// Host side of the launch order with feedback: cost[c] = busy cycles of chain c in the previous launch, blk_sm[b] = SM of CTA b in the
-// previous launch -> perm[b] = chain of CTA b.  Model: the chains of an SM share its throughput, which falls only slowly with the number
-// of resident chains (measured: 1 chain alone runs 1.44x faster than one of 7), so an SM finishes at about
-//     T = W_MAX * (its most expensive chain) + W_REST * (the sum of its other chains),   W_MAX = 4.85, W_REST = 0.36
-// (from the measured throughput-per-resident-chains curve, profiles/README.md) -- the launch lasts as long as the SM with the largest T.
-// Greedy on T: chains by decreasing cost, each to the SM with the smallest T that still has a free CTA (the first chain of an SM weighs
-// W_MAX, the others W_REST): the most expensive chains get an SM each, and the cheapest neighbours.  Chains are independent, so the order
-// changes nothing but the timing.
-static void balance_launch_order(int n, const std::vector<float> &cost, const std::vector<int32_t> &blk_sm, std::vector<int32_t> &perm) {
-    const double W_MAX = 4.85, W_REST = 0.36;
-    perm.assign(n, 0);
-    int nsm = 0;
-    for (int b = 0; b < n; b++) nsm = std::max(nsm, blk_sm[b] + 1);
-    std::vector<std::vector<int>> slots(nsm);  // the CTAs of every SM
-    for (int b = 0; b < n; b++) slots[blk_sm[b] < 0 ? 0 : blk_sm[b]].push_back(b);
-    std::vector<int> order(n);
-    for (int c = 0; c < n; c++) order[c] = c;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
-    typedef std::pair<double, int> LS;  // (T, sm): min-heap
-    std::priority_queue<LS, std::vector<LS>, std::greater<LS>> heap;
-    std::vector<char> seeded(nsm, 0);
-    // (seeding the SMs that received fewer CTAs first was measured: no gain -- which SMs get 6 instead of 7 CTAs is not stable)
-    for (int sm = 0; sm < nsm; sm++) if (!slots[sm].empty()) heap.push(LS(0.0, sm));
-    for (int i = 0; i < n; i++) {
-        const LS top = heap.top(); heap.pop();
-        const int sm = top.second, c = order[i];
-        perm[slots[sm].back()] = c; slots[sm].pop_back();
-        const double w = seeded[sm] ? W_REST : W_MAX;
-        seeded[sm] = 1;
-        if (!slots[sm].empty()) heap.push(LS(top.first + w * (double)cost[c], sm));
-    }
-}
-
+// (Measured and rejected, profiles/README.md round 2: a launch order from FEEDBACK -- the previous launch's per-chain busy cycles and
+// CTA -> SM map, balanced on the host -- gains 1.5-2 % when a launch repeats the previous one exactly, and loses 0.5-9 % for the
+// launches of a continuing run, whose cost the previous launch predicts worse than K does.)
 // One CTA: counting sort on K (K <= 127 for the resident sampler), O(n).
 __global__ void __launch_bounds__(1024) tg_order_kernel(int n, const int32_t *__restrict__ K, int32_t *__restrict__ perm) {
     __shared__ int hist[129], base[129];
@@ -300,13 +267,6 @@ struct tonga_chains {
     long long *d_counts = nullptr;
     int32_t *d_pending = nullptr;
     int32_t *d_perm = nullptr;  // resident sampler: launch order
-    float *d_cost = nullptr;    // resident sampler: per-chain busy cycles of the last launch, and
-    int32_t *d_blk_sm = nullptr;  // the SM of every CTA of the last launch (feedback for the next launch's order)
-    std::vector<float> h_cost;
-    std::vector<int32_t> h_blk_sm;
-    bool have_cost = false;
-    bool order_feedback = true;  // TONGA_ORDER_FEEDBACK=0: always the K-sorted order (A/B measurements)
-    std::vector<int32_t> h_perm;
     int32_t *d_n_hist = nullptr;
     long long *d_model_num = nullptr;
     int32_t *d_hist_K = nullptr;
@@ -440,7 +400,6 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     ch->wide = wide;
     ch->host_history = host_history;
     ch->no_order = std::getenv("TONGA_NO_ORDER") != nullptr;
-    if (const char *e = std::getenv("TONGA_ORDER_FEEDBACK")) ch->order_feedback = std::atoi(e) != 0;
     ch->streamed = streamed;
     ch->stream_smem = stream_smem;
     ch->stile_pts = stile_pts;
@@ -528,8 +487,6 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
     TG_ALLOC(ch->d_counts, 8 * n * 15);
     TG_ALLOC(ch->d_pending, 4 * n);
     TG_ALLOC(ch->d_perm, 4 * n);
-    TG_ALLOC(ch->d_cost, 4 * n);
-    TG_ALLOC(ch->d_blk_sm, 4 * n);
     TG_ALLOC(ch->d_n_hist, 4 * n);
     TG_ALLOC(ch->d_model_num, 8 * n);
 #define TG_HIST_ALLOC(ptr, bytes)                                                                                              \
@@ -604,7 +561,7 @@ static void tonga_chains_destroy_unlocked(tonga_chains *ch) {
     cudaStreamSynchronize(ch->ctx->stream);
     void *ptrs[] = {ch->d_K, ch->d_cells, ch->d_phi, ch->d_noise, ch->d_beta, ch->d_tstar, ch->d_owner, ch->d_dcache, ch->d_dcache_tmp, ch->d_counts, ch->d_pending,
                     ch->d_n_hist, ch->d_model_num, ch->d_ptS_tmp, ch->d_phi_tmp, ch->d_owner_tmp, ch->d_mism,
-                    ch->d_maxd, ch->d_swapstat, ch->d_perm, ch->d_cost, ch->d_blk_sm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles, ch->d_tile_changed};
+                    ch->d_maxd, ch->d_swapstat, ch->d_perm, ch->d_Kc, ch->d_cells_c, ch->d_props, ch->d_owner16, ch->d_tstar_c, ch->d_accept, ch->d_cells_cf, ch->d_term_c, ch->d_active, ch->d_stiles, ch->d_tile_changed};
     for (void *p : ptrs) cudaFree(p);
     void *hist[] = {ch->d_hist_K, ch->d_hist_cells, ch->d_hist_phi, ch->d_hist_ptS, ch->d_hist_iter, ch->d_hist_action, ch->d_hist_accept, ch->d_hist_next};
     for (void *p : hist) {
@@ -920,20 +877,10 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             const long long tot = (long long)ch->n * ni;
             tg::tg_pregen_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ch->n, ni, a.iter0, ch->seed, ch->chain_id0, ctx->prm.n_actions, (tg::RawDraw *)(d + o_raw));
         }
-        a.perm = nullptr; a.cost = nullptr; a.blk_sm = nullptr;
+        a.perm = nullptr;
         if (!ch->no_order) {
-            // Launch order.  The launch lasts as long as its slowest SM, every chain stays on the SM its CTA lands on, and both a chain's
-            // cost and the CTA -> SM map repeat from one launch to the next: the previous launch's per-chain busy cycles and per-CTA
-            // SM ids give the next launch's assignment (balance_launch_order: the expensive chains one per SM, with the cheapest neighbours).
-            // First launch of a batch: chains sorted by K (one of every cost tier per SM).
-            if (ch->have_cost && it0 == 0 && !ch->d_prof) tg::balance_launch_order(ch->n, ch->h_cost, ch->h_blk_sm, ch->h_perm);
-            if (ch->have_cost && !ch->d_prof) {
-                if (it0 == 0) TG_CUDA(cudaMemcpyAsync(ch->d_perm, ch->h_perm.data(), 4 * (size_t)ch->n, cudaMemcpyHostToDevice, s));
-            } else {
-                tg::tg_order_kernel<<<1, 1024, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
-            }
+            tg::tg_order_kernel<<<1, 1024, 0, s>>>(ch->n, ch->d_K, ch->d_perm);
             a.perm = ch->d_perm;
-            if (ch->order_feedback) { a.cost = ch->d_cost; a.blk_sm = ch->d_blk_sm; }
         }
         const bool small = ctx->R <= tg::ST * TG_SMALL_CHUNKS;
         if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
@@ -954,12 +901,6 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
     if (tr_K) TG_CUDA(cudaMemcpyAsync(tr_K, d + o_K, 4 * N, cudaMemcpyDeviceToHost, s));
     TG_CUDA(cudaStreamSynchronize(s));
     TG_CUDA(cudaEventElapsedTime(&ch->last_ms, ch->ev0, ch->ev1));
-    if (!ch->wide && !ch->streamed && !ch->no_order && ch->order_feedback && nIter > 0) {  // feedback for the next launch's order (8 bytes per chain)
-        ch->h_cost.resize(ch->n); ch->h_blk_sm.resize(ch->n);
-        TG_CUDA(cudaMemcpy(ch->h_cost.data(), ch->d_cost, 4 * (size_t)ch->n, cudaMemcpyDeviceToHost));
-        TG_CUDA(cudaMemcpy(ch->h_blk_sm.data(), ch->d_blk_sm, 4 * (size_t)ch->n, cudaMemcpyDeviceToHost));
-        ch->have_cost = true;
-    }
     if (ch->streamed && ch->sh_world > 1) {
         int err = 0;
         TG_CUDA(cudaMemcpy(&err, ch->d_xch + 128 * (size_t)ch->sh_world, 4, cudaMemcpyDeviceToHost));

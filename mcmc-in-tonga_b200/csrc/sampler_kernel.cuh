@@ -35,9 +35,7 @@ struct SamplerArgs {
     const int32_t *ray_off, *ray_rank;
     int R, Rp, KC;
     int P, Ppad;
-    const int32_t *perm;  // CTA -> chain: the launch order (tonga_chains_run: balanced over the SMs by measured cost; NULL = identity)
-    float *cost;          // [n] busy cycles of this launch per chain, and
-    int32_t *blk_sm;      // [n] the SM every CTA ran on: feedback for the next launch's order (NULL = not recorded)
+    const int32_t *perm;  // CTA -> chain: chains sorted by expected cost so that every SM hosts the same mix (NULL = identity)
     tonga_params prm;
     // chain state (global)
     int32_t *K;
@@ -110,7 +108,6 @@ struct Hdr {
     uint16_t queue[NW][SQ_CAP];
     uint8_t perm[NW][32];
     unsigned long long bar;
-    long long t0;  // clock64 at the start of the launch (thread 0)
 };
 extern __shared__ __align__(16) unsigned char tg_smem[];
 __device__ __forceinline__ Hdr &hdr() { return *reinterpret_cast<Hdr *>(tg_smem); }
@@ -662,7 +659,6 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         h.ta2 = a.tol_alpha * (1.0f + 0x1.0p-16f) + 0x1.0p-16f + 0x1.0p-20f;
         h.st.phi = a.phi[chain]; h.st.noise = a.noise[chain]; h.st.beta = a.beta[chain];
         h.st.pending_slot = a.pending_slot[chain];
-        h.t0 = clock64();
     }
     __syncthreads();
     if (tid == 0) {
@@ -929,12 +925,6 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         bulk_store(a.tstar + (size_t)chain * a.Rp, s_tstar, (uint32_t)(8 * a.Rp));
         bulk_store(a.cells + (size_t)chain * 4 * KC, s_nx, (uint32_t)(32 * KC));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (a.cost) {  // feedback for the next launch's order: what this chain cost and where this CTA ran
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            a.cost[chain] = (float)(clock64() - h.t0);
-            a.blk_sm[blockIdx.x] = (int32_t)smid;
-        }
         a.K[chain] = K; a.phi[chain] = s_st->phi; a.noise[chain] = s_st->noise;
         a.n_hist[chain] = n_hist; a.model_num[chain] += mn_inc; a.pending_slot[chain] = s_st->pending_slot;
         long long *c = a.counts + (size_t)chain * 15;
