@@ -531,10 +531,12 @@ extern "C" int tonga_chains_create_ex(tonga_ctx *ctx, tonga_chains **out, int32_
         TG_CUDA(cudaStreamSynchronize(s));
     }
     if (!wide) {
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
-        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
+        TG_CUDA(cudaFuncSetAttribute(tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch->smem));
     }
     if (8 * 4 * KC > 48 * 1024) {
         if (8 * 4 * KC > ctx->smem_optin) return tg::fail(TONGA_ERR_CAPACITY, "tonga_chains_create: max_cells too large for shared memory");
@@ -883,12 +885,16 @@ extern "C" int tonga_chains_run(tonga_chains *ch, int64_t nIter, int32_t mode, t
             a.perm = ch->d_perm;
         }
         const bool small = ctx->R <= tg::ST * TG_SMALL_CHUNKS;
+        const bool plain = a.mode == 0 && !a.recs_out && !a.tr_accept && !a.tr_phi && !a.tr_K;  // no replay, records or traces: the lean instantiation
         if (ch->d_prof) {  // instrumented instantiation (tonga_chains_profile)
-            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
-            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, true, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, true, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+        } else if (plain) {
+            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false, true><<<ch->n, tg::ST, ch->smem, s>>>(a);
         } else {
-            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
-            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            if (small) tg::tg_sampler_kernel<TG_SMALL_CHUNKS, false, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
+            else tg::tg_sampler_kernel<TG_RESIDENT_MAX_CHUNKS, false, false><<<ch->n, tg::ST, ch->smem, s>>>(a);
         }
         TG_CUDA(cudaGetLastError());
     }

@@ -461,26 +461,28 @@ static __device__ __noinline__ CRes phase_c_chunk(const uint32_t info) {
         // breaks up: 27.2 against 28.4 M/s); separate code for the last 1..3 passes (phase C 22.0 k -> 18.5 k cycles, but the build
         // falls into the slow regime: 22.5 M/s); the first round's dt of the NEXT group requested while this one is summed (phase C
         // -11 %, the other phases grow by as much).
-        double dn[4];  // dt of the next round: the only global (L2) loads of the loop, requested one round ahead
+        // Rounds of 2 passes, staged (all loads of a stage before the first use); dt -- the only global (L2) loads -- is requested one round
+        // ahead, and only if that round exists.  Rounds of 4 passes overlap more but waste more (Tonga's rays need 2, 3, 5, 9 or 17
+        // passes) and are twice the code: phase C itself is 3 % faster with them, every other phase 3-5 % slower (instruction supply);
+        // a fully rolled loop of single passes is 22 % slower in phase C (profiles/README.md, round 2).
+        double dn[2];
 #pragma unroll
-        for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
+        for (int u = 0; u < 2; u++) dn[u] = __ldg(dtp + 8 * u);
 #pragma unroll 1
-        for (int k0 = 0; k0 < trip; k0 += 4, ow += 32) {
-            // 4 passes per round, staged: all loads of a stage are issued before the first use (the per-pass chain owner byte ->
-            // halved zeta -> term is a sequence of dependent shared-memory round trips; four of them overlap)
-            double d[4], za[4], zb[4];
-            uint32_t oa[4], ob[4];
-            dtp += 32;
+        for (int k0 = 0; k0 < trip; k0 += 2, ow += 16) {
+            double d[2], za[2], zb[2];
+            uint32_t oa[2], ob[2];
+            dtp += 16;
 #pragma unroll
-            for (int u = 0; u < 4; u++) { d[u] = dn[u]; oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
-            if (k0 + 4 < trip) {  // warp-uniform: the next round's dt only if there is a next round (phase C issues 60 % of the kernel's global L1 requests)
+            for (int u = 0; u < 2; u++) { d[u] = dn[u]; oa[u] = ow[8 * u]; ob[u] = ow[8 * u + 1]; }
+            if (k0 + 2 < trip) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) dn[u] = __ldg(dtp + 8 * u);
+                for (int u = 0; u < 2; u++) dn[u] = __ldg(dtp + 8 * u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
+            for (int u = 0; u < 2; u++) { za[u] = s_zh[oa[u]]; zb[u] = s_zh[ob[u]]; }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const double term = __dmul_rn(d[u], div1000_exact(__dadd_rn(za[u], zb[u])));
                 if (8 * (k0 + u) < nl) acc = __dadd_rn(acc, term);
             }
@@ -621,7 +623,9 @@ static __device__ __noinline__ void write_history(double *__restrict__ hc, doubl
 }
 
 // =================================================================================================== the kernel
-template <int NCH, bool PROF>
+// PLAIN: the generate-mode launch without proposal records and per-iteration traces (what a production run uses); the replay / record / trace
+// paths are compiled out of this instantiation (168 instructions less on the once-per-iteration code path: instruction supply).
+template <int NCH, bool PROF, bool PLAIN>
 __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) {
     const SmemLayout L = smem_layout(a.Ppad, a.Rp, a.KC);
     Hdr &h = hdr();
@@ -700,6 +704,11 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
     const bool cold = (a.beta[chain] == 1.0);  // tempered replicas (beta < 1, extension) do not contribute to the posterior
 
     const tonga_params &pm = a.prm;
+    const int a_mode = PLAIN ? 0 : a.mode;
+    tonga_proposal *const a_recs_out = PLAIN ? nullptr : a.recs_out;
+    int8_t *const a_tr_accept = PLAIN ? nullptr : a.tr_accept;
+    double *const a_tr_phi = PLAIN ? nullptr : a.tr_phi;
+    int32_t *const a_tr_K = PLAIN ? nullptr : a.tr_K;
     const double sig_zeta = pm.zeta_scale * pm.sig / 100;  // TD_inversion_function.jl:22
 
     // thinning (:276-279): keep when fmod(model_num, keep_each) == 0.  For an integral keep_each (the reference's 1e1) that is a
@@ -713,8 +722,8 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
         if (PROF && tid == 0) { const long long t = clock64(); pt[ph] += t - tprev; tprev = t; }
     };
     // raw draw of the next iteration: lane l < 8 holds double l of the record (requested one iteration ahead)
-    const double *rawp = (a.mode == 0) ? reinterpret_cast<const double *>(a.raw + (size_t)chain * a.nIter) + (lane & 7) : nullptr;
-    double raw_next = (a.mode == 0 && a.nIter > 0) ? __ldcs(rawp) : 0.0;
+    const double *rawp = (a_mode == 0) ? reinterpret_cast<const double *>(a.raw + (size_t)chain * a.nIter) + (lane & 7) : nullptr;
+    double raw_next = (a_mode == 0 && a.nIter > 0) ? __ldcs(rawp) : 0.0;
     const int nIter = (int)a.nIter;  // a launch covers at most 2^31 iterations (sampler.cu cuts longer runs)
 
 #pragma unroll 1
@@ -727,7 +736,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
             pr.do_eval = 0; pr.accept = 0; pr.idx = 0; pr.action = 0;
             pr.x = pr.y = pr.z = pr.zeta = pr.u = pr.aux = pr.ox = pr.oy = pr.oz = pr.ztag = 0.0;
             double u1 = 0, u2 = 0, u3 = 0, n0 = 0, n1 = 0, n2 = 0, u7 = 0;
-            if (a.mode == 0) {
+            if (a_mode == 0) {
                 const double rv = raw_next;
                 if (it + 1 < nIter) raw_next = __ldcs(rawp + 8 * (it + 1));
                 pr.action = (int)__shfl_sync(FULL, rv, 0);
@@ -738,7 +747,7 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 const tonga_proposal rec = a.recs_in[(size_t)chain * a.trace_stride + a.it0 + it];
                 pr.action = rec.action; pr.idx = rec.idx; pr.x = rec.x; pr.y = rec.y; pr.z = rec.z; pr.zeta = rec.zeta; pr.u = rec.u;
             }
-            assemble_proposal<0>(pr, a.mode, u1, u2, u3, n0, n1, n2, u7, s_nx, s_ny, s_nz, s_zeta, K, s_st->noise, pm, sig_zeta, lane);
+            assemble_proposal<0>(pr, a_mode, u1, u2, u3, n0, n1, n2, u7, s_nx, s_ny, s_nz, s_zeta, K, s_st->noise, pm, sig_zeta, lane);
             act = pr.action; do_eval = pr.do_eval; pidx = pr.idx;
             cxf = (float)pr.x; cyf = (float)pr.y; czf = (float)pr.z;
             if (lane == 0) {  // scalars needed again at the acceptance / commit: parked in shared memory, one copy per warp
@@ -747,10 +756,10 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 s_prop->cx = pr.x; s_prop->cy = pr.y; s_prop->cz = pr.z;
             }
             if (tid == 0) {
-                if (a.mode == 0 && a.recs_out) {
+                if (a_mode == 0 && a_recs_out) {
                     tonga_proposal rec;
                     rec.action = pr.action; rec.idx = pr.idx; rec.x = pr.x; rec.y = pr.y; rec.z = pr.z; rec.zeta = pr.zeta; rec.u = pr.u;
-                    a.recs_out[(size_t)chain * a.trace_stride + a.it0 + it] = rec;
+                    a_recs_out[(size_t)chain * a.trace_stride + a.it0 + it] = rec;
                 }
                 const int ps = s_st->pending_slot;
                 if (ps >= 0) { a.hist_next[(size_t)chain * a.hist_cap + ps] = pr.action; s_st->pending_slot = -1; }
@@ -890,9 +899,9 @@ __global__ void __launch_bounds__(ST, 7) tg_sampler_kernel(const SamplerArgs a) 
                 if (accepted) s_cnt[5 + act - 1] += 1u;
                 if (do_eval) s_cnt[10 + act - 1] += 1u;
             }
-            if (a.tr_accept) a.tr_accept[(size_t)chain * a.trace_stride + a.it0 + it] = (int8_t)accepted;
-            if (a.tr_phi) a.tr_phi[(size_t)chain * a.trace_stride + a.it0 + it] = s_st->phi;
-            if (a.tr_K) a.tr_K[(size_t)chain * a.trace_stride + a.it0 + it] = K;
+            if (a_tr_accept) a_tr_accept[(size_t)chain * a.trace_stride + a.it0 + it] = (int8_t)accepted;
+            if (a_tr_phi) a_tr_phi[(size_t)chain * a.trace_stride + a.it0 + it] = s_st->phi;
+            if (a_tr_K) a_tr_K[(size_t)chain * a.trace_stride + a.it0 + it] = K;
         }
         if (keep && cold) {
             if (n_hist < a.hist_cap) {
